@@ -1,0 +1,88 @@
+// Shared host-side plumbing of libhgr_b200: error reporting, launch accounting, constants.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <atomic>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+
+#include "../../include/hgr_b200.h"
+
+namespace hgr {
+
+constexpr int kNumSMsB200 = 148;
+// Hit@k cut-offs of the eval loop, main.py:120
+__host__ __device__ constexpr int hit_cut(int c) { return c == 0 ? 1 : c == 1 ? 2 : c == 2 ? 5 : c == 3 ? 10 : 20; }
+
+int set_error(int code, const char* fmt, ...);
+void count_launch(int n = 1);
+int num_sms();  // SM count of the current device (cached)
+
+#define HGR_CHECK_ARG(cond, ...)                                   \
+  do {                                                             \
+    if (!(cond)) return ::hgr::set_error(HGR_ERR_BAD_ARG, __VA_ARGS__); \
+  } while (0)
+
+#define HGR_CHECK_CUDA(expr)                                                            \
+  do {                                                                                  \
+    cudaError_t _e = (expr);                                                            \
+    if (_e != cudaSuccess)                                                              \
+      return ::hgr::set_error(HGR_ERR_CUDA, "%s failed: %s (%d) at %s:%d", #expr,       \
+                              cudaGetErrorString(_e), (int)_e, __FILE__, __LINE__);     \
+  } while (0)
+
+#define HGR_CHECK_LAUNCH()                                                              \
+  do {                                                                                  \
+    cudaError_t _e = cudaGetLastError();                                                \
+    if (_e != cudaSuccess)                                                              \
+      return ::hgr::set_error(HGR_ERR_CUDA, "kernel launch failed: %s (%d) at %s:%d",   \
+                              cudaGetErrorString(_e), (int)_e, __FILE__, __LINE__);     \
+    ::hgr::count_launch();                                                              \
+  } while (0)
+
+// Total order used everywhere a top-k list is kept: larger value first; among equal values
+// the smaller tag (bank row / part position) first.  NaNs never enter a list (v > x is false).
+struct Cand {
+  float v;
+  int32_t i;
+};
+
+// ---- entry points implemented in the individual .cu files (called from hgr_abi.cu) ----
+int launch_aggregate_normalize(const void* E, int e_dtype, int64_t n_src, int64_t D,
+                               const int32_t* rowptr, const int32_t* col, const float* w,
+                               const int32_t* row_map, int64_t n_out, void* out, int out_dtype,
+                               float* out_norm, cudaStream_t stream);
+
+// sched == nullptr: all P lists of every row are valid (public hgr_topk_merge); otherwise row
+// tile mt owns sched->parts(mt) lists (the per-CTA partials of the tcgen05 kernel).
+struct Sched;
+int launch_topk_merge(const float* part_val, const int32_t* part_idx, int64_t P, int64_t B, int K,
+                      const Sched* sched, const int32_t* col_id, int32_t id_base, float scale,
+                      const int32_t* targets, float* topk_val, int32_t* topk_idx, int64_t* hits,
+                      cudaStream_t stream);
+
+size_t simt_score_workspace_bytes(int64_t B, int64_t C, int K);
+int launch_score_topk_simt(const __nv_bfloat16* X, const __nv_bfloat16* bank, const int32_t* col_id,
+                           int32_t id_base, const int32_t* targets, int64_t B, int64_t C, int64_t D,
+                           float scale, int K, void* ws, size_t ws_bytes, float* topk_val,
+                           int32_t* topk_idx, int64_t* hits, cudaStream_t stream);
+int launch_logits_simt(const __nv_bfloat16* X, const __nv_bfloat16* bank, int64_t B, int64_t C,
+                       int64_t D, float scale, float* out, int64_t ldo, cudaStream_t stream);
+
+size_t umma_score_workspace_bytes(int64_t B, int64_t C, int K);
+bool umma_supported(int64_t B, int64_t C, int64_t D, int K);
+int launch_score_topk_umma(const __nv_bfloat16* X, const __nv_bfloat16* bank, const int32_t* col_id,
+                           int32_t id_base, const int32_t* targets, int64_t B, int64_t C, int64_t D,
+                           float scale, int K, void* ws, size_t ws_bytes, float* topk_val,
+                           int32_t* topk_idx, int64_t* hits, cudaStream_t stream);
+int launch_logits_umma(const __nv_bfloat16* X, const __nv_bfloat16* bank, int64_t B, int64_t C,
+                       int64_t D, float scale, float* out, int64_t ldo, cudaStream_t stream);
+
+size_t masked_ce_workspace_bytes(int64_t B, int64_t U, int64_t T);
+int launch_masked_ce(const float* logits, int64_t ldl, int64_t B, int64_t U, const int32_t* set_ptr,
+                     const int32_t* set_col, const int32_t* label_pos, const float* weight, int64_t T,
+                     float* loss, float* dlogits, void* ws, size_t ws_bytes, cudaStream_t stream);
+
+}  // namespace hgr

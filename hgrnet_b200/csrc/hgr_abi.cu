@@ -1,0 +1,156 @@
+// extern "C" surface of libhgr_b200.so (declared in include/hgr_b200.h): argument checks,
+// implementation selection and error reporting.  No device memory is allocated here.
+#include <cstdlib>
+#include <cstring>
+
+#include "common.cuh"
+#include "sched.cuh"
+
+namespace hgr {
+
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+int set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+int num_sms() {
+  static int cached = [] {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) {
+      cudaGetLastError();
+      return kNumSMsB200;  // no device visible (build box): size queries assume a B200
+    }
+    return n;
+  }();
+  return cached;
+}
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+static int pick_impl(int impl, int64_t B, int64_t C, int64_t D, int K) {
+  if (impl == HGR_IMPL_AUTO) {
+    const char* e = getenv("HGR_IMPL");
+    if (e && !strcmp(e, "simt")) return HGR_IMPL_SIMT;
+    return umma_supported(B, C, D, K) ? HGR_IMPL_TCGEN05 : HGR_IMPL_SIMT;
+  }
+  return impl;
+}
+
+}  // namespace hgr
+
+using namespace hgr;
+
+extern "C" {
+
+int hgr_version(void) { return HGR_ABI_VERSION; }
+
+const char* hgr_last_error(void) { return g_err; }
+
+int64_t hgr_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int hgr_aggregate_normalize(const void* E, int e_dtype, int64_t n_src, int64_t D, const int32_t* rowptr,
+                            const int32_t* col, const float* w, int64_t n_rows, const int32_t* row_map,
+                            int64_t n_out, void* out, int out_dtype, float* out_norm, void* stream) {
+  HGR_CHECK_ARG(n_src >= 0 && n_rows >= 0 && n_out >= 0, "hgr_aggregate_normalize: negative size");
+  HGR_CHECK_ARG(D > 0 && D % 8 == 0, "hgr_aggregate_normalize: D = %lld must be a positive multiple of 8", (long long)D);
+  if (n_out == 0) return HGR_OK;
+  HGR_CHECK_ARG(E && out, "hgr_aggregate_normalize: null E/out");
+  HGR_CHECK_ARG(aligned16(E) && aligned16(out), "hgr_aggregate_normalize: E/out must be 16-byte aligned");
+  HGR_CHECK_ARG(rowptr == nullptr || col != nullptr, "hgr_aggregate_normalize: rowptr given without col");
+  HGR_CHECK_ARG(rowptr != nullptr || n_rows == n_src, "hgr_aggregate_normalize: identity CSR needs n_rows == n_src");
+  HGR_CHECK_ARG(row_map != nullptr || n_out == n_rows, "hgr_aggregate_normalize: n_out != n_rows without row_map");
+  HGR_CHECK_ARG(n_src < (int64_t(1) << 31) && n_rows < (int64_t(1) << 31), "hgr_aggregate_normalize: > 2^31 rows");
+  return launch_aggregate_normalize(E, e_dtype, n_src, D, rowptr, col, w, row_map, n_out, out, out_dtype, out_norm,
+                                    static_cast<cudaStream_t>(stream));
+}
+
+size_t hgr_score_topk_workspace_bytes(int64_t B, int64_t C, int64_t D, int K) {
+  if (B <= 0 || C <= 0 || K <= 0) return 16;
+  size_t a = simt_score_workspace_bytes(B, C, K);
+  size_t b = umma_supported(B, C, D, K) ? umma_score_workspace_bytes(B, C, K) : 0;
+  return (a > b ? a : b) + 16;
+}
+
+int hgr_score_topk(const void* X, const void* bank, const int32_t* col_id, int32_t id_base, const int32_t* targets,
+                   int64_t B, int64_t C, int64_t D, float scale, int K, void* workspace, size_t workspace_bytes,
+                   float* topk_val, int32_t* topk_idx, int64_t* hits, int impl, void* stream) {
+  HGR_CHECK_ARG(B >= 0 && C >= 0, "hgr_score_topk: negative size");
+  HGR_CHECK_ARG(D > 0 && D % 8 == 0, "hgr_score_topk: D = %lld must be a positive multiple of 8", (long long)D);
+  HGR_CHECK_ARG(K >= 1 && K <= HGR_TOPK_MAX, "hgr_score_topk: K = %d outside [1, %d]", K, HGR_TOPK_MAX);
+  HGR_CHECK_ARG(scale > 0.f, "hgr_score_topk: scale must be > 0 (top-k order is taken on unscaled cosines)");
+  if (B == 0) return HGR_OK;
+  HGR_CHECK_ARG(topk_val && topk_idx, "hgr_score_topk: null output");
+  HGR_CHECK_ARG(C == 0 || (X && bank), "hgr_score_topk: null X/bank");
+  HGR_CHECK_ARG(aligned16(X) && aligned16(bank) && aligned16(workspace), "hgr_score_topk: X/bank/workspace must be 16-byte aligned");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (C == 0) {
+    // empty class set: every list is (-inf, -1); the merge of zero lists writes exactly that
+    return launch_topk_merge(nullptr, nullptr, 0, B, K, nullptr, nullptr, 0, 1.f, nullptr, topk_val, topk_idx, nullptr, s);
+  }
+  const int which = pick_impl(impl, B, C, D, K);
+  if (which == HGR_IMPL_TCGEN05) {
+    if (!umma_supported(B, C, D, K)) return set_error(HGR_ERR_UNSUPPORTED, "hgr_score_topk: shape not supported by the tcgen05 kernel");
+    return launch_score_topk_umma(static_cast<const __nv_bfloat16*>(X), static_cast<const __nv_bfloat16*>(bank), col_id,
+                                  id_base, targets, B, C, D, scale, K, workspace, workspace_bytes, topk_val, topk_idx,
+                                  hits, s);
+  }
+  if (which == HGR_IMPL_SIMT)
+    return launch_score_topk_simt(static_cast<const __nv_bfloat16*>(X), static_cast<const __nv_bfloat16*>(bank), col_id,
+                                  id_base, targets, B, C, D, scale, K, workspace, workspace_bytes, topk_val, topk_idx,
+                                  hits, s);
+  return set_error(HGR_ERR_BAD_ARG, "hgr_score_topk: unknown impl %d", impl);
+}
+
+int hgr_topk_merge(const float* part_val, const int32_t* part_idx, int64_t P, int64_t B, int K, const int32_t* targets,
+                   float* topk_val, int32_t* topk_idx, int64_t* hits, void* stream) {
+  HGR_CHECK_ARG(P >= 0 && B >= 0, "hgr_topk_merge: negative size");
+  HGR_CHECK_ARG(K >= 1 && K <= HGR_TOPK_MAX, "hgr_topk_merge: K = %d outside [1, %d]", K, HGR_TOPK_MAX);
+  if (B == 0) return HGR_OK;
+  HGR_CHECK_ARG(topk_val && topk_idx, "hgr_topk_merge: null output");
+  HGR_CHECK_ARG(P == 0 || (part_val && part_idx), "hgr_topk_merge: null parts");
+  return launch_topk_merge(part_val, part_idx, P, B, K, nullptr, nullptr, 0, 1.f, targets, topk_val, topk_idx, hits,
+                           static_cast<cudaStream_t>(stream));
+}
+
+int hgr_logits_dense(const void* X, const void* bank, int64_t B, int64_t C, int64_t D, float scale, float* out,
+                     int64_t ldo, int impl, void* stream) {
+  HGR_CHECK_ARG(B >= 0 && C >= 0, "hgr_logits_dense: negative size");
+  HGR_CHECK_ARG(D > 0 && D % 8 == 0, "hgr_logits_dense: D = %lld must be a positive multiple of 8", (long long)D);
+  if (B == 0 || C == 0) return HGR_OK;
+  HGR_CHECK_ARG(X && bank && out, "hgr_logits_dense: null pointer");
+  HGR_CHECK_ARG(ldo >= C, "hgr_logits_dense: ldo < C");
+  HGR_CHECK_ARG(aligned16(X) && aligned16(bank), "hgr_logits_dense: X/bank must be 16-byte aligned");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int which = pick_impl(impl, B, C, D, 1);
+  if (which == HGR_IMPL_TCGEN05)
+    return launch_logits_umma(static_cast<const __nv_bfloat16*>(X), static_cast<const __nv_bfloat16*>(bank), B, C, D,
+                              scale, out, ldo, s);
+  if (which == HGR_IMPL_SIMT)
+    return launch_logits_simt(static_cast<const __nv_bfloat16*>(X), static_cast<const __nv_bfloat16*>(bank), B, C, D,
+                              scale, out, ldo, s);
+  return set_error(HGR_ERR_BAD_ARG, "hgr_logits_dense: unknown impl %d", impl);
+}
+
+size_t hgr_masked_ce_workspace_bytes(int64_t B, int64_t U, int64_t T) { return masked_ce_workspace_bytes(B, U, T) + 16; }
+
+int hgr_masked_ce(const float* logits, int64_t ldl, int64_t B, int64_t U, const int32_t* set_ptr, const int32_t* set_col,
+                  const int32_t* label_pos, const float* weight, int64_t T, float* loss, float* dlogits, void* workspace,
+                  size_t workspace_bytes, void* stream) {
+  HGR_CHECK_ARG(B > 0 && U > 0 && T >= 0, "hgr_masked_ce: bad sizes B=%lld U=%lld T=%lld", (long long)B, (long long)U, (long long)T);
+  HGR_CHECK_ARG(ldl >= U, "hgr_masked_ce: ldl < U");
+  if (T == 0) return HGR_OK;
+  HGR_CHECK_ARG(logits && set_ptr && set_col && label_pos && weight && loss, "hgr_masked_ce: null pointer");
+  return launch_masked_ce(logits, ldl, B, U, set_ptr, set_col, label_pos, weight, T, loss, dlogits, workspace,
+                          workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

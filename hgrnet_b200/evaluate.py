@@ -1,0 +1,132 @@
+"""Re-hosted eval loop of the reference (``main.test``, main.py:104-222).
+
+Per batch the reference materialises logits [B,N], gathers the test columns, runs
+``topk(20)``, maps ids, compares with the label and sums Hit@{1,2,5,10,20} (main.py:135-147).
+Here that whole chain is ONE fused call, ``model.score_topk`` (kernel (1) + kernel (2)); the
+hit counters stay on the device until the loop ends, as in the reference.  The hierarchical
+metrics TOR / POR (``hit_ratio`` / ``path_ratio`` / ``point_ratio``, main.py:143,152-191) are the
+first "next" row of SURVEY.md section 8f: they are computed from the dense logits of
+``hgr_logits_dense`` with vectorised device ops (no per-sample python loop, no D2H copies).
+Output format: ``count_acc`` (utils.py:135-146) and the log files of main.py:205-222.
+"""
+from __future__ import annotations
+
+import copy
+from typing import Iterable, Optional
+
+import torch
+
+from . import ops
+from ._cabi import HIT_CUTS
+
+
+def count_acc(hits_dict, num_tot):
+    """utils.py:135-146."""
+    out_str = ""
+    acc_dict = dict()
+    keys = list(hits_dict.keys())
+    for key, value in hits_dict.items():
+        acc = value / num_tot * 100.0
+        acc_dict[key] = acc
+        out_str += "Top@{}(%):{:.2f}".format(key, acc)
+        out_str += ", " if key != keys[-1] else "."
+    return out_str, acc_dict
+
+
+class HierMetrics:
+    """TOR / POR accumulators (main.py:123-127,152-191), vectorised over the batch."""
+
+    def __init__(self, model):
+        self.model = model
+        self.hits_all = torch.zeros((), dtype=torch.float64, device=model.device)
+        self.path_all = torch.zeros((), dtype=torch.float64, device=model.device)
+        self.point_all = torch.zeros((), dtype=torch.float64, device=model.device)
+        self.path_all_count = 0
+        N = len(model.nodes)
+        depth = torch.from_numpy(model.hierarchy.depth).to(model.device)
+        self._depth = depth
+        self._train_index = model.train_index
+        self._depth_train = depth[model.train_index]
+        self._N = N
+
+    def update(self, logits: torch.Tensor, target: int):
+        m = self.model
+        B = logits.shape[0]
+        parents = list(m.c2p[target]) + [target]
+        L = len(parents)
+        par = torch.tensor(parents, device=logits.device)
+        lt = logits[:, self._train_index]                                   # main.py:143
+        top1 = self._train_index[lt.argmax(1)]                              # main.py:155-156
+        self.hits_all += (top1[:, None] == par[None, :]).sum()              # main.py:158-160
+        # per chain level: arg-max over the nodes of that depth (everything else filled with -1), main.py:163-176
+        path = torch.empty((B, L), dtype=torch.long, device=logits.device)
+        for k, p in enumerate(parents):
+            level = len(m.c2p[p])
+            keep = self._depth_train == level                               # same_l = d2n[level] (p is in it)
+            lk = torch.where(keep[None, :], lt, torch.full_like(lt, -1.0))
+            path[:, k] = self._train_index[lk.argmax(1)]
+        match = path == par[None, :]                                        # main.py:179-189
+        point = match.sum()
+        if L - 1 == 0:
+            self.path_all += match[:, 0].sum()
+        else:
+            self.path_all += (match[:, :-1] & match[:, 1:]).sum().double() / (L - 1)
+        self.point_all += point.double() / L
+        self.path_all_count += B
+
+    def ratios(self, num_sample):
+        return (float(self.hits_all) / num_sample * 100.0, float(self.path_all) / self.path_all_count * 100.0,
+                float(self.point_all) / num_sample * 100.0)
+
+
+def test(opts, model, device, splits=None, loader: Optional[Iterable] = None, log: bool = True):
+    """Drop-in for main.py:104-222.  ``loader`` yields the reference's batch dicts
+    ``{'img': [1,B,...], 'label': [1,B]}`` (single-label batches, imagenet_group_test.py)."""
+    print("out", opts.out_ratio)
+    print("in", opts.in_ratio)
+    model.eval()
+    model.update_classifier()
+    if loader is None:
+        raise ValueError("hgrnet_b200.evaluate.test needs a loader: image I/O (dataset/imagenet_group_test.py) is "
+                         "an upstream component; pass loader=DataManager_test(...).get_data_loader()")
+    print("Running.", flush=True)
+    hier = HierMetrics(model) if getattr(opts, "hgr_hier_metrics", True) else None
+    hits = ops.new_hits(model.device)
+    num_sample = 0
+    out_str = ""
+    with torch.no_grad():
+        for i, data in enumerate(loader):
+            imgs, targets = data["img"].to(device, non_blocking=True)[0], data["label"].to(device, non_blocking=True)[0]
+            x = model.encode_image_normalized(imgs)
+            model.score_topk(None, targets, hits=hits, feats_normalized=x)   # main.py:135-147, fused
+            num_sample += len(targets)
+            if hier is not None:
+                logits = ops.logits_dense(x, model.zsl_weights)              # clip_tree.py:331 (for TOR/POR only)
+                hier.update(logits, int(data["label"][0][0]))
+            if i % opts.print_freq == 0:
+                out_str = _format(hits, num_sample, hier)
+                print(out_str, flush=True)
+    print("End of testing.")
+    out_str = _format(hits, num_sample, hier)
+    print(out_str, flush=True)
+    if log:
+        with open(model.save_path + "arugements.log", "a") as f:       # [sic] main.py:217
+            f.writelines(out_str + "\n")
+        with open("{}.txt".format(opts.weights), "a") as f:            # main.py:219-222
+            method = "{},{},{}:".format(opts.weights, opts.out_ratio, opts.in_ratio)
+            f.writelines(method + "\n" + out_str + "\n")
+    return out_str
+
+
+def _format(hits, num_sample, hier):
+    h = hits.tolist()
+    hits_dict = dict(zip(HIT_CUTS, h))
+    out_str = "\n"
+    tmp_str, _ = count_acc(hits_dict, num_sample)
+    out_str += tmp_str
+    if hier is not None:
+        hit_ratio, path_ratio, point_ratio = hier.ratios(num_sample)
+        out_str += " hit_ratio(%):{:.2f}".format(hit_ratio)
+        out_str += " path_ratio(%):{:.2f}".format(path_ratio)
+        out_str += " point_ratio(%):{:.2f}".format(point_ratio)
+    return out_str

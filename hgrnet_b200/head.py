@@ -1,0 +1,286 @@
+"""``tree_model``: drop-in for the reference's hierarchy-aware CLIP wrapper (model/clip_tree.py).
+
+Same constructor arguments, methods and attributes as the reference class as used by its
+``main.py``; the hot path behind them runs in ``libhgr_b200.so``:
+
+* ``update_classifier``  -> kernel (1) ``hgr_aggregate_normalize``   (clip_tree.py:318-325)
+* ``forward``            -> kernel (1) + ``hgr_logits_dense``        (clip_tree.py:328-333)
+* ``score_topk`` (NEW)   -> kernel (1) + kernel (2) ``hgr_score_topk`` fused logits/top-20/Hit@k
+                            (clip_tree.py:330-331 + main.py:136-147), no [B,N] matrix
+* ``train_batch``        -> kernel (1) + ``hgr_logits_dense`` + kernel (3) ``hgr_masked_ce``
+                            (clip_tree.py:222-316), all (k,m) iterations in one launch
+
+The CLIP encoders stay upstream torch modules (``clip_model.encode_image`` / ``encode_text``);
+only their output contract matters.  There is no CPU path: tensors must live on a CUDA device.
+"""
+from __future__ import annotations
+
+import copy
+import os
+import random
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import ops
+from .hierarchy import Hierarchy
+from .levels import layer_weight_init, level_weights
+from .sampling import contra_brothers, contra_random, contra_topk, hierarchical_schedule, om_schedule
+
+TEMPLATE_SIMPLE = "a photo of a {}."  # data/templates.py:98-100 (TEMPLATES_SIMPLE[0], hard-wired at clip_tree.py:52)
+
+
+def _default_node_names(nodes: Sequence[str]) -> List[str]:
+    """Prompt names as in clip_tree.py:53-58 (WordNet lemma of the wnid); falls back to the wnid."""
+    try:
+        from nltk.corpus import wordnet as wn  # optional upstream dependency
+    except Exception:  # pragma: no cover - nltk is not part of this image
+        wn = None
+    names = []
+    for node in nodes:
+        name = node
+        if wn is not None:
+            try:
+                name = wn.synset_from_pos_and_offset("n", int(node[1:])).name().split(".")[0].replace("_", " ")
+            except Exception:
+                name = node
+        names.append(TEMPLATE_SIMPLE.format(name))
+    return names
+
+
+class tree_model(nn.Module):
+    def __init__(self, opts, candidates_train, candidates_test, clip_model: Optional[nn.Module] = None,
+                 hierarchy: Optional[Hierarchy] = None, node_tokens: Optional[torch.Tensor] = None,
+                 tokenizer=None):
+        super().__init__()
+        self.opts = opts
+        self.device = torch.device("cuda:%d" % opts.device) if isinstance(opts.device, int) else torch.device(opts.device)
+        self.save_path = "{}/{}/{}_{}_{}/".format(opts.folder, opts.exp_name, opts.weights, opts.out_ratio, opts.in_ratio)
+        self.file_path = self.save_path + "clip_{}".format(opts.from_epoch)
+        if not os.path.exists(self.save_path):
+            os.makedirs(self.save_path)
+
+        # semantic structure (utils.gen_tree, utils.py:39-72)
+        self.hierarchy = hierarchy if hierarchy is not None else Hierarchy.from_json(opts.graph_path)
+        self.p2c, self.c2p, self.d2n, self.nodes, self.start_up = self.hierarchy.as_tuple()
+        self.nodes_id = list(range(len(self.nodes)))
+
+        # upstream encoders
+        if clip_model is None:
+            try:
+                import clip  # the upstream OpenAI package / the reference's vendored copy on PYTHONPATH
+            except ImportError as e:
+                raise ImportError("pass clip_model=... or put an OpenAI-CLIP compatible `clip` package on "
+                                  "PYTHONPATH: the encoders are upstream producers, not part of hgrnet_b200") from e
+            clip_model, _ = clip.load(name=opts.arch, device=self.device, download_root="pretrained")
+            if tokenizer is None:
+                tokenizer = clip.tokenize
+        self.clip_model = clip_model
+        if getattr(opts, "fetch", False):
+            self.clip_model.load_state_dict(torch.load(opts.fetch_path))
+        if getattr(opts, "load", False):
+            path = self.file_path if opts.load_path == "none" else opts.load_path
+            self.clip_model.load_state_dict(torch.load(path))
+            print("successfully loaded")
+        self.clip_model.eval()
+        for params in self.clip_model.parameters():
+            params.requires_grad_(True)
+
+        # prompts -> tokens (clip_tree.py:52-60)
+        if node_tokens is None:
+            if tokenizer is None:
+                raise ValueError("node_tokens or tokenizer required when clip_model is supplied")
+            with torch.no_grad():
+                node_tokens = tokenizer(_default_node_names(self.nodes))
+        self.node_tokens = node_tokens.to(self.device)
+
+        # misc (clip_tree.py:63-68)
+        self.resolution = getattr(getattr(self.clip_model, "visual", None), "input_resolution", 224)
+        self.candidates_train = candidates_train
+        self.candidates_test = candidates_test
+        index = self.hierarchy.index
+        self.train_index = torch.tensor([index[c] for c in candidates_train], dtype=torch.long, device=self.device)
+        self.test_index = torch.tensor([index[c] for c in candidates_test], dtype=torch.long, device=self.device)
+        self._train_ids_host = [index[c] for c in candidates_train]
+        self._test_index_i32 = self.test_index.to(torch.int32)
+        self.max_depth = max(self.d2n.keys())
+
+        if self.opts.weights == "adaptive":
+            # The reference builds a NON-leaf tensor here (clip_tree.py:74), which
+            # makes its own optimizer2 unusable.  Same values, but a real Parameter named "layer_weight"
+            # so that main.py's filters (`name != "layer_weight"`, SGD([model.layer_weight])) work.
+            self.layer_weight = nn.Parameter(layer_weight_init(self.d2n, self.opts.scale).to(self.device))
+
+        self.zsl_weights: Optional[torch.Tensor] = None   # [N, D] bf16 class bank
+        self.bank_test: Optional[torch.Tensor] = None     # [C, D] bf16 rows of test_index
+        self._rng = random  # Python's global RNG, as the reference (clip_tree.py:82,134,189)
+
+    # ------------------------------------------------------------------ checkpoint
+    def save(self, opts, epoch):
+        """clip_tree.py:76-78."""
+        torch.save(self.clip_model.state_dict(), self.save_path + "clip_{}".format(epoch))
+
+    # ------------------------------------------------------------------ sampling / weights
+    def _contra_ids(self, method, target, depth=None, parents=None):
+        if method == "topk":
+            return contra_topk(self.d2n, target, depth, parents, self.opts.k, self.opts.num_compare, self._rng)
+        if method == "random":
+            return contra_random(self._train_ids_host, target, self.opts.num_compare, self._rng)
+        if method == "brothers":
+            return contra_brothers(self.p2c, self.start_up, target, depth, parents, self.opts.num_compare, self._rng)
+        raise NotImplementedError(
+            "sample_strategy %r: the reference's 'simi'/'near_simi' branches (clip_tree.py:91-114,143-178) mix "
+            "python lists with tensors and cannot run as published; supported: topk, random, brothers" % method)
+
+    def get_contra(self, method, target, batch_size, depth=None, parents=None):
+        """clip_tree.py:80-196 -> ``(compare_idx LongTensor[n], labels LongTensor[B])`` on the device."""
+        ids, pos = self._contra_ids(method, target, depth, parents)
+        compare_idx = torch.tensor(ids, device=self.device)
+        return compare_idx, torch.full((batch_size,), pos, dtype=torch.long, device=self.device)
+
+    def _layer_weight_host(self):
+        lw = getattr(self, "layer_weight", None)
+        return None if lw is None else lw.detach().float().cpu()
+
+    def get_weights(self, method, max_depth=None):
+        """clip_tree.py:198-219 -> fp32 tensor [max_depth] on the device."""
+        lw = getattr(self, "layer_weight", None)
+        w = level_weights(method, max_depth, lw)
+        return w.to(self.device)
+
+    # ------------------------------------------------------------------ class bank
+    def _bank_csr(self):
+        if getattr(self.opts, "hgr_bank", "node") != "chain":
+            return None
+        lw = self._layer_weight_host()
+        rp, col, w = self.hierarchy.chain_csr(self.opts.out_ratio,
+                                              lambda n: level_weights(self.opts.weights, n, lw).numpy())
+        to = lambda a: torch.from_numpy(a).to(self.device)
+        return to(rp), to(col), to(w)
+
+    def update_classifier(self, chunk: int = 4096):
+        """clip_tree.py:318-325.  Text features are encoded in chunks (the reference: two halves) and
+        normalised -- or hierarchy-aggregated and normalised -- by kernel (1) into the bf16 bank."""
+        with torch.no_grad():
+            N = len(self.nodes)
+            feats = []
+            for s in range(0, N, chunk):
+                feats.append(self.clip_model.encode_text(self.node_tokens[s:s + chunk]))
+            text = torch.cat(feats) if len(feats) > 1 else feats[0]
+            csr = self._bank_csr()
+            if csr is None:
+                self.zsl_weights = ops.aggregate_normalize(text)
+                self.bank_test = ops.aggregate_normalize(text, row_map=self._test_index_i32)
+            else:
+                rp, col, w = csr
+                self.zsl_weights = ops.aggregate_normalize(text, rp, col, w)
+                self.bank_test = ops.aggregate_normalize(text, rp, col, w, row_map=self._test_index_i32)
+
+    # ------------------------------------------------------------------ eval
+    def encode_image_normalized(self, inputs):
+        feats = self.clip_model.encode_image(inputs)
+        return ops.normalize_rows(feats.detach())
+
+    def forward(self, inputs, targets=None):
+        """clip_tree.py:328-333: cosine logits [B, N] (fp32) for ALL nodes."""
+        x = self.encode_image_normalized(inputs)
+        return ops.logits_dense(x, self.zsl_weights)
+
+    def score_topk(self, inputs, targets, hits: Optional[torch.Tensor] = None, K: int = 20, feats_normalized=None):
+        """Fused replacement of ``model(imgs)`` + main.py:136-147.
+
+        Returns ``(val [B,K], idx [B,K] node ids)`` and accumulates Hit@{1,2,5,10,20} into ``hits``.
+        """
+        x = feats_normalized if feats_normalized is not None else self.encode_image_normalized(inputs)
+        t = targets.to(torch.int32) if targets is not None else None
+        return ops.score_topk(x, self.bank_test, col_id=self._test_index_i32, targets=t, K=K, hits=hits)
+
+    # ------------------------------------------------------------------ training step
+    def _iterations(self, training_method, sample_strategy, target):
+        """Host-side expansion of the loop nest into T (ids, label position, weight-recipe) records."""
+        its = []
+        if training_method == "OM":
+            for (k_loop, m_loop, p_out, depth, parents_in, n_out, n_in) in om_schedule(
+                    self.c2p, target, self.opts.out_ratio, self.opts.in_ratio):
+                ids, pos = self._contra_ids(sample_strategy, p_out, depth, parents_in)
+                weighting = self.opts.weighting                                  # clip_tree.py:265-273
+                m_in = "equal" if weighting == "out" else self.opts.weights
+                m_out = "equal" if weighting == "in" else self.opts.weights
+                its.append((ids, pos, ((m_in, n_in, m_loop), (m_out, n_out, k_loop))))
+        elif training_method == "hierarchical":
+            for (j, t_in, depth, parents, n_lvl) in hierarchical_schedule(self.c2p, target):
+                ids, pos = self._contra_ids(sample_strategy, t_in, depth, parents)
+                its.append((ids, pos, ((self.opts.weights, n_lvl, j),)))         # clip_tree.py:304-305
+        else:
+            raise NotImplementedError("training_method %r (the reference implements OM and hierarchical)" % training_method)
+        return its
+
+    @staticmethod
+    def _iteration_weight(recipe, lw):
+        w = None
+        for (method, n, pos) in recipe:
+            f = level_weights(method, n, lw)[pos]
+            w = f if w is None else w * f
+        return w
+
+    def train_batch(self, inputs, targets, training_method, sample_strategy):
+        """clip_tree.py:222-316.  Returns the python-float loss sum; gradients are accumulated on the
+        encoder parameters, ``logit_scale`` and ``layer_weight`` as a side effect (no zero_grad, as the
+        reference)."""
+        img_feats = self.clip_model.encode_image(inputs)
+        x, x_norm = ops.normalize_rows(img_feats.detach(), return_norm=True)          # :225
+        target = int(targets[0].item())                                                # :228 (single-label batch)
+        B = x.shape[0]
+
+        its = self._iterations(training_method, sample_strategy, target)
+        T = len(its)
+        union = sorted(set(i for ids, _, _ in its for i in ids))
+        pos_of = {nid: u for u, nid in enumerate(union)}
+        set_ptr = np.zeros(T + 1, dtype=np.int32)
+        set_col = []
+        for t, (ids, _, _) in enumerate(its):
+            set_col.extend(pos_of[i] for i in ids)
+            set_ptr[t + 1] = len(set_col)
+        lw_host = self._layer_weight_host()
+        weight_host = torch.stack([self._iteration_weight(r, lw_host) for _, _, r in its]).float()
+        meta = torch.from_numpy(np.concatenate([set_ptr, np.asarray(set_col, np.int32),
+                                                np.asarray([p for _, p, _ in its], np.int32)])).to(self.device)
+        d_set_ptr, d_set_col, d_label = meta[:T + 1], meta[T + 1:T + 1 + len(set_col)], meta[T + 1 + len(set_col):]
+        d_weight = weight_host.to(self.device)
+        union_t = torch.tensor(union, device=self.device)
+
+        # one encoder call for the union instead of T calls (:261); rows are independent in eval mode
+        text_raw = self.clip_model.encode_text(self.node_tokens[union_t])
+        tn, t_norm = ops.normalize_rows(text_raw.detach(), return_norm=True)          # :262
+        scale = float(self.clip_model.logit_scale.detach().exp().item())
+        logits = ops.logits_dense(x, tn, scale=scale)                                  # :263
+        loss_t, dlogits = ops.masked_ce(logits, d_set_ptr, d_set_col, d_label, d_weight)   # :275-276
+
+        # backward of logits = scale * x @ tn^T, then of the two row normalisations
+        xf, tnf = x.float(), tn.float()
+        d_x = (dlogits @ tnf) * scale
+        d_tn = (dlogits.t() @ xf) * scale
+        d_log_scale = (dlogits * logits).sum()
+        d_img_raw = (d_x - xf * (xf * d_x).sum(-1, keepdim=True)) / x_norm[:, None]
+        d_text_raw = (d_tn - tnf * (tnf * d_tn).sum(-1, keepdim=True)) / t_norm[:, None]
+        ls = self.clip_model.logit_scale
+        if ls.requires_grad:
+            g = d_log_scale.to(ls.dtype).reshape(ls.shape)
+            ls.grad = g if ls.grad is None else ls.grad + g
+        if text_raw.requires_grad:
+            text_raw.backward(d_text_raw.to(text_raw.dtype))
+        if img_feats.requires_grad:
+            img_feats.backward(d_img_raw.to(img_feats.dtype))                         # :280
+
+        loss_host = loss_t.cpu()                                                        # the step's only result read-back
+        lw_param = getattr(self, "layer_weight", None)
+        if lw_param is not None and lw_param.requires_grad and self.opts.weights == "adaptive":
+            lw_leaf = lw_host.clone().requires_grad_(True)
+            w_again = torch.stack([self._iteration_weight(r, lw_leaf) for _, _, r in its])
+            ((loss_host / weight_host).detach() * w_again).sum().backward()            # d loss_t / d w_t = CE_t
+            g = lw_leaf.grad.to(lw_param.device, lw_param.dtype)
+            lw_param.grad = g if lw_param.grad is None else lw_param.grad + g
+        self.last_losses = loss_host.tolist()
+        return sum(self.last_losses)                                                    # :279

@@ -1,0 +1,174 @@
+"""torch-tensor front end of the C ABI (``include/hgr_b200.h``).
+
+PyTorch is plumbing here: it owns device memory and the current stream; every function
+below validates tensors, hands raw device pointers to ``libhgr_b200.so`` and returns the
+output tensors.  Nothing computes in torch and nothing falls back to the CPU.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import _cabi
+from ._cabi import HGR_IMPL_AUTO, HGR_IMPL_SIMT, HGR_IMPL_TCGEN05, HGR_NUM_HITS  # noqa: F401
+
+_DTYPE_CODE = {torch.float32: _cabi.HGR_F32, torch.bfloat16: _cabi.HGR_BF16, torch.float16: _cabi.HGR_F16}
+_workspaces = {}
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _require(t: torch.Tensor, name: str, dtype=None) -> torch.Tensor:
+    if not t.is_cuda:
+        raise ValueError("%s must be a CUDA tensor: hgrnet_b200 has no CPU path" % name)
+    if dtype is not None and t.dtype != dtype:
+        raise TypeError("%s must be %s, got %s" % (name, dtype, t.dtype))
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _workspace(nbytes: int, device) -> torch.Tensor:
+    key = (device.type, device.index, torch.cuda.current_stream().cuda_stream)
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+def new_hits(device) -> torch.Tensor:
+    """Device-resident Hit@{1,2,5,10,20} counters (the reference keeps them on device too, main.py:121,146)."""
+    return torch.zeros(HGR_NUM_HITS, dtype=torch.int64, device=device)
+
+
+def aggregate_normalize(E: torch.Tensor, rowptr: Optional[torch.Tensor] = None,
+                        col: Optional[torch.Tensor] = None, w: Optional[torch.Tensor] = None,
+                        row_map: Optional[torch.Tensor] = None, out_dtype=torch.bfloat16,
+                        return_norm: bool = False):
+    """``out[r] = normalize(sum_j w[j] * E[col[j]])`` over CSR row ``row_map[r]`` (identity CSR if ``rowptr is None``).
+
+    model/clip_tree.py:323 / :330 and, with ``row_map = test_index``, the gather of main.py:136.
+    """
+    lib = _cabi.load()
+    E = _require(E, "E")
+    if E.dtype not in _DTYPE_CODE:
+        raise TypeError("E dtype %s not supported" % E.dtype)
+    n_src, D = E.shape
+    if rowptr is not None:
+        rowptr = _require(rowptr, "rowptr", torch.int32)
+        col = _require(col, "col", torch.int32)
+        n_rows = rowptr.numel() - 1
+        if w is not None:
+            w = _require(w, "w", torch.float32)
+    else:
+        n_rows = n_src
+    if row_map is not None:
+        row_map = _require(row_map, "row_map", torch.int32)
+        n_out = row_map.numel()
+    else:
+        n_out = n_rows
+    out = torch.empty((n_out, D), dtype=out_dtype, device=E.device)
+    norm = torch.empty((n_out,), dtype=torch.float32, device=E.device) if return_norm else None
+    _cabi.check(lib.hgr_aggregate_normalize(_ptr(E), _DTYPE_CODE[E.dtype], n_src, D, _ptr(rowptr), _ptr(col),
+                                            _ptr(w), n_rows, _ptr(row_map), n_out, _ptr(out),
+                                            _DTYPE_CODE[out_dtype], _ptr(norm), _stream()))
+    return (out, norm) if return_norm else out
+
+
+def normalize_rows(x: torch.Tensor, out_dtype=torch.bfloat16, return_norm: bool = False):
+    """Row L2-normalise (``x / x.norm(dim=-1, keepdim=True)``, model/clip_tree.py:330)."""
+    return aggregate_normalize(x, out_dtype=out_dtype, return_norm=return_norm)
+
+
+def score_topk(X: torch.Tensor, bank: torch.Tensor, *, col_id: Optional[torch.Tensor] = None, id_base: int = 0,
+               targets: Optional[torch.Tensor] = None, K: int = 20, scale: float = 1.0,
+               hits: Optional[torch.Tensor] = None, impl: int = HGR_IMPL_AUTO) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Fused logits + per-row sorted top-K (+ Hit@k accumulation into ``hits``).
+
+    model/clip_tree.py:331 + main.py:136-147.  Returns ``(val [B,K] fp32, idx [B,K] int32 node ids)``.
+    """
+    lib = _cabi.load()
+    X = _require(X, "X", torch.bfloat16)
+    bank = _require(bank, "bank", torch.bfloat16)
+    B, D = X.shape
+    C, D2 = bank.shape
+    if D != D2:
+        raise ValueError("X and bank disagree on D: %d vs %d" % (D, D2))
+    if col_id is not None:
+        col_id = _require(col_id, "col_id", torch.int32)
+        if col_id.numel() != C:
+            raise ValueError("col_id must have one entry per bank row")
+    if targets is not None:
+        targets = _require(targets, "targets", torch.int32)
+        if targets.numel() != B:
+            raise ValueError("targets must have one entry per image row")
+    if hits is not None:
+        hits = _require(hits, "hits", torch.int64)
+    val = torch.empty((B, K), dtype=torch.float32, device=X.device)
+    idx = torch.empty((B, K), dtype=torch.int32, device=X.device)
+    nbytes = lib.hgr_score_topk_workspace_bytes(B, C, D, K)
+    ws = _workspace(nbytes, X.device)
+    _cabi.check(lib.hgr_score_topk(_ptr(X), _ptr(bank), _ptr(col_id), id_base, _ptr(targets), B, C, D,
+                                   float(scale), K, _ptr(ws), ws.numel(), _ptr(val), _ptr(idx), _ptr(hits),
+                                   impl, _stream()))
+    return val, idx
+
+
+def topk_merge(part_val: torch.Tensor, part_idx: torch.Tensor, *, targets: Optional[torch.Tensor] = None,
+               hits: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Merge ``[P, B, K]`` partial lists (node ids) into the final ``[B, K]`` top-K + hits."""
+    lib = _cabi.load()
+    part_val = _require(part_val, "part_val", torch.float32)
+    part_idx = _require(part_idx, "part_idx", torch.int32)
+    P, B, K = part_val.shape
+    if targets is not None:
+        targets = _require(targets, "targets", torch.int32)
+    if hits is not None:
+        hits = _require(hits, "hits", torch.int64)
+    val = torch.empty((B, K), dtype=torch.float32, device=part_val.device)
+    idx = torch.empty((B, K), dtype=torch.int32, device=part_val.device)
+    _cabi.check(lib.hgr_topk_merge(_ptr(part_val), _ptr(part_idx), P, B, K, _ptr(targets), _ptr(val), _ptr(idx),
+                                   _ptr(hits), _stream()))
+    return val, idx
+
+
+def logits_dense(X: torch.Tensor, bank: torch.Tensor, scale: float = 1.0, impl: int = HGR_IMPL_AUTO,
+                 out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``scale * X @ bank.T`` in fp32 (model/clip_tree.py:331 / :263) on the tcgen05 main loop."""
+    lib = _cabi.load()
+    X = _require(X, "X", torch.bfloat16)
+    bank = _require(bank, "bank", torch.bfloat16)
+    B, D = X.shape
+    C = bank.shape[0]
+    if out is None:
+        out = torch.empty((B, C), dtype=torch.float32, device=X.device)
+    _cabi.check(lib.hgr_logits_dense(_ptr(X), _ptr(bank), B, C, D, float(scale), _ptr(out), out.stride(0), impl,
+                                     _stream()))
+    return out
+
+
+def masked_ce(logits: torch.Tensor, set_ptr: torch.Tensor, set_col: torch.Tensor, label_pos: torch.Tensor,
+              weight: torch.Tensor, need_grad: bool = True):
+    """Fused masked CE over T class sets (model/clip_tree.py:241-277).  Returns ``(loss [T], dlogits [B,U] | None)``."""
+    lib = _cabi.load()
+    logits = _require(logits, "logits", torch.float32)
+    set_ptr = _require(set_ptr, "set_ptr", torch.int32)
+    set_col = _require(set_col, "set_col", torch.int32)
+    label_pos = _require(label_pos, "label_pos", torch.int32)
+    weight = _require(weight, "weight", torch.float32)
+    B, U = logits.shape
+    T = label_pos.numel()
+    loss = torch.empty((T,), dtype=torch.float32, device=logits.device)
+    dl = torch.empty_like(logits) if need_grad else None
+    nbytes = lib.hgr_masked_ce_workspace_bytes(B, U, T)
+    ws = _workspace(nbytes, logits.device)
+    _cabi.check(lib.hgr_masked_ce(_ptr(logits), logits.stride(0), B, U, _ptr(set_ptr), _ptr(set_col),
+                                  _ptr(label_pos), _ptr(weight), T, _ptr(loss), _ptr(dl), _ptr(ws), ws.numel(),
+                                  _stream()))
+    return loss, dl

@@ -1,0 +1,150 @@
+/*
+ * hgr_b200.h -- C ABI of libhgr_b200.so: the B200 (sm_100a) scoring head of HGR-Net.
+ *
+ * The reference (WilliamYi96/HGR-Net) is pure Python/PyTorch and has no FFI; the seam this
+ * library sits behind is the `tree_model` nn.Module API used by the reference's main.py
+ * (SURVEY.md section 8b).  Each entry point below names the reference code it replaces
+ * (paths relative to the reference checkout).  INTEGRATION.md shows the ctypes binding.
+ *
+ * Conventions
+ *  - plain pointers and sizes; every pointer is a DEVICE pointer unless stated otherwise;
+ *  - the caller owns all memory; the library never allocates device memory and keeps no
+ *    state between calls (TMA descriptors are rebuilt per call on the host);
+ *  - work is enqueued on `stream` (a cudaStream_t passed as void*); calls are asynchronous;
+ *  - every function returns 0 (HGR_OK) or a negative HGR_ERR_* code; hgr_last_error()
+ *    returns a thread-local message for the last failure;
+ *  - matrices are row-major and dense (leading dimension == number of columns) unless a
+ *    leading dimension is passed explicitly;
+ *  - no CPU fallback exists: without a CUDA device every compute entry returns HGR_ERR_CUDA.
+ */
+#ifndef HGR_B200_H
+#define HGR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HGR_ABI_VERSION 1
+
+#define HGR_OK 0
+#define HGR_ERR_BAD_ARG (-1)      /* null pointer, negative size, misaligned pointer        */
+#define HGR_ERR_UNSUPPORTED (-2)  /* shape / dtype / K outside what the kernels implement   */
+#define HGR_ERR_CUDA (-3)         /* CUDA runtime / driver error, message has the code      */
+#define HGR_ERR_WORKSPACE (-4)    /* workspace smaller than hgr_*_workspace_bytes()         */
+
+/* element types of feature matrices */
+#define HGR_F32 0
+#define HGR_BF16 1
+#define HGR_F16 2
+
+/* Hit@k cut-offs of the reference's eval loop (main.py:120) */
+#define HGR_NUM_HITS 5
+#define HGR_TOPK_MAX 32 /* K <= 32; the reference uses maxk = 20 (main.py:137)              */
+
+/* implementation selector of hgr_score_topk (all compute the same result) */
+#define HGR_IMPL_AUTO 0
+#define HGR_IMPL_SIMT 1     /* CUDA-core kernel: any shape, exactness fallback and debug aid */
+#define HGR_IMPL_TCGEN05 2  /* TMA + tcgen05/TMEM kernel with fused top-k epilogue           */
+
+int hgr_version(void);
+const char* hgr_last_error(void);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+int64_t hgr_launch_count(void);
+
+/*
+ * Class-bank builder: out[r] = normalize( sum_{j in row(r)} w[j] * E[col[j]] ), fp32 math.
+ *
+ * Replaces `text_feats / text_feats.norm(dim=-1, keepdim=True)` of update_classifier
+ * (model/clip_tree.py:318-325), the image-feature normalisation of forward
+ * (model/clip_tree.py:330) and of train_batch (:225,:262), and -- with row_map -- the
+ * `logits[:, test_index]` column gather of main.py:136 (gather bank rows once instead of
+ * logit columns per batch).  The multi-node CSR form is the hierarchy aggregation named by
+ * north_star; its operator shape follows baseline/DGP/models/gcn_dense_att.py:31-46,:116.
+ *
+ *  E        [n_src, D] of e_dtype (HGR_F32 | HGR_BF16 | HGR_F16), D % 8 == 0
+ *  rowptr   [n_rows+1] int32 CSR offsets, or NULL for the identity CSR (row i = {i}, w = 1)
+ *  col, w   [nnz] int32 / fp32; w may be NULL (all ones)
+ *  row_map  [n_out] int32: output row r is CSR row row_map[r]; NULL -> r
+ *  out      [n_out, D] of out_dtype (HGR_BF16 | HGR_F32)
+ *  out_norm [n_out] fp32 pre-normalisation L2 norms, or NULL
+ * A zero-norm row yields NaNs exactly like the reference's division.
+ */
+int hgr_aggregate_normalize(const void* E, int e_dtype, int64_t n_src, int64_t D,
+                            const int32_t* rowptr, const int32_t* col, const float* w,
+                            int64_t n_rows, const int32_t* row_map, int64_t n_out,
+                            void* out, int out_dtype, float* out_norm, void* stream);
+
+/*
+ * Fused eval head: logits = scale * X @ bank^T are produced tile by tile on the tensor
+ * cores and reduced on the fly to the per-row sorted top-K and the Hit@{1,2,5,10,20}
+ * counters; the B x C logit matrix is never written to memory.
+ *
+ * Replaces `feats @ self.zsl_weights.T` (model/clip_tree.py:331) + `logits[:, test_index]`,
+ * `.topk(maxk, 1, True, True)`, `model.test_index[pred]`, `pred.eq(targets)` and the
+ * per-k `correct[:k].sum()` of main.py:136-147.
+ *
+ *  X         [B, D] bf16, already row-normalised (hgr_aggregate_normalize)
+ *  bank      [C, D] bf16 class bank (rows of the test classes), 16-byte aligned, D % 8 == 0
+ *  col_id    [C] int32 node id of bank row c (== test_index), or NULL -> id_base + c
+ *  targets   [B] int32 node id of the label of each image, or NULL (no hit counting)
+ *  topk_val  [B, K] fp32 logits, sorted descending; ties broken by ascending bank row
+ *  topk_idx  [B, K] int32 node ids (col_id applied)
+ *  hits      [HGR_NUM_HITS] int64, INCREMENTED by the number of rows whose label is within
+ *            the top-{1,2,5,10,20}; NULL to skip.  (k beyond K counts within K.)
+ *  workspace at least hgr_score_topk_workspace_bytes(B, C, D, K) bytes, 16-byte aligned
+ * If C < K the missing entries are (-inf, -1).
+ */
+size_t hgr_score_topk_workspace_bytes(int64_t B, int64_t C, int64_t D, int K);
+int hgr_score_topk(const void* X, const void* bank, const int32_t* col_id, int32_t id_base,
+                   const int32_t* targets, int64_t B, int64_t C, int64_t D, float scale, int K,
+                   void* workspace, size_t workspace_bytes, float* topk_val, int32_t* topk_idx,
+                   int64_t* hits, int impl, void* stream);
+
+/*
+ * Merge P partial top-K lists per row into the final sorted top-K and the hit counters.
+ * Used for the class-sharded multi-GPU head (one list per rank after the NCCL all-gather)
+ * and internally for the per-CTA partial lists of hgr_score_topk.
+ *
+ *  part_val / part_idx  [P, B, K] fp32 / int32 (idx already global node ids; -1 = empty)
+ *  outputs as hgr_score_topk.  Order: value descending, then part index, then position.
+ */
+int hgr_topk_merge(const float* part_val, const int32_t* part_idx, int64_t P, int64_t B, int K,
+                   const int32_t* targets, float* topk_val, int32_t* topk_idx, int64_t* hits,
+                   void* stream);
+
+/*
+ * Dense logits, out[b, c] = scale * <X[b], bank[c]>, fp32, leading dimension ldo >= C.
+ * Same TMA/tcgen05 main loop as hgr_score_topk with a plain store epilogue.  Keeps
+ * tree_model.forward()'s contract (model/clip_tree.py:328-333: returns [B, N] logits) for
+ * callers that need the matrix (TOR/POR, main.py:143,162-176) and the training-step logits
+ * `(img_feats_ @ text_feats.t()) * logit_scale.exp()` (model/clip_tree.py:263).
+ */
+int hgr_logits_dense(const void* X, const void* bank, int64_t B, int64_t C, int64_t D,
+                     float scale, float* out, int64_t ldo, int impl, void* stream);
+
+/*
+ * Fused masked cross-entropy of the OM training step over T sampled class sets
+ * (model/clip_tree.py:241-277 with nn.CrossEntropyLoss, :49,:275).
+ *
+ *  logits   [B, U] fp32 (ld = ldl): scale * img_n @ text_n(union)^T, scale already applied
+ *  set_ptr  [T+1] int32 offsets into set_col; set_col [set_ptr[T]] int32 columns (< U) of
+ *           iteration t's sampled classes (`compare_idx`, :257); label_pos [T] int32 position
+ *           of the positive inside its set (:139); weight [T] fp32 = w_in[m] * w_out[k] (:275)
+ *  loss     [T] fp32: weight[t] * mean_b( logsumexp_j - logit_label )   (overwritten)
+ *  dlogits  [B, U] fp32 (ld = ldl): sum_t weight[t]/B * (softmax_t - onehot_t), zero outside
+ *           every set (overwritten); NULL to skip the backward.
+ *  workspace at least hgr_masked_ce_workspace_bytes(B, U, T) bytes.
+ */
+size_t hgr_masked_ce_workspace_bytes(int64_t B, int64_t U, int64_t T);
+int hgr_masked_ce(const float* logits, int64_t ldl, int64_t B, int64_t U,
+                  const int32_t* set_ptr, const int32_t* set_col, const int32_t* label_pos,
+                  const float* weight, int64_t T, float* loss, float* dlogits,
+                  void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HGR_B200_H */
