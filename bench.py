@@ -1,0 +1,334 @@
+#!/usr/bin/env python
+"""Benchmark of the HGR-Net scoring head on B200 -- the driver contract.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg4|cfg5]
+
+Metric (BASELINE.json): scored images/s at 21,841 classes.  A STEP is one pass of the hot path
+over one batch of synthetic image features: row-normalise the batch (kernel 1), fused
+logits + top-20 + Hit@k against the class bank (kernel 2 + merge).  N=1 runs BASELINE cfg 2
+(B=512, C=21,841, D=1024); N>1 runs the class-sharded sweep of cfg 5 (B=4096, bank row-sharded
+over the ranks, one all-gather per batch) -- ``config.workload`` names which.
+
+``value``   device-timed throughput with inputs resident in HBM (CUDA events, max over ranks).
+``e2e``     the same metric through the public API (``tree_model.score_topk``) with pinned HOST
+            feature batches: H2D copy in, hit counters read back D2H, every step, inside the
+            timed region.
+``roofline`` the dominant kernel (tcgen05 GEMM + fused top-k) timed alone, FLOPs = 2*B*C*D.
+``cpu_baseline`` / ``--impl reference``: the reference's own torch ops for this path
+            (oracle port, fp32) on the box's host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    "cfg2": dict(B=512, C=21841, D=1024, name="ImageNet-21K zero-shot head: 21,841 classes, 12-level synthetic hierarchy, RN50 dim 1024, batch 512"),
+    "cfg4": dict(B=1024, C=10450, D=512, name="ImageNet-21K-P split: 10,450 classes, ViT-B/32 dim 512, batch 1024"),
+    "cfg5": dict(B=4096, C=21841, D=1024, name="class-sharded sweep: 21,841 classes x batch 4096, dim 1024"),
+}
+K = 20
+METRIC = "scored images/sec @21,841 classes"
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return d.get("bf16_tflops", 1590.0), d.get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json, burst)"
+    return 1590.0, 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """Samples SM clocks / throttle reasons with nvidia-smi while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.rows = []
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for n, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------ CPU reference arm
+def _cpu_steps(wl, steps, warmup, seed=0):
+    """The reference's torch ops for this path on the host: row-normalise + `feats @ bank.T`
+    (model/clip_tree.py:330-331), column select + topk(20) + id map + eq + per-k sums (main.py:136-147)."""
+    import torch
+    from oracle import hgr_oracle as orc
+    from hgrnet_b200.synthetic import synthetic_embeddings
+    B, C, D = wl["B"], wl["C"], wl["D"]
+    bank = orc.normalize_rows(synthetic_embeddings(C, D, seed + 1))
+    test_index = torch.arange(C)
+    feats = [synthetic_embeddings(B, D, seed + 10 + i, normalize=False) for i in range(2)]
+    targets = torch.randint(0, C, (1,)).expand(B).contiguous()
+    hits_tot = {k: 0 for k in orc.TOPK}
+
+    def one(i):
+        logits = orc.forward_logits(feats[i % 2], bank)
+        _, _, h = orc.eval_hits(logits, test_index, targets)
+        for k in h:
+            hits_tot[k] += h[k]
+
+    for i in range(warmup):
+        one(i)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        one(i)
+    dt = time.perf_counter() - t0
+    return dt / steps, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    wl = WORKLOADS[args.workload or ("cfg2" if args.gpus == 1 else "cfg5")]
+    steps = max(1, args.steps)
+    sec, cores = _cpu_steps(wl, steps, max(1, args.warmup))
+    value = wl["B"] / sec
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": args.gpus,
+            "steps": steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+            "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl["name"], "B": wl["B"], "C": wl["C"], "D": wl["D"], "K": K},
+            "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": "port",
+                             "sample": "%d batches of %d images (one batch per step), torch CPU fp32" % (steps, wl["B"])},
+            "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------ our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from hgrnet_b200 import _cabi, ops
+    from hgrnet_b200.dist import ShardedScorer, shard_bounds
+    from hgrnet_b200.head import tree_model
+    from hgrnet_b200.flags import parse_args
+    from hgrnet_b200.hierarchy import scaled_levels, synthetic_hierarchy
+    from hgrnet_b200.synthetic import TableEncoder, node_id_tokens, synthetic_embeddings
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if args.gpus > 1 and world == 1:
+            raise SystemExit("bench.py --gpus %d must be launched with torch.distributed.run (one rank per GPU)" % args.gpus)
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    wl_key = args.workload or ("cfg2" if world == 1 else "cfg5")
+    wl = WORKLOADS[wl_key]
+    B, C, D = wl["B"], wl["C"], wl["D"]
+    steps, warmup = args.steps, max(3, args.warmup)
+    tf_peak, hbm_peak, peak_src = _peaks()
+
+    # ---- synthetic hierarchy + class bank through the public module surface (kernel 1)
+    hier = synthetic_hierarchy(scaled_levels(C), seed=1)
+    table = synthetic_embeddings(C, D, 1, normalize=False)
+    opts = parse_args([])
+    opts.device, opts.folder, opts.weights = local_rank, "/tmp/hgr_bench_out_%d" % rank, "equal"
+    model = tree_model(opts, hier.nodes, hier.nodes, clip_model=TableEncoder(table).to(dev), hierarchy=hier,
+                       node_tokens=node_id_tokens(C))
+    model.eval()
+    model.update_classifier()
+    torch.cuda.synchronize()
+
+    # inputs larger than L2 (126 MB): rotate over several bank copies and feature batches
+    n_bank = max(2, -(-int(1.6 * 126e6) // (C * D * 2))) if world == 1 else 2
+    lo, hi = shard_bounds(C, world)[rank]
+    shard = model.bank_test[lo:hi]
+    banks = [shard.clone() for _ in range(n_bank)]
+    n_feat = 8
+    feats_host = [synthetic_embeddings(B, D, 100 + i, normalize=False).pin_memory() for i in range(n_feat)]
+    feats_dev = [f.to(dev) for f in feats_host]
+    g = torch.Generator().manual_seed(7)
+    labels_host = [torch.full((B,), int(torch.randint(0, C, (1,), generator=g)), dtype=torch.long).pin_memory()
+                   for _ in range(n_feat)]
+    labels_dev = [l.to(dev).to(torch.int32) for l in labels_host]
+    hits = ops.new_hits(dev)
+    scorers = [ShardedScorer(b, None, id_base=lo, K=K) for b in banks] if world > 1 else None
+
+    def step_resident(i):
+        x = ops.normalize_rows(feats_dev[i % n_feat])
+        if world == 1:
+            ops.score_topk(x, banks[i % n_bank], targets=labels_dev[i % n_feat], K=K, hits=hits)
+        else:
+            sc = scorers[i % n_bank]
+            sc.submit(x, labels_dev[i % n_feat])
+            pending.append(sc)
+            if len(pending) > 1:           # merge batch i-1 while batch i's GEMM / gather are in flight
+                pending.pop(0).collect(hits)
+
+    def drain():
+        while pending:
+            pending.pop(0).collect(hits)
+
+    pending = []
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, n, flush=None):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(n):
+            fn(i)
+        if flush:
+            flush()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        return ms
+
+    # ---- device-resident throughput
+    for i in range(warmup):
+        step_resident(i)
+    drain()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = _cabi.launch_count()
+    ms = timed(step_resident, steps, drain)
+    launches = _cabi.launch_count() - l0
+    ms_per_step = ms / steps
+    value = B / (ms_per_step * 1e-3)
+
+    # ---- dominant kernel alone (GEMM + fused top-k, no merge): the roofline figure
+    Cs = hi - lo
+    nomerge = ops.HGR_IMPL_TCGEN05 | _cabi.HGR_IMPL_FLAG_NO_MERGE
+    xs = [ops.normalize_rows(f) for f in feats_dev]
+
+    def kern_only(i):
+        ops.score_topk(xs[i % n_feat], banks[i % n_bank], K=K, impl=nomerge)
+
+    for i in range(warmup):
+        kern_only(i)
+    kms = timed(kern_only, steps) / steps
+    clocks = sampler.stop() if rank == 0 else None
+    flops = 2.0 * B * Cs * D
+    achieved = flops / (kms * 1e-3) / 1e12
+
+    # ---- end to end through the public API with host buffers
+    def step_e2e(i):
+        f = feats_host[i % n_feat].to(dev, non_blocking=True)
+        t = labels_host[i % n_feat].to(dev, non_blocking=True)
+        if world == 1:
+            model.bank_test = banks[i % n_bank]          # the public call a user makes: tree_model.score_topk
+            model.score_topk(f, t, hits=hits)
+        else:
+            x = model.encode_image_normalized(f)
+            scorers[i % n_bank].score(x, t, hits)
+        e2e_out[0] = hits.cpu()                          # D2H read of the step's result (Hit@k counters)
+
+    e2e_out = [None]
+    for i in range(warmup):
+        step_e2e(i)
+    e2e_ms = timed(step_e2e, steps) / steps
+    e2e_value = B / (e2e_ms * 1e-3)
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            sec, cores = _cpu_steps(wl, 40 if wl_key == "cfg2" else 8, 3)
+            cpu = {"value": wl["B"] / sec, "unit": "images/s", "cores": cores, "kind": "port",
+                   "sample": "%d batches of %d images, torch CPU fp32 (reference ops of clip_tree.py:330-331 + main.py:136-147)"
+                             % (40 if wl_key == "cfg2" else 8, wl["B"])}
+        line = {
+            "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak" if world == 1 else "strong",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": wl["name"], "B": B, "C": C, "D": D, "K": K,
+                       "sharding": "none" if world == 1 else "class dimension row-sharded over %d ranks, 1 all-gather/batch" % world,
+                       "l2": "inputs larger than L2: %d bank copies (%.0f MB) + %d feature batches rotated" %
+                             (n_bank, n_bank * Cs * D * 2 / 1e6, n_feat)},
+            "e2e": {"value": e2e_value, "unit": "images/s", "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": B * D * 4 + B * 8, "d2h_bytes_per_step": 5 * 8},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s",
+                         "frac": achieved / tf_peak, "traffic": None, "kernel": "score_umma_kernel (GEMM + fused top-20)",
+                         "kernel_ms": kms, "flops_per_launch": flops, "peak_source": peak_src},
+            "cpu_baseline": cpu,
+            "clocks": clocks,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=None, choices=[None, "cfg2", "cfg4", "cfg5"])
+    ap.add_argument("--no-cpu-baseline", dest="no_cpu_baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -15,7 +15,8 @@ LIB_PATH = os.path.join(HERE, "lib", "libhgr_b200.so")
 
 HGR_OK = 0
 HGR_F32, HGR_BF16, HGR_F16 = 0, 1, 2
-HGR_IMPL_AUTO, HGR_IMPL_SIMT, HGR_IMPL_TCGEN05 = 0, 1, 2
+HGR_IMPL_AUTO, HGR_IMPL_SIMT, HGR_IMPL_TCGEN05, HGR_IMPL_TCGEN05_RELOAD = 0, 1, 2, 3
+HGR_IMPL_FLAG_NO_MERGE = 0x100
 HGR_NUM_HITS = 5
 HGR_TOPK_MAX = 32
 HIT_CUTS = (1, 2, 5, 10, 20)  # main.py:120
@@ -31,7 +32,7 @@ SIGNATURES = {
     "hgr_score_topk": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_int64, c_int64, c_int64,
                                c_float, c_int, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, c_int,
                                c_void_p]),
-    "hgr_topk_merge": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p,
+    "hgr_topk_merge": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_int64, c_void_p, c_void_p, c_void_p,
                                c_void_p, c_void_p]),
     "hgr_logits_dense": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_float, c_void_p, c_int64,
                                  c_int, c_void_p]),

@@ -59,7 +59,7 @@ int launch_aggregate_normalize(const void* E, int e_dtype, int64_t n_src, int64_
 // tile mt owns sched->parts(mt) lists (the per-CTA partials of the tcgen05 kernel).
 struct Sched;
 int launch_topk_merge(const float* part_val, const int32_t* part_idx, int64_t P, int64_t B, int K,
-                      const Sched* sched, const int32_t* col_id, int32_t id_base, float scale,
+                      int64_t part_stride, const Sched* sched, const int32_t* col_id, int32_t id_base, float scale,
                       const int32_t* targets, float* topk_val, int32_t* topk_idx, int64_t* hits,
                       cudaStream_t stream);
 
@@ -76,7 +76,8 @@ bool umma_supported(int64_t B, int64_t C, int64_t D, int K);
 int launch_score_topk_umma(const __nv_bfloat16* X, const __nv_bfloat16* bank, const int32_t* col_id,
                            int32_t id_base, const int32_t* targets, int64_t B, int64_t C, int64_t D,
                            float scale, int K, void* ws, size_t ws_bytes, float* topk_val,
-                           int32_t* topk_idx, int64_t* hits, cudaStream_t stream);
+                           int32_t* topk_idx, int64_t* hits, bool reload_epilogue, bool skip_merge,
+                           cudaStream_t stream);
 int launch_logits_umma(const __nv_bfloat16* X, const __nv_bfloat16* bank, int64_t B, int64_t C,
                        int64_t D, float scale, float* out, int64_t ldo, cudaStream_t stream);
 

@@ -94,14 +94,16 @@ int hgr_score_topk(const void* X, const void* bank, const int32_t* col_id, int32
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (C == 0) {
     // empty class set: every list is (-inf, -1); the merge of zero lists writes exactly that
-    return launch_topk_merge(nullptr, nullptr, 0, B, K, nullptr, nullptr, 0, 1.f, nullptr, topk_val, topk_idx, nullptr, s);
+    return launch_topk_merge(nullptr, nullptr, 0, B, K, 0, nullptr, nullptr, 0, 1.f, nullptr, topk_val, topk_idx, nullptr, s);
   }
+  const bool skip_merge = (impl & HGR_IMPL_FLAG_NO_MERGE) != 0;
+  impl &= ~HGR_IMPL_FLAG_NO_MERGE;
   const int which = pick_impl(impl, B, C, D, K);
-  if (which == HGR_IMPL_TCGEN05) {
+  if (which == HGR_IMPL_TCGEN05 || which == HGR_IMPL_TCGEN05_RELOAD) {
     if (!umma_supported(B, C, D, K)) return set_error(HGR_ERR_UNSUPPORTED, "hgr_score_topk: shape not supported by the tcgen05 kernel");
     return launch_score_topk_umma(static_cast<const __nv_bfloat16*>(X), static_cast<const __nv_bfloat16*>(bank), col_id,
                                   id_base, targets, B, C, D, scale, K, workspace, workspace_bytes, topk_val, topk_idx,
-                                  hits, s);
+                                  hits, which == HGR_IMPL_TCGEN05_RELOAD, skip_merge, s);
   }
   if (which == HGR_IMPL_SIMT)
     return launch_score_topk_simt(static_cast<const __nv_bfloat16*>(X), static_cast<const __nv_bfloat16*>(bank), col_id,
@@ -110,14 +112,15 @@ int hgr_score_topk(const void* X, const void* bank, const int32_t* col_id, int32
   return set_error(HGR_ERR_BAD_ARG, "hgr_score_topk: unknown impl %d", impl);
 }
 
-int hgr_topk_merge(const float* part_val, const int32_t* part_idx, int64_t P, int64_t B, int K, const int32_t* targets,
-                   float* topk_val, int32_t* topk_idx, int64_t* hits, void* stream) {
+int hgr_topk_merge(const float* part_val, const int32_t* part_idx, int64_t P, int64_t B, int K, int64_t part_stride,
+                   const int32_t* targets, float* topk_val, int32_t* topk_idx, int64_t* hits, void* stream) {
   HGR_CHECK_ARG(P >= 0 && B >= 0, "hgr_topk_merge: negative size");
   HGR_CHECK_ARG(K >= 1 && K <= HGR_TOPK_MAX, "hgr_topk_merge: K = %d outside [1, %d]", K, HGR_TOPK_MAX);
   if (B == 0) return HGR_OK;
   HGR_CHECK_ARG(topk_val && topk_idx, "hgr_topk_merge: null output");
   HGR_CHECK_ARG(P == 0 || (part_val && part_idx), "hgr_topk_merge: null parts");
-  return launch_topk_merge(part_val, part_idx, P, B, K, nullptr, nullptr, 0, 1.f, targets, topk_val, topk_idx, hits,
+  HGR_CHECK_ARG(part_stride == 0 || part_stride >= B * K, "hgr_topk_merge: part_stride < B*K");
+  return launch_topk_merge(part_val, part_idx, P, B, K, part_stride, nullptr, nullptr, 0, 1.f, targets, topk_val, topk_idx, hits,
                            static_cast<cudaStream_t>(stream));
 }
 

@@ -161,7 +161,7 @@ int launch_score_topk_simt(const __nv_bfloat16* X, const __nv_bfloat16* bank, co
   else HGR_SIMT_LAUNCH(32);
 #undef HGR_SIMT_LAUNCH
   HGR_CHECK_LAUNCH();
-  return launch_topk_merge(part_val, part_idx, S, B, K, nullptr, col_id, id_base, scale, targets, topk_val,
+  return launch_topk_merge(part_val, part_idx, S, B, K, 0, nullptr, col_id, id_base, scale, targets, topk_val,
                            topk_idx, hits, stream);
 }
 

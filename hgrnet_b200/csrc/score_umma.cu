@@ -350,15 +350,6 @@ int make_map(CUtensorMap* map, const void* base, int64_t rows, int64_t D, int bo
   return HGR_OK;
 }
 
-int epi_mode_from_env() {
-  static int mode = [] {
-    const char* e = getenv("HGR_UMMA_EPILOGUE");
-    if (e && e[0] == 'r') return (int)kEpiTopkReload;
-    return (int)kEpiTopkQueue;
-  }();
-  return mode;
-}
-
 template <int EPI, int KL>
 int launch_kernel(const CUtensorMap& mx, const CUtensorMap& mb, const Params& p, cudaStream_t stream) {
   const size_t smem = 1024 + static_cast<size_t>(kStages) * kStageBytes + (EPI == kEpiTopkQueue ? kQueueBytes : 0) +
@@ -398,7 +389,7 @@ size_t umma_score_workspace_bytes(int64_t B, int64_t C, int K) {
 int launch_score_topk_umma(const __nv_bfloat16* X, const __nv_bfloat16* bank, const int32_t* col_id,
                            int32_t id_base, const int32_t* targets, int64_t B, int64_t C, int64_t D, float scale,
                            int K, void* ws, size_t ws_bytes, float* topk_val, int32_t* topk_idx, int64_t* hits,
-                           cudaStream_t stream) {
+                           bool reload_epilogue, bool skip_merge, cudaStream_t stream) {
   CUtensorMap mx, mb;
   Params p{};
   int rc = common_setup(X, bank, B, C, D, &mx, &mb, &p);
@@ -410,7 +401,7 @@ int launch_score_topk_umma(const __nv_bfloat16* X, const __nv_bfloat16* bank, co
   p.scale = scale;
   p.part_val = static_cast<float*>(ws);
   p.part_idx = reinterpret_cast<int32_t*>(p.part_val + static_cast<size_t>(p.sched.P) * B * K);
-  const int mode = epi_mode_from_env();
+  const int mode = reload_epilogue ? kEpiTopkReload : kEpiTopkQueue;
 #define HGR_UMMA_LAUNCH(KL)                                                                  \
   rc = mode == kEpiTopkReload ? launch_kernel<kEpiTopkReload, KL>(mx, mb, p, stream)         \
                               : launch_kernel<kEpiTopkQueue, KL>(mx, mb, p, stream)
@@ -418,8 +409,8 @@ int launch_score_topk_umma(const __nv_bfloat16* X, const __nv_bfloat16* bank, co
   else if (K <= 20) HGR_UMMA_LAUNCH(20);
   else HGR_UMMA_LAUNCH(32);
 #undef HGR_UMMA_LAUNCH
-  if (rc != HGR_OK) return rc;
-  return launch_topk_merge(p.part_val, p.part_idx, p.sched.P, B, K, &p.sched, col_id, id_base, scale, targets,
+  if (rc != HGR_OK || skip_merge) return rc;
+  return launch_topk_merge(p.part_val, p.part_idx, p.sched.P, B, K, 0, &p.sched, col_id, id_base, scale, targets,
                            topk_val, topk_idx, hits, stream);
 }
 

@@ -25,7 +25,7 @@ struct MergeSched {
 
 __global__ void __launch_bounds__(kMergeWarps * 32)
 topk_merge_kernel(const float* __restrict__ part_val, const int32_t* __restrict__ part_idx, int P, int64_t B,
-                  int K, MergeSched ms, const int32_t* __restrict__ col_id, int32_t id_base, float scale,
+                  int K, int64_t pstride, MergeSched ms, const int32_t* __restrict__ col_id, int32_t id_base, float scale,
                   const int32_t* __restrict__ targets, float* __restrict__ topk_val,
                   int32_t* __restrict__ topk_idx, unsigned long long* __restrict__ hits) {
   __shared__ int s_hits[HGR_NUM_HITS];
@@ -37,7 +37,6 @@ topk_merge_kernel(const float* __restrict__ part_val, const int32_t* __restrict_
   if (row < B) {
     int cnt = P;
     if (ms.use) cnt = ms.s.parts(static_cast<int32_t>(row / kTileM));
-    const int64_t pstride = B * K;  // [P][B][K]
     const float* pv = part_val + row * K;
     const int32_t* pi = part_idx + row * K;
 
@@ -116,7 +115,7 @@ topk_merge_kernel(const float* __restrict__ part_val, const int32_t* __restrict_
 }  // namespace
 
 int launch_topk_merge(const float* part_val, const int32_t* part_idx, int64_t P, int64_t B, int K,
-                      const Sched* sched, const int32_t* col_id, int32_t id_base, float scale,
+                      int64_t part_stride, const Sched* sched, const int32_t* col_id, int32_t id_base, float scale,
                       const int32_t* targets, float* topk_val, int32_t* topk_idx, int64_t* hits,
                       cudaStream_t stream) {
   if (B == 0 || K == 0) return HGR_OK;
@@ -129,7 +128,7 @@ int launch_topk_merge(const float* part_val, const int32_t* part_idx, int64_t P,
   else ms.s = Sched{1, 1, 1, 1, 1};
   const int blocks = static_cast<int>((B + kMergeWarps - 1) / kMergeWarps);
   topk_merge_kernel<<<blocks, kMergeWarps * 32, 0, stream>>>(
-      part_val, part_idx, static_cast<int>(P), B, K, ms, col_id, id_base, scale, targets, topk_val, topk_idx,
+      part_val, part_idx, static_cast<int>(P), B, K, part_stride > 0 ? part_stride : B * K, ms, col_id, id_base, scale, targets, topk_val, topk_idx,
       reinterpret_cast<unsigned long long*>(hits));
   HGR_CHECK_LAUNCH();
   return HGR_OK;

@@ -11,7 +11,8 @@ from typing import Optional, Tuple
 import torch
 
 from . import _cabi
-from ._cabi import HGR_IMPL_AUTO, HGR_IMPL_SIMT, HGR_IMPL_TCGEN05, HGR_NUM_HITS  # noqa: F401
+from ._cabi import (HGR_IMPL_AUTO, HGR_IMPL_SIMT, HGR_IMPL_TCGEN05, HGR_IMPL_TCGEN05_RELOAD,  # noqa: F401
+                    HGR_NUM_HITS)
 
 _DTYPE_CODE = {torch.float32: _cabi.HGR_F32, torch.bfloat16: _cabi.HGR_BF16, torch.float16: _cabi.HGR_F16}
 _workspaces = {}
@@ -122,19 +123,26 @@ def score_topk(X: torch.Tensor, bank: torch.Tensor, *, col_id: Optional[torch.Te
 
 def topk_merge(part_val: torch.Tensor, part_idx: torch.Tensor, *, targets: Optional[torch.Tensor] = None,
                hits: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
-    """Merge ``[P, B, K]`` partial lists (node ids) into the final ``[B, K]`` top-K + hits."""
+    """Merge ``[P, B, K]`` partial lists (node ids) into the final ``[B, K]`` top-K + hits.
+
+    The two inputs may be strided views of one gathered buffer (same part stride, dense ``[B, K]`` inside).
+    """
     lib = _cabi.load()
-    part_val = _require(part_val, "part_val", torch.float32)
-    part_idx = _require(part_idx, "part_idx", torch.int32)
+    if part_val.dtype != torch.float32 or part_idx.dtype != torch.int32 or not part_val.is_cuda:
+        raise TypeError("part_val/part_idx must be CUDA float32/int32 tensors")
     P, B, K = part_val.shape
+    dense_inner = lambda t: t.stride(2) == 1 and t.stride(1) == K
+    if not (dense_inner(part_val) and dense_inner(part_idx) and part_val.stride(0) == part_idx.stride(0)):
+        part_val, part_idx = part_val.contiguous(), part_idx.contiguous()
+    part_stride = part_val.stride(0) if P > 1 else 0
     if targets is not None:
         targets = _require(targets, "targets", torch.int32)
     if hits is not None:
         hits = _require(hits, "hits", torch.int64)
     val = torch.empty((B, K), dtype=torch.float32, device=part_val.device)
     idx = torch.empty((B, K), dtype=torch.int32, device=part_val.device)
-    _cabi.check(lib.hgr_topk_merge(_ptr(part_val), _ptr(part_idx), P, B, K, _ptr(targets), _ptr(val), _ptr(idx),
-                                   _ptr(hits), _stream()))
+    _cabi.check(lib.hgr_topk_merge(_ptr(part_val), _ptr(part_idx), P, B, K, part_stride, _ptr(targets), _ptr(val),
+                                   _ptr(idx), _ptr(hits), _stream()))
     return val, idx
 
 

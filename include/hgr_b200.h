@@ -48,6 +48,10 @@ extern "C" {
 #define HGR_IMPL_AUTO 0
 #define HGR_IMPL_SIMT 1     /* CUDA-core kernel: any shape, exactness fallback and debug aid */
 #define HGR_IMPL_TCGEN05 2  /* TMA + tcgen05/TMEM kernel with fused top-k epilogue           */
+#define HGR_IMPL_TCGEN05_RELOAD 3 /* same kernel, simpler epilogue variant (kept as a cross-check) */
+/* OR-ed into `impl`: run only the GEMM + fused top-k kernel and leave the per-CTA partial lists in
+ * the workspace (outputs untouched).  Lets bench.py time the dominant kernel alone for the roofline. */
+#define HGR_IMPL_FLAG_NO_MERGE 0x100
 
 int hgr_version(void);
 const char* hgr_last_error(void);
@@ -108,12 +112,14 @@ int hgr_score_topk(const void* X, const void* bank, const int32_t* col_id, int32
  * Used for the class-sharded multi-GPU head (one list per rank after the NCCL all-gather)
  * and internally for the per-CTA partial lists of hgr_score_topk.
  *
- *  part_val / part_idx  [P, B, K] fp32 / int32 (idx already global node ids; -1 = empty)
+ *  part_val / part_idx  [P, B, K] fp32 / int32 (idx already global node ids; -1 = empty);
+ *                       consecutive parts are part_stride ELEMENTS apart (0 -> B*K, dense), so a
+ *                       gathered buffer of per-rank {val[B,K], idx[B,K]} records can be merged in place
  *  outputs as hgr_score_topk.  Order: value descending, then part index, then position.
  */
 int hgr_topk_merge(const float* part_val, const int32_t* part_idx, int64_t P, int64_t B, int K,
-                   const int32_t* targets, float* topk_val, int32_t* topk_idx, int64_t* hits,
-                   void* stream);
+                   int64_t part_stride, const int32_t* targets, float* topk_val, int32_t* topk_idx,
+                   int64_t* hits, void* stream);
 
 /*
  * Dense logits, out[b, c] = scale * <X[b], bank[c]>, fp32, leading dimension ldo >= C.

@@ -46,6 +46,20 @@ def gen_tree_case():
     return out
 
 
+def flags_case():
+    """Flag surface of the reference's main.py (main.py:14-68): dest -> [option strings, default, nargs/type tag]."""
+    edges = cases.QUIRKY_EDGES
+    nodes = orc.gen_tree(edges)[3]
+    out = {}
+    with rh.reference_session(edges, _splits(nodes, range(len(nodes))), torch.zeros(len(nodes), 8), 0.0) as ns:
+        for a in ns.main.parser._actions:
+            if a.dest == "help":
+                continue
+            kind = "flag" if a.nargs == 0 else getattr(a.type, "__name__", str(a.type))
+            out[a.dest] = {"opts": list(a.option_strings), "default": a.default, "kind": kind}
+    return out
+
+
 def weights_case():
     """get_weights known answers for every method (clip_tree.py:198-219) incl. adaptive on (4,20,200)."""
     edges = cases.tree_edges([4, 20, 200], 3)
@@ -182,6 +196,7 @@ def main():
     meta = {"torch": torch.__version__, "generator": "oracle/gen_golden.py"}
     meta["gen_tree"] = gen_tree_case()
     meta["get_weights"] = weights_case()
+    meta["flags"] = flags_case()
     meta["eval"] = {s["name"]: eval_case(s) for s in cases.EVAL_CASES}
     meta["om"] = {s["name"]: om_case(s) for s in cases.OM_CASES}
     with open(os.path.join(GOLDEN, "golden.json"), "w") as f:

@@ -1,0 +1,232 @@
+"""CPU tests (``-m "not gpu"``): the oracle against the golden vectors frozen from the reference run,
+the host-side logic of the product against the same vectors, and the C-ABI library surface."""
+from __future__ import annotations
+
+import os
+import random
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import cases, hgr_oracle as orc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# ----------------------------------------------------------------------------- oracle vs golden
+def test_oracle_gen_tree_matches_reference(golden):
+    for name, edges in (("quirky", cases.QUIRKY_EDGES), ("tree_4_20_200", cases.tree_edges([4, 20, 200], 3))):
+        g = golden["gen_tree"][name]
+        p2c, c2p, d2n, nodes, start_up = orc.gen_tree(edges)
+        assert p2c == g["p2c"] and c2p == g["c2p"] and nodes == g["nodes"] and start_up == g["start_up"]
+        assert list(d2n.keys()) == g["d2n_keys"]           # insertion order, NOT depth order (utils.py:66-70)
+        assert {str(k): v for k, v in d2n.items()} == g["d2n"]
+    assert golden["gen_tree"]["quirky"]["d2n_keys"] == [1, 2, 0, 3]
+
+
+def test_oracle_get_weights_known_answers(golden):
+    d2n = orc.gen_tree(cases.tree_edges([4, 20, 200], 3))[2]
+    lw = orc.layer_weight_init(d2n, 1.0)
+    np.testing.assert_allclose(lw.numpy(), golden["get_weights"]["layer_weight"], rtol=0)
+    for key, want in golden["get_weights"].items():
+        if key == "layer_weight":
+            continue
+        method, n = key.rsplit("_", 1)
+        np.testing.assert_array_equal(orc.get_weights(method, int(n), lw).float().numpy(), np.float32(want))
+    # SURVEY.md section 8a2 known answer: level sizes (4, 20, 200) -> adaptive(3)
+    np.testing.assert_allclose(golden["get_weights"]["adaptive_3"], [0.7894, 0.1177, 0.0930], atol=5e-5)
+
+
+@pytest.mark.parametrize("spec", cases.EVAL_CASES, ids=[s["name"] for s in cases.EVAL_CASES])
+def test_oracle_eval_matches_reference(spec, golden, golden_dir):
+    torch.set_num_threads(1)
+    g = golden["eval"][spec["name"]]
+    z = np.load(os.path.join(golden_dir, spec["name"] + ".npz"))
+    p2c, c2p, d2n, nodes, _ = orc.gen_tree(cases.tree_edges(spec["levels"], spec["tree_seed"]))
+    test_ids = cases.test_ids(spec, len(nodes))
+    table = cases.text_table(spec, len(nodes))
+    bank = orc.normalize_rows(table)
+    np.testing.assert_array_equal(bank[:: max(1, len(nodes) // 16)].numpy(), z["bank_rows"])
+    hits = {k: 0 for k in orc.TOPK}
+    tor = path = point = 0.0
+    n = 0
+    for b, (feats, label) in enumerate(cases.eval_batches(spec, test_ids)):
+        lg = orc.forward_logits(feats, bank)
+        if b == 0:
+            np.testing.assert_allclose(lg[:4].numpy(), z["logits0_rows"], rtol=1e-6, atol=1e-7)
+        pred, val, h = orc.eval_hits(lg, torch.tensor(test_ids), torch.full((feats.shape[0],), label))
+        np.testing.assert_array_equal(pred.t().numpy(), z["pred"][b])
+        np.testing.assert_allclose(val.numpy(), z["val"][b], rtol=1e-6, atol=1e-7)
+        for k in hits:
+            hits[k] += h[k]
+        a, bb, c = orc.tor_por(lg, torch.arange(len(nodes)), c2p, d2n, len(nodes), label)
+        tor, path, point = tor + a, path + bb, point + c
+        n += feats.shape[0]
+    assert {str(k): v for k, v in hits.items()} == g["hits"] and n == g["num_sample"]
+    s, _ = orc.count_acc(hits, n)
+    line = s + " hit_ratio(%):{:.2f}".format(tor / n * 100.0) + " path_ratio(%):{:.2f}".format(path / n * 100.0) \
+        + " point_ratio(%):{:.2f}".format(point / n * 100.0)
+    assert line == g["line"]                                # the string the reference's main.test printed
+
+
+@pytest.mark.parametrize("spec", cases.OM_CASES, ids=[s["name"] for s in cases.OM_CASES])
+def test_oracle_om_step_matches_reference(spec, golden, golden_dir):
+    torch.set_num_threads(1)
+    g = golden["om"][spec["name"]]
+    z = np.load(os.path.join(golden_dir, spec["name"] + ".npz"))
+    p2c, c2p, d2n, nodes, _ = orc.gen_tree(cases.tree_edges(spec["levels"], spec["tree_seed"]))
+    o = spec["opts"]
+    lw = orc.layer_weight_init(d2n, o.get("scale", 1.0)) if o["weights"] == "adaptive" else None
+    random.seed(spec["sample_seed"])
+    r = orc.om_step(cases.image_feats(spec), cases.text_table(spec, len(nodes), normalize=False),
+                    torch.tensor(float(np.log(1 / 0.07))), c2p, d2n, spec["target"], out_ratio=o["out_ratio"],
+                    in_ratio=o["in_ratio"], weights=o["weights"], weighting=o.get("weighting", "both"), k=o.get("k", 1),
+                    num_compare=o.get("num_compare", 256), layer_weight=lw)
+    assert r["compare_idx"] == g["compare_idx"] and r["labels"] == g["labels"]
+    np.testing.assert_allclose(r["losses"], g["losses"], rtol=1e-6)
+    assert abs(r["loss"] - g["loss"]) <= 1e-6 * abs(g["loss"])
+    np.testing.assert_allclose(r["d_text_raw"][torch.from_numpy(z["d_text_rows"])].numpy(), z["d_text"], rtol=1e-4, atol=1e-8)
+    np.testing.assert_allclose(r["d_log_scale"].numpy(), z["d_log_scale"], rtol=1e-5)
+
+
+def test_oracle_aggregate_identity_is_update_classifier():
+    e = cases.bf16_valued(torch.randn(50, 64, generator=torch.Generator().manual_seed(1)))
+    ident = orc.aggregate_normalize(e, list(range(51)), list(range(50)), [1.0] * 50)
+    assert torch.equal(ident, orc.normalize_rows(e))
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/model"), reason="reference checkout not mounted")
+def test_oracle_against_live_reference():
+    """When the reference is mounted (build container) re-run one case through the unmodified code."""
+    from oracle import ref_harness as rh
+    spec = cases.OM_CASES[0]
+    edges = cases.tree_edges(spec["levels"], spec["tree_seed"])
+    p2c, c2p, d2n, nodes, _ = orc.gen_tree(edges)
+    splits = {"train": nodes, "rest": nodes[24:], "all": nodes}
+    table = cases.text_table(spec, len(nodes), normalize=False)
+    img = cases.image_feats(spec)
+    with rh.reference_session(edges, splits, table, float(np.log(1 / 0.07))) as ns:
+        model = rh.build_tree_model(ns, splits, **spec["opts"])
+        random.seed(spec["sample_seed"])
+        loss = model.train_batch(img.clone().requires_grad_(True), torch.full((spec["B"],), spec["target"]), "OM", "topk")
+    random.seed(spec["sample_seed"])
+    o = spec["opts"]
+    mine = orc.om_step(img, table, torch.tensor(float(np.log(1 / 0.07))), c2p, d2n, spec["target"],
+                       out_ratio=o["out_ratio"], in_ratio=o["in_ratio"], weights=o["weights"], weighting="both", k=1,
+                       num_compare=256)
+    assert abs(mine["loss"] - loss) <= 1e-6 * abs(loss)
+
+
+# ----------------------------------------------------------------------------- host logic vs golden
+def test_hierarchy_matches_gen_tree(golden):
+    from hgrnet_b200.hierarchy import Hierarchy
+    for name, edges in (("quirky", cases.QUIRKY_EDGES), ("tree_4_20_200", cases.tree_edges([4, 20, 200], 3))):
+        g = golden["gen_tree"][name]
+        p2c, c2p, d2n, nodes, start_up = Hierarchy(edges).as_tuple()
+        assert p2c == g["p2c"] and c2p == g["c2p"] and nodes == g["nodes"] and start_up == g["start_up"]
+        assert list(d2n.keys()) == g["d2n_keys"] and {str(k): v for k, v in d2n.items()} == g["d2n"]
+
+
+def test_hierarchy_scales_and_csr():
+    from hgrnet_b200.hierarchy import WORDNET_LIKE_21841, scaled_levels, synthetic_hierarchy
+    from hgrnet_b200.levels import level_weights
+    assert sum(WORDNET_LIKE_21841) == 21841
+    assert sum(scaled_levels(10450)) == 10450 and len(scaled_levels(10450)) == 12
+    h = synthetic_hierarchy(WORDNET_LIKE_21841, seed=1)          # O(N+E): must be quick at ImageNet-21K scale
+    assert len(h) == 21841 and h.max_depth == 11 and [len(h.d2n[d]) for d in range(12)] == WORDNET_LIKE_21841
+    rp, col, w = h.identity_csr()
+    assert rp[-1] == 21841 and (col == np.arange(21841)).all() and (w == 1).all()
+    rp, col, w = h.chain_csr(0.25, lambda n: level_weights("increasing", n).numpy())
+    leaf = 21840
+    chain = h.c2p[leaf] + [leaf]
+    assert list(col[rp[leaf]:rp[leaf + 1]]) == chain[::-1][:3]   # ceil(0.25 * 12) deepest-first (clip_tree.py:232-237)
+    np.testing.assert_allclose(w[rp[leaf]:rp[leaf + 1]], [1 / 6, 2 / 6, 3 / 6], rtol=1e-6)
+    rp0, col0, w0 = h.chain_csr(0.0, lambda n: level_weights("equal", n).numpy())
+    assert (np.diff(rp0) == 1).all() and (col0 == np.arange(21841)).all() and (w0 == 1).all()
+
+
+def test_level_weights_match_reference(golden):
+    from hgrnet_b200.hierarchy import Hierarchy
+    from hgrnet_b200.levels import layer_weight_init, level_weights
+    lw = layer_weight_init(Hierarchy(cases.tree_edges([4, 20, 200], 3)).d2n, 1.0)
+    for key, want in golden["get_weights"].items():
+        if key == "layer_weight":
+            np.testing.assert_allclose(lw.numpy(), want, rtol=0)
+            continue
+        method, n = key.rsplit("_", 1)
+        np.testing.assert_array_equal(level_weights(method, int(n), lw).float().numpy(), np.float32(want))
+    with pytest.raises(ValueError):
+        level_weights("bogus", 3)
+
+
+@pytest.mark.parametrize("spec", cases.OM_CASES, ids=[s["name"] for s in cases.OM_CASES])
+def test_sampling_schedule_matches_reference(spec, golden):
+    from hgrnet_b200.hierarchy import Hierarchy
+    from hgrnet_b200.sampling import contra_topk, om_schedule
+    g = golden["om"][spec["name"]]
+    h = Hierarchy(cases.tree_edges(spec["levels"], spec["tree_seed"]))
+    o = spec["opts"]
+    random.seed(spec["sample_seed"])
+    ids, labels = [], []
+    for (k_loop, m_loop, p_out, depth, parents_in, n_out, n_in) in om_schedule(h.c2p, spec["target"], o["out_ratio"], o["in_ratio"]):
+        ci, pos = contra_topk(h.d2n, p_out, depth, parents_in, o.get("k", 1), o.get("num_compare", 256))
+        ids.append(ci)
+        labels.append(pos)
+        assert pos == len(ci) - 1                           # the anchor is always appended last in 'topk' mode
+    assert ids == g["compare_idx"] and labels == g["labels"]
+
+
+def test_flag_surface_matches_reference_main(golden):
+    from hgrnet_b200.flags import build_parser
+    mine = {a.dest: a for a in build_parser()._actions if a.dest != "help"}
+    for dest, ref in golden["flags"].items():
+        a = mine[dest]
+        assert list(a.option_strings) == ref["opts"], dest
+        assert a.default == ref["default"], dest
+        if ref["kind"] == "flag":
+            assert a.nargs == 0
+    from hgrnet_b200.flags import parse_args
+    o = parse_args(["--train", "False", "--open_eval", "True", "--serial_batches", "False", "--out_ratio", "0.5"])
+    assert o.train is False and o.open_eval is True and o.serial_batches is False and o.out_ratio == 0.5
+    assert o.weights == "adaptive" and o.num_compare == 256 and o.test_batch_size == 512 and o.k == 1
+
+
+def test_count_acc_format():
+    from hgrnet_b200.evaluate import count_acc
+    s, acc = count_acc({1: 112, 2: 120, 5: 129, 10: 137, 20: 140}, 192)
+    assert s == "Top@1(%):58.33, Top@2(%):62.50, Top@5(%):67.19, Top@10(%):71.35, Top@20(%):72.92."
+    assert s == orc.count_acc({1: 112, 2: 120, 5: 129, 10: 137, 20: 140}, 192)[0]
+
+
+# ----------------------------------------------------------------------------- C ABI surface (no compute)
+def test_cabi_library_exports_every_declared_symbol():
+    from hgrnet_b200 import _cabi
+    header = open(os.path.join(ROOT, "include", "hgr_b200.h")).read()
+    declared = set(re.findall(r"\b(hgr_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_cabi.SIGNATURES), declared ^ set(_cabi.SIGNATURES)
+    lib = _cabi.load()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.hgr_version() == 1
+    assert lib.hgr_score_topk_workspace_bytes(512, 21841, 1024, 20) >= 37 * 512 * 20 * 8
+    assert lib.hgr_launch_count() >= 0
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "hgrnet_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), os.path.join(dirpath, f)
+
+
+def test_ops_refuse_cpu_tensors():
+    from hgrnet_b200 import ops
+    x = torch.zeros(4, 64, dtype=torch.bfloat16)
+    with pytest.raises(ValueError, match="no CPU path"):
+        ops.score_topk(x, x, K=20)
+    with pytest.raises(ValueError, match="no CPU path"):
+        ops.logits_dense(x, x)
