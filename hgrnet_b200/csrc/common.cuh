@@ -9,6 +9,7 @@
 #include <cstdio>
 
 #include "../../include/hgr_b200.h"
+#include "sched.cuh"
 
 namespace hgr {
 
@@ -55,13 +56,34 @@ int launch_aggregate_normalize(const void* E, int e_dtype, int64_t n_src, int64_
                                const int32_t* row_map, int64_t n_out, void* out, int out_dtype,
                                float* out_norm, cudaStream_t stream);
 
-// sched == nullptr: all P lists of every row are valid (public hgr_topk_merge); otherwise row
-// tile mt owns sched->parts(mt) lists (the per-CTA partials of the tcgen05 kernel).
-struct Sched;
-int launch_topk_merge(const float* part_val, const int32_t* part_idx, int64_t P, int64_t B, int K,
-                      int64_t part_stride, const Sched* sched, const int32_t* col_id, int32_t id_base, float scale,
-                      const int32_t* targets, float* topk_val, int32_t* topk_idx, int64_t* hits,
-                      cudaStream_t stream);
+// Arguments of the list-merge kernel (topk_merge.cu).
+//  * public use (hgr_topk_merge / SIMT path): `P` lists of length KL == K per row, all valid.
+//  * tcgen05 path: `use_sched` -- row tile mt owns sched.parts(mt) * wpq lists of length KL (the per-warp
+//    partial lists of each CTA segment).  When KL < K the lists are SPECULATIVE (narrower than K); the merge
+//    certifies every row (a full list whose last entry still beats the merged K-th value may hide candidates)
+//    and re-scans uncertified rows exactly on the CUDA cores, for which it needs X / bank.
+struct MergeArgs {
+  const float* part_val;
+  const int32_t* part_idx;
+  int64_t P, B;
+  int KL, K;
+  int64_t part_stride;      // elements between consecutive lists (0 -> B * KL)
+  int use_sched, wpq;
+  Sched sched;
+  const int32_t* col_id;
+  int32_t id_base;
+  float scale;
+  const int32_t* targets;
+  float* topk_val;
+  int32_t* topk_idx;
+  int64_t* hits;
+  const void* X;            // [B, D] bf16 -- exact re-scan only
+  const void* bank;         // [C, D] bf16
+  int64_t C;
+  int D8;
+  unsigned int* rescan_count;  // optional statistics: number of rows re-scanned
+};
+int launch_topk_merge(const MergeArgs& args, cudaStream_t stream);
 
 size_t simt_score_workspace_bytes(int64_t B, int64_t C, int K);
 int launch_score_topk_simt(const __nv_bfloat16* X, const __nv_bfloat16* bank, const int32_t* col_id,
@@ -76,7 +98,7 @@ bool umma_supported(int64_t B, int64_t C, int64_t D, int K);
 int launch_score_topk_umma(const __nv_bfloat16* X, const __nv_bfloat16* bank, const int32_t* col_id,
                            int32_t id_base, const int32_t* targets, int64_t B, int64_t C, int64_t D,
                            float scale, int K, void* ws, size_t ws_bytes, float* topk_val,
-                           int32_t* topk_idx, int64_t* hits, bool reload_epilogue, bool skip_merge,
+                           int32_t* topk_idx, int64_t* hits, int variant, bool skip_merge,
                            cudaStream_t stream);
 int launch_logits_umma(const __nv_bfloat16* X, const __nv_bfloat16* bank, int64_t B, int64_t C,
                        int64_t D, float scale, float* out, int64_t ldo, cudaStream_t stream);

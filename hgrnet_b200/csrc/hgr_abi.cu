@@ -94,16 +94,25 @@ int hgr_score_topk(const void* X, const void* bank, const int32_t* col_id, int32
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (C == 0) {
     // empty class set: every list is (-inf, -1); the merge of zero lists writes exactly that
-    return launch_topk_merge(nullptr, nullptr, 0, B, K, 0, nullptr, nullptr, 0, 1.f, nullptr, topk_val, topk_idx, nullptr, s);
+    MergeArgs m{};
+    m.B = B;
+    m.KL = K;
+    m.K = K;
+    m.scale = 1.f;
+    m.topk_val = topk_val;
+    m.topk_idx = topk_idx;
+    return launch_topk_merge(m, s);
   }
   const bool skip_merge = (impl & HGR_IMPL_FLAG_NO_MERGE) != 0;
   impl &= ~HGR_IMPL_FLAG_NO_MERGE;
   const int which = pick_impl(impl, B, C, D, K);
-  if (which == HGR_IMPL_TCGEN05 || which == HGR_IMPL_TCGEN05_RELOAD) {
+  if (which == HGR_IMPL_TCGEN05 || which == HGR_IMPL_TCGEN05_RELOAD || which == HGR_IMPL_TCGEN05_EXACT ||
+      which == HGR_IMPL_TCGEN05_NULL) {
     if (!umma_supported(B, C, D, K)) return set_error(HGR_ERR_UNSUPPORTED, "hgr_score_topk: shape not supported by the tcgen05 kernel");
+    const int variant = which == HGR_IMPL_TCGEN05 ? 0 : which == HGR_IMPL_TCGEN05_RELOAD ? 1 : which == HGR_IMPL_TCGEN05_EXACT ? 2 : 3;
     return launch_score_topk_umma(static_cast<const __nv_bfloat16*>(X), static_cast<const __nv_bfloat16*>(bank), col_id,
                                   id_base, targets, B, C, D, scale, K, workspace, workspace_bytes, topk_val, topk_idx,
-                                  hits, which == HGR_IMPL_TCGEN05_RELOAD, skip_merge, s);
+                                  hits, variant, skip_merge || variant == 3, s);
   }
   if (which == HGR_IMPL_SIMT)
     return launch_score_topk_simt(static_cast<const __nv_bfloat16*>(X), static_cast<const __nv_bfloat16*>(bank), col_id,
@@ -120,8 +129,20 @@ int hgr_topk_merge(const float* part_val, const int32_t* part_idx, int64_t P, in
   HGR_CHECK_ARG(topk_val && topk_idx, "hgr_topk_merge: null output");
   HGR_CHECK_ARG(P == 0 || (part_val && part_idx), "hgr_topk_merge: null parts");
   HGR_CHECK_ARG(part_stride == 0 || part_stride >= B * K, "hgr_topk_merge: part_stride < B*K");
-  return launch_topk_merge(part_val, part_idx, P, B, K, part_stride, nullptr, nullptr, 0, 1.f, targets, topk_val, topk_idx, hits,
-                           static_cast<cudaStream_t>(stream));
+  MergeArgs m{};
+  m.part_val = part_val;
+  m.part_idx = part_idx;
+  m.P = P;
+  m.B = B;
+  m.KL = K;
+  m.K = K;
+  m.part_stride = part_stride;
+  m.scale = 1.f;
+  m.targets = targets;
+  m.topk_val = topk_val;
+  m.topk_idx = topk_idx;
+  m.hits = hits;
+  return launch_topk_merge(m, static_cast<cudaStream_t>(stream));
 }
 
 int hgr_logits_dense(const void* X, const void* bank, int64_t B, int64_t C, int64_t D, float scale, float* out,

@@ -3,35 +3,19 @@
 // Same contract as the tcgen05 kernel (score_umma.cu): logits = X @ bank^T, per-row sorted
 // top-K, never materialising B x C.  It accepts any shape (D % 8 == 0) and exists for three
 // reasons: (a) shapes the tensor-core kernel does not take, (b) an on-device cross-check of
-// the tcgen05 path in the GPU tests, (c) the exact re-scan of rows whose speculative narrow
-// lists could not be certified (see score_umma.cu).  It is NOT a CPU fallback.
+// the tcgen05 path in the GPU tests, (c) its row scan (simt_row.cuh) is the exact re-scan of
+// rows whose speculative narrow lists could not be certified (topk_merge.cu).  It is NOT a
+// CPU fallback.
 //
 // Reference: model/clip_tree.py:331 (`feats @ self.zsl_weights.T`) + main.py:136-141.
 #include "common.cuh"
 #include "sched.cuh"
-#include "topk_list.cuh"
+#include "simt_row.cuh"
 
 namespace hgr {
 namespace {
 
 constexpr int kSimtWarps = 8;
-
-__device__ __forceinline__ float dot8(const uint4& a, const uint4& b, float acc) {
-  const uint32_t ua[4] = {a.x, a.y, a.z, a.w};
-  const uint32_t ub[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    acc = fmaf(__uint_as_float(ua[i] << 16), __uint_as_float(ub[i] << 16), acc);
-    acc = fmaf(__uint_as_float(ua[i] & 0xFFFF0000u), __uint_as_float(ub[i] & 0xFFFF0000u), acc);
-  }
-  return acc;
-}
-
-__device__ __forceinline__ float warp_sum(float v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
 
 __device__ __forceinline__ void stage_rows(uint4* s_x, const uint4* X4, int64_t B, int D8) {
   for (int i = threadIdx.x; i < kSimtWarps * D8; i += blockDim.x) {
@@ -53,32 +37,9 @@ score_topk_simt_kernel(const uint4* __restrict__ X4, const uint4* __restrict__ b
   if (row >= B) return;
   const int64_t c0 = blockIdx.y * cols_per_split;
   const int64_t c1 = c0 + cols_per_split < C ? c0 + cols_per_split : C;
-  const uint4* xr = s_x + warp * D8;
-
-  SortedList<KL> list;  // replicated in every lane of the warp (all lanes see the same sums)
+  SortedList<KL> list;
   list.init();
-  int64_t c = c0;
-  for (; c + 1 < c1; c += 2) {
-    float a0 = 0.f, a1 = 0.f;
-    const uint4* b0 = bank4 + c * D8;
-    const uint4* b1 = b0 + D8;
-    for (int idx = lane; idx < D8; idx += 32) {
-      const uint4 x = xr[idx];
-      a0 = dot8(__ldg(b0 + idx), x, a0);
-      a1 = dot8(__ldg(b1 + idx), x, a1);
-    }
-    a0 = warp_sum(a0);
-    a1 = warp_sum(a1);
-    if (a0 > list.thr()) list.insert(a0, static_cast<int32_t>(c));
-    if (a1 > list.thr()) list.insert(a1, static_cast<int32_t>(c + 1));
-  }
-  if (c < c1) {
-    float a0 = 0.f;
-    const uint4* b0 = bank4 + c * D8;
-    for (int idx = lane; idx < D8; idx += 32) a0 = dot8(__ldg(b0 + idx), xr[idx], a0);
-    a0 = warp_sum(a0);
-    if (a0 > list.thr()) list.insert(a0, static_cast<int32_t>(c));
-  }
+  scan_row_range<KL>(s_x + warp * D8, bank4, c0, c1, D8, lane, list);
   if (lane == 0) {
     float* pv = part_val + (static_cast<int64_t>(blockIdx.y) * B + row) * K;
     int32_t* pi = part_idx + (static_cast<int64_t>(blockIdx.y) * B + row) * K;
@@ -108,8 +69,8 @@ logits_simt_kernel(const uint4* __restrict__ X4, const uint4* __restrict__ bank4
     for (int j = 0; j < 32 && cb + j < c1; ++j) {
       float a = 0.f;
       const uint4* b = bank4 + (cb + j) * D8;
-      for (int idx = lane; idx < D8; idx += 32) a = dot8(__ldg(b + idx), xr[idx], a);
-      a = warp_sum(a);
+      for (int idx = lane; idx < D8; idx += 32) a = dot8_bf16(__ldg(b + idx), xr[idx], a);
+      a = warp_sum_f32(a);
       if (lane == j) keep = a;
     }
     if (cb + lane < c1) out[row * ldo + cb + lane] = keep * scale;
@@ -161,8 +122,21 @@ int launch_score_topk_simt(const __nv_bfloat16* X, const __nv_bfloat16* bank, co
   else HGR_SIMT_LAUNCH(32);
 #undef HGR_SIMT_LAUNCH
   HGR_CHECK_LAUNCH();
-  return launch_topk_merge(part_val, part_idx, S, B, K, 0, nullptr, col_id, id_base, scale, targets, topk_val,
-                           topk_idx, hits, stream);
+  MergeArgs m{};
+  m.part_val = part_val;
+  m.part_idx = part_idx;
+  m.P = S;
+  m.B = B;
+  m.KL = K;
+  m.K = K;
+  m.col_id = col_id;
+  m.id_base = id_base;
+  m.scale = scale;
+  m.targets = targets;
+  m.topk_val = topk_val;
+  m.topk_idx = topk_idx;
+  m.hits = hits;
+  return launch_topk_merge(m, stream);
 }
 
 int launch_logits_simt(const __nv_bfloat16* X, const __nv_bfloat16* bank, int64_t B, int64_t C, int64_t D,

@@ -6,20 +6,32 @@
 // + `.topk(20, 1, True, True)` (main.py:136-138); the id mapping / hit test (main.py:139-147)
 // runs in the merge kernel (topk_merge.cu).
 //
-// Structure (one persistent CTA per SM, 192 threads, warp-specialised):
-//   warp 0      TMA producer: X tile [128 x 64] and bank tile [<=256 x 64] bf16 per K block,
-//               128B-swizzled, 4-stage mbarrier ring;
-//   warp 1      allocates TMEM (512 columns = two 128 x 256 fp32 accumulators), one lane issues
-//               tcgen05.mma (M = 128, N = 16..256, K = 16) and commits to mbarriers;
-//   warps 2-5   epilogue: tcgen05.ld the accumulator of sub-tile t while the tensor core
-//               works on sub-tile t+1; thread = TMEM lane = image row keeps that row's sorted
-//               top-K in registers across all sub-tiles of the CTA's class range.
+// Structure (one persistent CTA per SM, warp-specialised):
+//   warp 0        TMA producer: X tile [128 x 64] and bank tile [<=256 x 64] bf16 per K block,
+//                 128B-swizzled, 4-stage mbarrier ring;
+//   warp 1        allocates TMEM (512 columns = two 128 x 256 fp32 accumulators), one lane issues
+//                 tcgen05.mma (M = 128, N = 16..256, K = 16) and commits to mbarriers;
+//   warps 2..     epilogue, WPQ warps per TMEM lane quarter: tcgen05.ld the accumulator of
+//                 sub-tile t while the tensor core works on sub-tile t+1.  Thread = TMEM lane =
+//                 image row; the WPQ warps of a quarter take the 32-column chunks of a sub-tile
+//                 round-robin, and each thread keeps its row's sorted top-KL of the chunks it saw in
+//                 registers across all sub-tiles of the CTA's class range.
+//
+// Epilogue cost model (what the design answers to): a warp owns an SM sub-partition's issue
+// port, so (a) values that beat the row's current KL-th best are first COMPACTED per lane into
+// a shared-memory queue (predicated stores, no divergence) and then drained in lock-step -- the
+// long insert body runs max_lane(count) times per chunk instead of once per column that any
+// lane hit; (b) several warps per quarter hide the dependent-select latency of the insert;
+// (c) when a row is split over many lists (many CTAs per row tile) the lists are SPECULATIVE,
+// KL < K entries, which divides the insert work by ~3; the merge kernel certifies each row and
+// re-scans the (practically never occurring) uncertified ones exactly.
 // Work split: sched.cuh (stream-K-style split of the class dimension in units of 16 rows).
 #include <cuda.h>
 
+#include <cmath>
+
 #include "common.cuh"
 #include "ptx.cuh"
-#include "sched.cuh"
 #include "topk_list.cuh"
 
 namespace hgr {
@@ -33,14 +45,11 @@ constexpr int kBBytes = kSubN * kBlockK * 2;        // 32 KB
 constexpr int kStageBytes = kABytes + kBBytes;      // 48 KB
 constexpr int kBBoxRows = 64;                       // bank rows per TMA box
 constexpr int kBBoxBytes = kBBoxRows * kBlockK * 2; // 8 KB
-constexpr int kThreads = 192;
 constexpr int kEpiWarp0 = 2;
-constexpr int kEpiThreads = 128;
 constexpr int kTmemCols = 512;
-constexpr int kQueueDepth = 32;                     // candidate slots per epilogue thread (one chunk)
-constexpr int kQueueBytes = kQueueDepth * kEpiThreads * 8;
+constexpr int kChunk = 32;                          // accumulator columns per tcgen05.ld
 
-enum EpiMode { kEpiDense = 0, kEpiTopkReload = 1, kEpiTopkQueue = 2 };
+enum EpiMode { kEpiDense = 0, kEpiTopkReload = 1, kEpiTopkQueue = 2, kEpiNull = 3 };
 
 struct Ctl {
   uint64_t full[kStages];
@@ -91,24 +100,24 @@ struct Params {
   Sched sched;
   int64_t B, C;
   int num_k_blocks;
-  int K;
+  int KL;              // entries written per list
   float scale;
-  float* part_val;     // [P][B][K]
-  int32_t* part_idx;   // [P][B][K] bank rows
+  float* part_val;     // [slots][B][KL]
+  int32_t* part_idx;   // [slots][B][KL] bank rows
   float* dense_out;    // [B][ldo]
   int64_t ldo;
+  unsigned int* stats; // [0] = rows re-scanned by the merge kernel of this call (reset here)
 };
 
 template <int KL>
-__device__ __forceinline__ void scan_chunk_reload(SortedList<KL>& list, const uint32_t (&r)[32], int nv,
+__device__ __forceinline__ void scan_chunk_reload(SortedList<KL>& list, const uint32_t (&r)[kChunk], int nv,
                                                   uint32_t taddr_chunk, int col_chunk) {
-  // which of my 32 values beat my current K-th best?
   const float thr = list.thr();
   uint32_t m = 0;
 #pragma unroll
-  for (int j = 0; j < 32; ++j)
+  for (int j = 0; j < kChunk; ++j)
     if (__uint_as_float(r[j]) > thr) m |= (1u << j);
-  if (nv < 32) m &= (1u << nv) - 1u;
+  if (nv < kChunk) m &= (1u << nv) - 1u;
   uint32_t wm = __reduce_or_sync(0xffffffffu, m);
   // visit the union of positions in ascending order; each lane re-reads its own value of that
   // column from TMEM (the address is warp-uniform) and inserts if it still qualifies
@@ -121,56 +130,59 @@ __device__ __forceinline__ void scan_chunk_reload(SortedList<KL>& list, const ui
   }
 }
 
-template <int KL>
-__device__ __forceinline__ void scan_chunk_queue(SortedList<KL>& list, const uint32_t (&r)[32], int nv,
-                                                 int col_chunk, uint2* queue /* + epilogue thread id */) {
-  // 1) lane-private compaction of the values that beat the K-th best at chunk entry
+// queue: this thread's column of the [kChunk][epilogue threads] fp32 staging array
+template <int KL, int QSTRIDE>
+__device__ __forceinline__ void scan_chunk_queue(SortedList<KL>& list, const uint32_t (&r)[kChunk], int nv,
+                                                 int col_chunk, float* queue) {
+  // 1) lane-private compaction of the values that beat the KL-th best at chunk entry:
+  //    values go to the queue in column order, their positions into a bit mask
   const float thr = list.thr();
+  uint32_t m = 0;
   int cnt = 0;
-  if (nv >= 32) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      if (__uint_as_float(r[j]) > thr) {
-        queue[cnt * kEpiThreads] = make_uint2(r[j], static_cast<uint32_t>(col_chunk + j));
-        ++cnt;
-      }
-    }
-  } else {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      if (j < nv && __uint_as_float(r[j]) > thr) {
-        queue[cnt * kEpiThreads] = make_uint2(r[j], static_cast<uint32_t>(col_chunk + j));
-        ++cnt;
-      }
+  for (int j = 0; j < kChunk; ++j) {
+    const float x = __uint_as_float(r[j]);
+    if (x > thr) {
+      queue[cnt * QSTRIDE] = x;
+      ++cnt;
+      m |= (1u << j);
     }
   }
-  // 2) dense drain: lanes walk their own queues in lock-step, so the (long) insert body is
-  //    executed max_lane(cnt) times instead of once per column any lane hit
+  if (nv < kChunk) {  // ragged tail: columns >= C were zero-filled by TMA, drop them
+    m &= (1u << nv) - 1u;
+    cnt = __popc(m);
+  }
+  // 2) dense drain: lanes walk their own queues in lock-step, so the (long) insert body runs
+  //    max_lane(cnt) times instead of once per column any lane hit
   const int maxc = __reduce_max_sync(0xffffffffu, cnt);
   for (int e = 0; e < maxc; ++e) {
     if (e < cnt) {
-      const uint2 c = queue[e * kEpiThreads];
-      const float x = __uint_as_float(c.x);
-      if (x > list.thr()) list.insert(x, static_cast<int32_t>(c.y));
+      const float x = queue[e * QSTRIDE];
+      const int j = __ffs(m) - 1;
+      m &= m - 1;
+      if (x > list.thr()) list.insert(x, col_chunk + j);
     }
   }
 }
 
-template <int EPI, int KL>
-__global__ void __launch_bounds__(kThreads, 1)
+template <int EPI, int KL, int WPQ>
+__global__ void __launch_bounds__(64 + 128 * WPQ, 1)
 score_umma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_bank,
                   const Params p) {
+  constexpr int kEpiThreads = 128 * WPQ;
+  constexpr int kQueueBytes = EPI == kEpiTopkQueue ? kChunk * kEpiThreads * 4 : 0;
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles must start on 1024-byte boundaries
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* stage_base = smem;
-  uint2* queue_base = reinterpret_cast<uint2*>(smem + kStages * kStageBytes);
-  Ctl* ctl = reinterpret_cast<Ctl*>(smem + kStages * kStageBytes + (EPI == kEpiTopkQueue ? kQueueBytes : 0));
+  float* queue_base = reinterpret_cast<float*>(smem + kStages * kStageBytes);
+  Ctl* ctl = reinterpret_cast<Ctl*>(smem + kStages * kStageBytes + kQueueBytes);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int cta = blockIdx.x;
 
+  if (cta == 0 && threadIdx.x == 0 && p.stats != nullptr) p.stats[0] = 0;
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&map_x);
     ptx::prefetch_tensormap(&map_bank);
@@ -257,13 +269,15 @@ score_umma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
   } else {
     // ===================== epilogue =====================
     const int quarter = warp & 3;                       // TMEM lane quarter this warp may access
+    const int member = (warp - kEpiWarp0) >> 2;         // which of the WPQ warps of that quarter
     const int row_in_tile = quarter * 32 + lane;
     const int epi_tid = (warp - kEpiWarp0) * 32 + lane;
-    uint2* queue = queue_base + epi_tid;
+    float* queue = queue_base + epi_tid;
     TileWalker walk(p.sched, cta, p.C);
     SubTile t;
     SortedList<KL> list;
     list.init();
+    float null_acc = -INFINITY;
     int it = 0;
     while (walk.next(t)) {
       const int buf = it & 1;
@@ -271,9 +285,12 @@ score_umma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + buf * kSubN;
       const int64_t row = static_cast<int64_t>(t.mt) * kTileM + row_in_tile;
-      if (EPI != kEpiDense && t.first) list.init();
-      for (int c0 = 0; c0 < t.nvalid; c0 += 32) {
-        uint32_t r[32];
+      if (t.first) {
+        list.init();
+        null_acc = -INFINITY;
+      }
+      for (int c0 = member * kChunk; c0 < t.nvalid; c0 += WPQ * kChunk) {
+        uint32_t r[kChunk];
         ptx::tmem_ld_x32(taddr + c0, r);
         ptx::tmem_ld_wait();
         const int nv = t.nvalid - c0;
@@ -281,13 +298,16 @@ score_umma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
           if (row < p.B) {
             float* o = p.dense_out + row * p.ldo + t.col0 + c0;
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
+            for (int j = 0; j < kChunk; ++j)
               if (j < nv) o[j] = __uint_as_float(r[j]) * p.scale;
           }
         } else if (EPI == kEpiTopkReload) {
           scan_chunk_reload<KL>(list, r, nv, taddr + c0, t.col0 + c0);
+        } else if (EPI == kEpiTopkQueue) {
+          scan_chunk_queue<KL, kEpiThreads>(list, r, nv, t.col0 + c0, queue);
         } else {
-          scan_chunk_queue<KL>(list, r, nv, t.col0 + c0, queue);
+#pragma unroll
+          for (int j = 0; j < kChunk; ++j) null_acc = fmaxf(null_acc, __uint_as_float(r[j]));
         }
       }
       // accumulator buffer drained: hand it back to the MMA warp
@@ -295,14 +315,19 @@ score_umma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&ctl->tmem_empty[buf]);
       if (EPI != kEpiDense && t.last && row < p.B) {
-        const int slot = cta - p.sched.first_cta(t.mt);
-        float* pv = p.part_val + (static_cast<int64_t>(slot) * p.B + row) * p.K;
-        int32_t* pi = p.part_idx + (static_cast<int64_t>(slot) * p.B + row) * p.K;
+        const int slot = (cta - p.sched.first_cta(t.mt)) * WPQ + member;
+        float* pv = p.part_val + (static_cast<int64_t>(slot) * p.B + row) * p.KL;
+        int32_t* pi = p.part_idx + (static_cast<int64_t>(slot) * p.B + row) * p.KL;
+        if (EPI == kEpiNull) {
+          pv[0] = null_acc;
+          pi[0] = -1;
+        } else {
 #pragma unroll
-        for (int k = 0; k < KL; ++k) {
-          if (k < p.K) {
-            pv[k] = list.v[k];
-            pi[k] = list.i[k];
+          for (int k = 0; k < KL; ++k) {
+            if (k < p.KL) {
+              pv[k] = list.v[k];
+              pi[k] = list.i[k];
+            }
           }
         }
       }
@@ -350,13 +375,14 @@ int make_map(CUtensorMap* map, const void* base, int64_t rows, int64_t D, int bo
   return HGR_OK;
 }
 
-template <int EPI, int KL>
+template <int EPI, int KL, int WPQ>
 int launch_kernel(const CUtensorMap& mx, const CUtensorMap& mb, const Params& p, cudaStream_t stream) {
-  const size_t smem = 1024 + static_cast<size_t>(kStages) * kStageBytes + (EPI == kEpiTopkQueue ? kQueueBytes : 0) +
-                      sizeof(Ctl);
-  auto kern = score_umma_kernel<EPI, KL>;
+  constexpr int threads = 64 + 128 * WPQ;
+  const size_t smem = 1024 + static_cast<size_t>(kStages) * kStageBytes +
+                      (EPI == kEpiTopkQueue ? static_cast<size_t>(kChunk) * 128 * WPQ * 4 : 0) + sizeof(Ctl);
+  auto kern = score_umma_kernel<EPI, KL, WPQ>;
   HGR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  kern<<<p.sched.G, kThreads, smem, stream>>>(mx, mb, p);
+  kern<<<p.sched.G, threads, smem, stream>>>(mx, mb, p);
   HGR_CHECK_LAUNCH();
   return HGR_OK;
 }
@@ -374,6 +400,31 @@ int common_setup(const __nv_bfloat16* X, const __nv_bfloat16* bank, int64_t B, i
   return HGR_OK;
 }
 
+// ---- list-width policy -------------------------------------------------------------------
+// With `lists` lists per row and bank rows in random order, the true top-K members of a row fall
+// into a given list with probability 1/lists each, so a list of KL < K entries overflows with
+// probability <= C(K, KL) / lists^KL.  Speculate only while the expected number of re-scanned
+// rows per call stays below 1e-3 (a re-scan costs ~1 ms of one warp).
+double overflow_bound(int K, int KL, int lists) {
+  double c = 1.0;
+  for (int i = 0; i < KL; ++i) c = c * (K - i) / (i + 1);
+  return c * std::pow(1.0 / lists, KL);
+}
+
+int pick_list_len(int K, int64_t B, int lists_per_row, bool allow_speculation) {
+  const int exact = K <= 8 ? 8 : (K <= 12 ? 12 : (K <= 20 ? 20 : 32));
+  if (!allow_speculation) return exact;
+  const int cand[2] = {8, 12};
+  for (int i = 0; i < 2; ++i) {
+    const int kl = cand[i];
+    if (kl >= K) break;
+    if (static_cast<double>(B) * lists_per_row * overflow_bound(K, kl, lists_per_row) < 1e-3) return kl;
+  }
+  return exact;
+}
+
+constexpr int kWpq = 2;  // epilogue warps per TMEM lane quarter of the production kernel
+
 }  // namespace
 
 bool umma_supported(int64_t B, int64_t C, int64_t D, int K) {
@@ -383,35 +434,76 @@ bool umma_supported(int64_t B, int64_t C, int64_t D, int K) {
 
 size_t umma_score_workspace_bytes(int64_t B, int64_t C, int K) {
   const Sched s = make_sched(B, C, num_sms());
-  return static_cast<size_t>(s.P) * B * K * (sizeof(float) + sizeof(int32_t));
+  // worst case over the list-width policy: exact lists of up to HGR_TOPK_MAX entries
+  const int kl = K <= 8 ? 8 : (K <= 12 ? 12 : (K <= 20 ? 20 : 32));
+  return static_cast<size_t>(s.P) * kWpq * B * kl * (sizeof(float) + sizeof(int32_t)) + 64;
 }
 
 int launch_score_topk_umma(const __nv_bfloat16* X, const __nv_bfloat16* bank, const int32_t* col_id,
                            int32_t id_base, const int32_t* targets, int64_t B, int64_t C, int64_t D, float scale,
                            int K, void* ws, size_t ws_bytes, float* topk_val, int32_t* topk_idx, int64_t* hits,
-                           bool reload_epilogue, bool skip_merge, cudaStream_t stream) {
+                           int variant, bool skip_merge, cudaStream_t stream) {
   CUtensorMap mx, mb;
   Params p{};
   int rc = common_setup(X, bank, B, C, D, &mx, &mb, &p);
   if (rc != HGR_OK) return rc;
-  const size_t need = static_cast<size_t>(p.sched.P) * B * K * (sizeof(float) + sizeof(int32_t));
-  if (ws == nullptr || ws_bytes < need)
-    return set_error(HGR_ERR_WORKSPACE, "hgr_score_topk(tcgen05): workspace %zu < %zu bytes", ws_bytes, need);
-  p.K = K;
+  if (ws == nullptr || ws_bytes < umma_score_workspace_bytes(B, C, K))
+    return set_error(HGR_ERR_WORKSPACE, "hgr_score_topk(tcgen05): workspace %zu < %zu bytes", ws_bytes,
+                     umma_score_workspace_bytes(B, C, K));
+  // variants: 0 = production (queue epilogue, kWpq warps/quarter, speculative lists when safe)
+  //           1 = reload epilogue, 1 warp/quarter, exact lists (cross-check)
+  //           2 = queue epilogue, exact lists (no speculation)
+  //           3 = null epilogue (main-loop ceiling; results are NOT a top-k) -- bench diagnostics only
+  const int wpq = variant == 1 ? 1 : kWpq;
+  const int lists = p.sched.P * wpq;
+  const int KL = pick_list_len(K, B, lists, variant == 0);
+  p.KL = KL;
   p.scale = scale;
-  p.part_val = static_cast<float*>(ws);
-  p.part_idx = reinterpret_cast<int32_t*>(p.part_val + static_cast<size_t>(p.sched.P) * B * K);
-  const int mode = reload_epilogue ? kEpiTopkReload : kEpiTopkQueue;
-#define HGR_UMMA_LAUNCH(KL)                                                                  \
-  rc = mode == kEpiTopkReload ? launch_kernel<kEpiTopkReload, KL>(mx, mb, p, stream)         \
-                              : launch_kernel<kEpiTopkQueue, KL>(mx, mb, p, stream)
-  if (K <= 8) HGR_UMMA_LAUNCH(8);
-  else if (K <= 20) HGR_UMMA_LAUNCH(20);
-  else HGR_UMMA_LAUNCH(32);
-#undef HGR_UMMA_LAUNCH
+  p.stats = static_cast<unsigned int*>(ws);                              // first 64 bytes: statistics
+  p.part_val = reinterpret_cast<float*>(static_cast<uint8_t*>(ws) + 64);
+  p.part_idx = reinterpret_cast<int32_t*>(p.part_val + static_cast<size_t>(lists) * B * KL);
+  if (variant == 3) {
+    rc = launch_kernel<kEpiNull, 8, kWpq>(mx, mb, p, stream);
+    return rc;
+  }
+#define HGR_UMMA_CASE(KLV)                                                                            \
+  case KLV:                                                                                           \
+    rc = variant == 1 ? launch_kernel<kEpiTopkReload, KLV, 1>(mx, mb, p, stream)                      \
+                      : launch_kernel<kEpiTopkQueue, KLV, kWpq>(mx, mb, p, stream);                   \
+    break
+  switch (KL) {
+    HGR_UMMA_CASE(8);
+    HGR_UMMA_CASE(12);
+    HGR_UMMA_CASE(20);
+    HGR_UMMA_CASE(32);
+    default:
+      return set_error(HGR_ERR_UNSUPPORTED, "hgr_score_topk(tcgen05): list length %d", KL);
+  }
+#undef HGR_UMMA_CASE
   if (rc != HGR_OK || skip_merge) return rc;
-  return launch_topk_merge(p.part_val, p.part_idx, p.sched.P, B, K, 0, &p.sched, col_id, id_base, scale, targets,
-                           topk_val, topk_idx, hits, stream);
+  MergeArgs m{};
+  m.part_val = p.part_val;
+  m.part_idx = p.part_idx;
+  m.P = lists;
+  m.B = B;
+  m.KL = KL;
+  m.K = K;
+  m.use_sched = 1;
+  m.wpq = wpq;
+  m.sched = p.sched;
+  m.col_id = col_id;
+  m.id_base = id_base;
+  m.scale = scale;
+  m.targets = targets;
+  m.topk_val = topk_val;
+  m.topk_idx = topk_idx;
+  m.hits = hits;
+  m.X = X;
+  m.bank = bank;
+  m.C = C;
+  m.D8 = static_cast<int>(D / 8);
+  m.rescan_count = p.stats;
+  return launch_topk_merge(m, stream);
 }
 
 int launch_logits_umma(const __nv_bfloat16* X, const __nv_bfloat16* bank, int64_t B, int64_t C, int64_t D,
@@ -420,11 +512,11 @@ int launch_logits_umma(const __nv_bfloat16* X, const __nv_bfloat16* bank, int64_
   Params p{};
   int rc = common_setup(X, bank, B, C, D, &mx, &mb, &p);
   if (rc != HGR_OK) return rc;
-  p.K = 0;
+  p.KL = 0;
   p.scale = scale;
   p.dense_out = out;
   p.ldo = ldo;
-  return launch_kernel<kEpiDense, 8>(mx, mb, p, stream);
+  return launch_kernel<kEpiDense, 8, kWpq>(mx, mb, p, stream);
 }
 
 }  // namespace hgr

@@ -12,7 +12,7 @@ import torch
 
 from . import _cabi
 from ._cabi import (HGR_IMPL_AUTO, HGR_IMPL_SIMT, HGR_IMPL_TCGEN05, HGR_IMPL_TCGEN05_RELOAD,  # noqa: F401
-                    HGR_NUM_HITS)
+                    HGR_IMPL_TCGEN05_EXACT, HGR_IMPL_TCGEN05_NULL, HGR_NUM_HITS)
 
 _DTYPE_CODE = {torch.float32: _cabi.HGR_F32, torch.bfloat16: _cabi.HGR_BF16, torch.float16: _cabi.HGR_F16}
 _workspaces = {}
@@ -41,6 +41,14 @@ def _workspace(nbytes: int, device) -> torch.Tensor:
         ws = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
         _workspaces[key] = ws
     return ws
+
+
+def last_rescan_count(device=None) -> int:
+    """Rows the last tcgen05 ``score_topk`` call on this stream re-scanned exactly (speculative lists that
+    could not be certified).  Diagnostics: reads 4 bytes back from the workspace (synchronises)."""
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    ws = _workspaces.get((device.type, device.index, torch.cuda.current_stream().cuda_stream))
+    return 0 if ws is None else int(ws[:4].view(torch.int32).item())
 
 
 def new_hits(device) -> torch.Tensor:

@@ -49,6 +49,8 @@ extern "C" {
 #define HGR_IMPL_SIMT 1     /* CUDA-core kernel: any shape, exactness fallback and debug aid */
 #define HGR_IMPL_TCGEN05 2  /* TMA + tcgen05/TMEM kernel with fused top-k epilogue           */
 #define HGR_IMPL_TCGEN05_RELOAD 3 /* same kernel, simpler epilogue variant (kept as a cross-check) */
+#define HGR_IMPL_TCGEN05_EXACT 4  /* production kernel with speculation off: every list holds K entries */
+#define HGR_IMPL_TCGEN05_NULL 5   /* diagnostics: GEMM main loop with a trivial epilogue; outputs untouched */
 /* OR-ed into `impl`: run only the GEMM + fused top-k kernel and leave the per-CTA partial lists in
  * the workspace (outputs untouched).  Lets bench.py time the dominant kernel alone for the roofline. */
 #define HGR_IMPL_FLAG_NO_MERGE 0x100

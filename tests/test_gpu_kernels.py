@@ -21,7 +21,8 @@ def _load():
     assert torch.cuda.is_available(), "GPU tests need a CUDA device"
     from hgrnet_b200 import ops as _ops
     ops = _ops
-    IMPLS = {"simt": ops.HGR_IMPL_SIMT, "tcgen05": ops.HGR_IMPL_TCGEN05, "tcgen05_reload": ops.HGR_IMPL_TCGEN05_RELOAD}
+    IMPLS = {"simt": ops.HGR_IMPL_SIMT, "tcgen05": ops.HGR_IMPL_TCGEN05, "tcgen05_reload": ops.HGR_IMPL_TCGEN05_RELOAD,
+             "tcgen05_exact": ops.HGR_IMPL_TCGEN05_EXACT}
     yield
     torch.cuda.synchronize()
 
@@ -116,7 +117,7 @@ SHAPES = [
 ]
 
 
-@pytest.mark.parametrize("impl", ["simt", "tcgen05", "tcgen05_reload"])
+@pytest.mark.parametrize("impl", ["simt", "tcgen05", "tcgen05_reload", "tcgen05_exact"])
 @pytest.mark.parametrize("B,C,D", SHAPES)
 def test_score_topk_matches_oracle(impl, B, C, D):
     K = 20
@@ -157,7 +158,7 @@ def test_score_topk_tie_order_is_value_desc_then_row_asc():
     w = _emb(C // 2, D, 32).repeat(2, 1)  # row c and row c + C/2 are identical
     xn = ops.normalize_rows(x.to(DEV))
     outs = []
-    for impl in ("simt", "tcgen05", "tcgen05_reload"):
+    for impl in ("simt", "tcgen05_exact", "tcgen05_reload", "tcgen05"):
         val, idx = ops.score_topk(xn, w.to(DEV).bfloat16(), K=20, impl=IMPLS[impl])
         v, i = val.cpu(), idx.cpu().long()
         same = v[:, :-1] == v[:, 1:]
@@ -166,6 +167,7 @@ def test_score_topk_tie_order_is_value_desc_then_row_asc():
         outs.append((v, i))
     # the two tcgen05 epilogues see bit-identical accumulators: identical lists, ties included
     assert torch.equal(outs[1][1], outs[2][1]) and torch.equal(outs[1][0], outs[2][0])
+    assert torch.equal(outs[1][1], outs[3][1]) and torch.equal(outs[1][0], outs[3][0])
 
 
 def test_score_topk_implementations_agree_at_cfg2_size():
@@ -183,6 +185,33 @@ def test_score_topk_implementations_agree_at_cfg2_size():
     t2 = compare_topk(v2, i2, logits, torch.arange(C), K)
     assert (i1 != i2).any(1).sum() <= t1 + t2
     assert h1.tolist() == hits_from_idx(i1, targets)
+
+
+def test_speculative_lists_are_certified_or_rescanned_exactly():
+    """At cfg 2 size a row is split over 74 lists, so the production kernel keeps SPECULATIVE 8-entry lists.
+    (a) random bank order: every row certifies, no re-scan; (b) an adversarial bank whose best classes sit in
+    adjacent rows overflows single lists: the merge must detect it and re-scan those rows exactly."""
+    B, C, D, K = 512, 21841, 1024, 20
+    x, w = _emb(B, D, 51), _emb(C, D, 52)
+    xn = ops.normalize_rows(x.to(DEV))
+    v0, i0 = ops.score_topk(xn, w.to(DEV).bfloat16(), K=K, impl=IMPLS["tcgen05"])
+    assert ops.last_rescan_count(DEV) == 0
+    v1, i1 = ops.score_topk(xn, w.to(DEV).bfloat16(), K=K, impl=IMPLS["tcgen05_exact"])
+    assert torch.equal(i0, i1) and torch.equal(v0, v1)          # speculation never changes the result
+    # adversarial: rows 5000..5039 of the bank are all close to the mean image direction
+    w2 = w.clone()
+    mean_dir = x.mean(0)
+    mean_dir = mean_dir / mean_dir.norm()
+    noise = _emb(40, D, 53)
+    w2[5000:5040] = ((mean_dir[None, :] * 3 + noise) / (mean_dir[None, :] * 3 + noise).norm(dim=-1, keepdim=True)
+                     ).to(torch.bfloat16).float()
+    v2, i2 = ops.score_topk(xn, w2.to(DEV).bfloat16(), K=K, impl=IMPLS["tcgen05"])
+    rescans = ops.last_rescan_count(DEV)
+    assert rescans > 0, "the adversarial bank should overflow at least one speculative list"
+    logits = xn.float().cpu() @ w2.T
+    compare_topk(v2, i2, logits, torch.arange(C), K)
+    v3, i3 = ops.score_topk(xn, w2.to(DEV).bfloat16(), K=K, impl=IMPLS["tcgen05_exact"])
+    assert (i2 != i3).any(1).sum() <= 2                         # re-scanned rows use CUDA-core sums: near-ties may swap
 
 
 def test_score_topk_empty_and_bad_args():
