@@ -23,8 +23,10 @@ namespace hgr {
 namespace {
 
 constexpr int kMergeWarps = 4;
-constexpr int kMaxListsPerLane = 4;  // P <= 128
 
+// kMaxListsPerLane: 4 covers P <= 128 lists per row, 10 covers P <= 320 (one list per epilogue warp of
+// every CTA when a single row tile is spread over all 148 SMs)
+template <int kMaxListsPerLane>
 __global__ void __launch_bounds__(kMergeWarps * 32)
 topk_merge_kernel(const MergeArgs a) {
   extern __shared__ uint8_t smem_raw[];
@@ -173,20 +175,26 @@ topk_merge_kernel(const MergeArgs a) {
 
 int launch_topk_merge(const MergeArgs& args, cudaStream_t stream) {
   if (args.B == 0 || args.K == 0) return HGR_OK;
-  if (args.P > 32 * kMaxListsPerLane)
-    return set_error(HGR_ERR_UNSUPPORTED, "topk merge: %lld lists per row exceed %d", (long long)args.P,
-                     32 * kMaxListsPerLane);
+  if (args.P > 320)
+    return set_error(HGR_ERR_UNSUPPORTED, "topk merge: %lld lists per row exceed 320", (long long)args.P);
   if (args.K > HGR_TOPK_MAX || args.KL < 1)
     return set_error(HGR_ERR_UNSUPPORTED, "topk merge: K = %d / KL = %d unsupported", args.K, args.KL);
   if (args.KL < args.K && (args.X == nullptr || args.bank == nullptr))
     return set_error(HGR_ERR_BAD_ARG, "topk merge: speculative lists need X / bank for the exact re-scan");
   const size_t smem = static_cast<size_t>(kMergeWarps) * args.P * args.KL * 8;
   if (smem > 200 * 1024) return set_error(HGR_ERR_UNSUPPORTED, "topk merge: %zu bytes of lists per CTA", smem);
-  if (smem > 48 * 1024)
-    HGR_CHECK_CUDA(cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        static_cast<int>(smem)));
   const int blocks = static_cast<int>((args.B + kMergeWarps - 1) / kMergeWarps);
-  topk_merge_kernel<<<blocks, kMergeWarps * 32, smem, stream>>>(args);
+  if (args.P <= 128) {
+    if (smem > 48 * 1024)
+      HGR_CHECK_CUDA(cudaFuncSetAttribute(topk_merge_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          static_cast<int>(smem)));
+    topk_merge_kernel<4><<<blocks, kMergeWarps * 32, smem, stream>>>(args);
+  } else {
+    if (smem > 48 * 1024)
+      HGR_CHECK_CUDA(cudaFuncSetAttribute(topk_merge_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          static_cast<int>(smem)));
+    topk_merge_kernel<10><<<blocks, kMergeWarps * 32, smem, stream>>>(args);
+  }
   HGR_CHECK_LAUNCH();
   return HGR_OK;
 }
