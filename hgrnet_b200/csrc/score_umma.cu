@@ -30,26 +30,15 @@
 
 #include <cmath>
 
-#include "common.cuh"
-#include "ptx.cuh"
-#include "topk_list.cuh"
+#include "umma_common.cuh"
 
 namespace hgr {
+using namespace umma;
 namespace {
 
-constexpr int kBlockK = 64;                         // bf16 per K block: 128 bytes = one swizzle row
-constexpr int kUmmaK = 16;                          // K of one tcgen05.mma.kind::f16
 constexpr int kStages = 4;
-constexpr int kABytes = kTileM * kBlockK * 2;       // 16 KB
 constexpr int kBBytes = kSubN * kBlockK * 2;        // 32 KB
 constexpr int kStageBytes = kABytes + kBBytes;      // 48 KB
-constexpr int kBBoxRows = 64;                       // bank rows per TMA box
-constexpr int kBBoxBytes = kBBoxRows * kBlockK * 2; // 8 KB
-constexpr int kEpiWarp0 = 2;
-constexpr int kTmemCols = 512;
-constexpr int kChunk = 32;                          // accumulator columns per tcgen05.ld
-
-enum EpiMode { kEpiDense = 0, kEpiTopkReload = 1, kEpiTopkQueue = 2, kEpiNull = 3 };
 
 struct Ctl {
   uint64_t full[kStages];
@@ -58,112 +47,6 @@ struct Ctl {
   uint64_t tmem_empty[2];
   uint32_t tmem_base;
 };
-
-struct SubTile {
-  int mt;      // row tile
-  int col0;    // first bank row
-  int n;       // MMA N (multiple of 16)
-  int nvalid;  // bank rows < C inside the sub-tile
-  bool first;  // first sub-tile of a (row tile, CTA) segment
-  bool last;   // last sub-tile of the segment
-};
-
-struct TileWalker {
-  int64_t u, u_end;
-  int U;
-  int64_t C;
-  bool first;
-  __device__ TileWalker(const Sched& s, int cta, int64_t C_)
-      : u(s.unit_begin(cta)), u_end(s.unit_begin(cta + 1)), U(s.U), C(C_), first(true) {}
-  __device__ bool next(SubTile& t) {
-    if (u >= u_end) return false;
-    const int mt = static_cast<int>(u / U);
-    int uu = static_cast<int>(u - static_cast<int64_t>(mt) * U);
-    int nu = kSubN / kUnit;
-    if (U - uu < nu) nu = U - uu;
-    if (u_end - u < nu) nu = static_cast<int>(u_end - u);
-    t.mt = mt;
-    t.col0 = uu * kUnit;
-    t.n = nu * kUnit;
-    const int64_t left = C - t.col0;
-    t.nvalid = left < t.n ? static_cast<int>(left) : t.n;
-    t.first = first;
-    u += nu;
-    uu += nu;
-    t.last = (u >= u_end) || (uu == U);
-    first = t.last;
-    return true;
-  }
-};
-
-struct Params {
-  Sched sched;
-  int64_t B, C;
-  int num_k_blocks;
-  int KL;              // entries written per list
-  float scale;
-  float* part_val;     // [slots][B][KL]
-  int32_t* part_idx;   // [slots][B][KL] bank rows
-  float* dense_out;    // [B][ldo]
-  int64_t ldo;
-  unsigned int* stats; // [0] = rows re-scanned by the merge kernel of this call (reset here)
-};
-
-template <int KL>
-__device__ __forceinline__ void scan_chunk_reload(SortedList<KL>& list, const uint32_t (&r)[kChunk], int nv,
-                                                  uint32_t taddr_chunk, int col_chunk) {
-  const float thr = list.thr();
-  uint32_t m = 0;
-#pragma unroll
-  for (int j = 0; j < kChunk; ++j)
-    if (__uint_as_float(r[j]) > thr) m |= (1u << j);
-  if (nv < kChunk) m &= (1u << nv) - 1u;
-  uint32_t wm = __reduce_or_sync(0xffffffffu, m);
-  // visit the union of positions in ascending order; each lane re-reads its own value of that
-  // column from TMEM (the address is warp-uniform) and inserts if it still qualifies
-  while (wm) {
-    const int j = __ffs(wm) - 1;
-    wm &= wm - 1;
-    const float x = __uint_as_float(ptx::tmem_ld_x1(taddr_chunk + j));
-    ptx::tmem_ld_wait();
-    if (((m >> j) & 1u) && x > list.thr()) list.insert(x, col_chunk + j);
-  }
-}
-
-// queue: this thread's column of the [kChunk][epilogue threads] fp32 staging array
-template <int KL, int QSTRIDE>
-__device__ __forceinline__ void scan_chunk_queue(SortedList<KL>& list, const uint32_t (&r)[kChunk], int nv,
-                                                 int col_chunk, float* queue) {
-  // 1) lane-private compaction of the values that beat the KL-th best at chunk entry:
-  //    values go to the queue in column order, their positions into a bit mask
-  const float thr = list.thr();
-  uint32_t m = 0;
-  int cnt = 0;
-#pragma unroll
-  for (int j = 0; j < kChunk; ++j) {
-    const float x = __uint_as_float(r[j]);
-    if (x > thr) {
-      queue[cnt * QSTRIDE] = x;
-      ++cnt;
-      m |= (1u << j);
-    }
-  }
-  if (nv < kChunk) {  // ragged tail: columns >= C were zero-filled by TMA, drop them
-    m &= (1u << nv) - 1u;
-    cnt = __popc(m);
-  }
-  // 2) dense drain: lanes walk their own queues in lock-step, so the (long) insert body runs
-  //    max_lane(cnt) times instead of once per column any lane hit
-  const int maxc = __reduce_max_sync(0xffffffffu, cnt);
-  for (int e = 0; e < maxc; ++e) {
-    if (e < cnt) {
-      const float x = queue[e * QSTRIDE];
-      const int j = __ffs(m) - 1;
-      m &= m - 1;
-      if (x > list.thr()) list.insert(x, col_chunk + j);
-    }
-  }
-}
 
 template <int EPI, int KL, int WPQ>
 __global__ void __launch_bounds__(64 + 128 * WPQ, 1)
@@ -272,7 +155,7 @@ score_umma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     const int member = (warp - kEpiWarp0) >> 2;         // which of the WPQ warps of that quarter
     const int row_in_tile = quarter * 32 + lane;
     const int epi_tid = (warp - kEpiWarp0) * 32 + lane;
-    float* queue = queue_base + epi_tid;
+    const uint32_t qaddr = ptx::smem_u32(queue_base + epi_tid);
     TileWalker walk(p.sched, cta, p.C);
     SubTile t;
     SortedList<KL> list;
@@ -285,9 +168,11 @@ score_umma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + buf * kSubN;
       const int64_t row = static_cast<int64_t>(t.mt) * kTileM + row_in_tile;
+      bool seed = false;  // the first chunk this warp sees of a segment seeds the empty list
       if (t.first) {
         list.init();
         null_acc = -INFINITY;
+        seed = true;
       }
       for (int c0 = member * kChunk; c0 < t.nvalid; c0 += WPQ * kChunk) {
         uint32_t r[kChunk];
@@ -304,7 +189,14 @@ score_umma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
         } else if (EPI == kEpiTopkReload) {
           scan_chunk_reload<KL>(list, r, nv, taddr + c0, t.col0 + c0);
         } else if (EPI == kEpiTopkQueue) {
-          scan_chunk_queue<KL, kEpiThreads>(list, r, nv, t.col0 + c0, queue);
+          constexpr int kSeed = KL < 8 ? KL : 8;
+          if (seed && nv >= kChunk) {
+            SeedPrefix<KL, kSeed>::run(list, r, t.col0 + c0);
+            scan_chunk_queue<KL, kEpiThreads * 4, kSeed>(list, r, nv, t.col0 + c0, qaddr);
+          } else {
+            scan_chunk_queue<KL, kEpiThreads * 4, 0>(list, r, nv, t.col0 + c0, qaddr);
+          }
+          seed = false;
         } else {
 #pragma unroll
           for (int j = 0; j < kChunk; ++j) null_acc = fmaxf(null_acc, __uint_as_float(r[j]));
@@ -387,13 +279,17 @@ int launch_kernel(const CUtensorMap& mx, const CUtensorMap& mb, const Params& p,
   return HGR_OK;
 }
 
-int common_setup(const __nv_bfloat16* X, const __nv_bfloat16* bank, int64_t B, int64_t C, int64_t D, CUtensorMap* mx,
-                 CUtensorMap* mb, Params* p) {
+Sched pick_sched(int64_t B, int64_t C, bool pair) {
+  return pair ? make_sched(B, C, num_sms() / 2, 2 * kTileM) : make_sched(B, C, num_sms(), kTileM);
+}
+
+int common_setup(const __nv_bfloat16* X, const __nv_bfloat16* bank, int64_t B, int64_t C, int64_t D, bool pair,
+                 CUtensorMap* mx, CUtensorMap* mb, Params* p) {
   int rc = make_map(mx, X, B, D, kTileM);
   if (rc != HGR_OK) return rc;
   rc = make_map(mb, bank, C, D, kBBoxRows);
   if (rc != HGR_OK) return rc;
-  p->sched = make_sched(B, C, num_sms());
+  p->sched = pick_sched(B, C, pair);
   p->B = B;
   p->C = C;
   p->num_k_blocks = static_cast<int>((D + kBlockK - 1) / kBlockK);
@@ -433,53 +329,58 @@ bool umma_supported(int64_t B, int64_t C, int64_t D, int K) {
 }
 
 size_t umma_score_workspace_bytes(int64_t B, int64_t C, int K) {
-  const Sched s = make_sched(B, C, num_sms());
-  // worst case over the list-width policy: exact lists of up to HGR_TOPK_MAX entries
+  // worst case over the kernel variants (single CTA / CTA pair) and the list-width policy (exact lists)
+  const int p1 = pick_sched(B, C, false).P * kWpq, p2 = pick_sched(B, C, true).P * kPairWpq;
   const int kl = K <= 8 ? 8 : (K <= 12 ? 12 : (K <= 20 ? 20 : 32));
-  return static_cast<size_t>(s.P) * kWpq * B * kl * (sizeof(float) + sizeof(int32_t)) + 64;
+  return static_cast<size_t>(p1 > p2 ? p1 : p2) * B * kl * (sizeof(float) + sizeof(int32_t)) + 64;
 }
 
 int launch_score_topk_umma(const __nv_bfloat16* X, const __nv_bfloat16* bank, const int32_t* col_id,
                            int32_t id_base, const int32_t* targets, int64_t B, int64_t C, int64_t D, float scale,
                            int K, void* ws, size_t ws_bytes, float* topk_val, int32_t* topk_idx, int64_t* hits,
                            int variant, bool skip_merge, cudaStream_t stream) {
+  // variants: 0 = production: CTA-pair kernel, queue epilogue, speculative lists when provably safe
+  //           1 = single-CTA kernel, reload epilogue, 1 warp/quarter, exact lists (cross-check)
+  //           2 = production kernel with exact lists (no speculation)
+  //           3 = production main loop with a null epilogue (ceiling; NOT a top-k) -- diagnostics only
+  //           4 = single-CTA kernel, queue epilogue, speculative lists (the pre-pair production kernel)
+  //           5 = single-CTA main loop with a null epilogue -- diagnostics only
+  const bool pair = (variant == 0 || variant == 2 || variant == 3) && num_sms() >= 2;
   CUtensorMap mx, mb;
   Params p{};
-  int rc = common_setup(X, bank, B, C, D, &mx, &mb, &p);
+  int rc = common_setup(X, bank, B, C, D, pair, &mx, &mb, &p);
   if (rc != HGR_OK) return rc;
   if (ws == nullptr || ws_bytes < umma_score_workspace_bytes(B, C, K))
     return set_error(HGR_ERR_WORKSPACE, "hgr_score_topk(tcgen05): workspace %zu < %zu bytes", ws_bytes,
                      umma_score_workspace_bytes(B, C, K));
-  // variants: 0 = production (queue epilogue, kWpq warps/quarter, speculative lists when safe)
-  //           1 = reload epilogue, 1 warp/quarter, exact lists (cross-check)
-  //           2 = queue epilogue, exact lists (no speculation)
-  //           3 = null epilogue (main-loop ceiling; results are NOT a top-k) -- bench diagnostics only
-  const int wpq = variant == 1 ? 1 : kWpq;
+  const int wpq = variant == 1 ? 1 : (pair ? kPairWpq : kWpq);
   const int lists = p.sched.P * wpq;
-  const int KL = pick_list_len(K, B, lists, variant == 0);
+  const int KL = pick_list_len(K, B, lists, variant == 0 || variant == 4);
   p.KL = KL;
   p.scale = scale;
   p.stats = static_cast<unsigned int*>(ws);                              // first 64 bytes: statistics
   p.part_val = reinterpret_cast<float*>(static_cast<uint8_t*>(ws) + 64);
   p.part_idx = reinterpret_cast<int32_t*>(p.part_val + static_cast<size_t>(lists) * B * KL);
-  if (variant == 3) {
-    rc = launch_kernel<kEpiNull, 8, kWpq>(mx, mb, p, stream);
-    return rc;
-  }
+  if (variant == 3) return launch_pair_kernel(kEpiNull, 8, mx, mb, p, stream);
+  if (variant == 5) return launch_kernel<kEpiNull, 8, kWpq>(mx, mb, p, stream);
+  if (pair) {
+    rc = launch_pair_kernel(kEpiTopkQueue, KL, mx, mb, p, stream);
+  } else {
 #define HGR_UMMA_CASE(KLV)                                                                            \
   case KLV:                                                                                           \
     rc = variant == 1 ? launch_kernel<kEpiTopkReload, KLV, 1>(mx, mb, p, stream)                      \
                       : launch_kernel<kEpiTopkQueue, KLV, kWpq>(mx, mb, p, stream);                   \
     break
-  switch (KL) {
-    HGR_UMMA_CASE(8);
-    HGR_UMMA_CASE(12);
-    HGR_UMMA_CASE(20);
-    HGR_UMMA_CASE(32);
-    default:
-      return set_error(HGR_ERR_UNSUPPORTED, "hgr_score_topk(tcgen05): list length %d", KL);
-  }
+    switch (KL) {
+      HGR_UMMA_CASE(8);
+      HGR_UMMA_CASE(12);
+      HGR_UMMA_CASE(20);
+      HGR_UMMA_CASE(32);
+      default:
+        return set_error(HGR_ERR_UNSUPPORTED, "hgr_score_topk(tcgen05): list length %d", KL);
+    }
 #undef HGR_UMMA_CASE
+  }
   if (rc != HGR_OK || skip_merge) return rc;
   MergeArgs m{};
   m.part_val = p.part_val;
@@ -508,14 +409,16 @@ int launch_score_topk_umma(const __nv_bfloat16* X, const __nv_bfloat16* bank, co
 
 int launch_logits_umma(const __nv_bfloat16* X, const __nv_bfloat16* bank, int64_t B, int64_t C, int64_t D,
                        float scale, float* out, int64_t ldo, cudaStream_t stream) {
+  const bool pair = num_sms() >= 2 && getenv("HGR_DENSE_1CTA") == nullptr;
   CUtensorMap mx, mb;
   Params p{};
-  int rc = common_setup(X, bank, B, C, D, &mx, &mb, &p);
+  int rc = common_setup(X, bank, B, C, D, pair, &mx, &mb, &p);
   if (rc != HGR_OK) return rc;
   p.KL = 0;
   p.scale = scale;
   p.dense_out = out;
   p.ldo = ldo;
+  if (pair) return launch_pair_kernel(kEpiDense, 8, mx, mb, p, stream);
   return launch_kernel<kEpiDense, 8, kWpq>(mx, mb, p, stream);
 }
 

@@ -1,0 +1,256 @@
+// Kernel (2), CTA-pair variant: the same fused GEMM + top-K head as score_umma.cu, but two CTAs of
+// a cluster (one TPC) share every MMA -- tcgen05.mma.cta_group::2 with M = 256.
+//
+// Why: a single-CTA 128 x 256 tile needs (128 + 256) x 64 x 2 B = 48 KB of operands per K block,
+// 96 B/clk/SM at the tensor core's issue rate, and the L2 -> SM path of this chip delivers ~50
+// B/clk/SM (measured: the single-CTA kernel with a null epilogue tops out at 14.4 TB/s of TMA
+// reads, profiles/).  In a pair each CTA contributes its own 128 image rows (A) but only HALF of
+// the bank sub-tile (B): 32 KB per K block per CTA for the same 128 x 256 outputs per CTA.
+//
+// Layout per CTA: A stage [128 x 64] bf16 (own rows), B stage [<=128 x 64] (leader: bank rows
+// [col0, col0 + n/2), peer: [col0 + n/2, col0 + n)), both 128B-swizzled; TMEM 2 x 256 columns,
+// each CTA holding the accumulators of its own 128 rows x all n columns.
+// Protocol: both producers signal the LEADER's `full` barrier (cp.async.bulk.tensor
+// .cta_group::2); the leader's single MMA thread commits with a cluster multicast to the `empty`
+// and `tmem_full` barriers of both CTAs; the epilogue warps of both CTAs arrive on the leader's
+// `tmem_empty`.  Epilogue and work split are shared with the single-CTA kernel (umma_common.cuh).
+#include "umma_common.cuh"
+
+namespace hgr {
+namespace umma {
+namespace {
+
+constexpr int kPairStages = 6;
+constexpr int kPairBBytes = (kSubN / 2) * kBlockK * 2;     // 16 KB: half of the bank sub-tile
+constexpr int kPairStageBytes = kABytes + kPairBBytes;     // 32 KB
+
+struct PairCtl {
+  uint64_t full[kPairStages];      // leader's copy is the one in use
+  uint64_t empty[kPairStages];     // per CTA, signalled by the leader's multicast commit
+  uint64_t tmem_full[2];           // per CTA, multicast commit
+  uint64_t tmem_empty[2];          // leader's copy: arrivals from the epilogue warps of both CTAs
+  uint32_t tmem_base;
+};
+
+template <int EPI, int KL, int WPQ>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 128 * WPQ, 1)
+score_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_bank,
+                       const Params p) {
+  constexpr int kEpiThreads = 128 * WPQ;
+  constexpr int kQueueBytes = EPI == kEpiTopkQueue ? kChunk * kEpiThreads * 4 : 0;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* stage_base = smem;
+  float* queue_base = reinterpret_cast<float*>(smem + kPairStages * kPairStageBytes);
+  PairCtl* ctl = reinterpret_cast<PairCtl*>(smem + kPairStages * kPairStageBytes + kQueueBytes);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = ptx::cluster_ctarank();  // 0 = leader (issues the MMAs), 1 = peer
+  const int pair = blockIdx.x >> 1;
+
+  if (blockIdx.x == 0 && threadIdx.x == 0 && p.stats != nullptr) p.stats[0] = 0;
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&map_x);
+    ptx::prefetch_tensormap(&map_bank);
+    for (int s = 0; s < kPairStages; ++s) {
+      ptx::mbar_init(&ctl->full[s], 1);
+      ptx::mbar_init(&ctl->empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      ptx::mbar_init(&ctl->tmem_full[b], 1);
+      ptx::mbar_init(&ctl->tmem_empty[b], 2 * (kEpiThreads / 32));
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc_cg2(&ctl->tmem_base, kTmemCols);
+    ptx::tmem_relinquish_cg2();
+  }
+  ptx::tc_fence_before();
+  ptx::cluster_sync_all();  // barriers of both CTAs initialised, TMEM allocated
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = ctl->tmem_base;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      const uint64_t pol = ptx::policy_evict_last();
+      TileWalker walk(p.sched, pair, p.C);
+      SubTile t;
+      int stage = 0;
+      uint32_t phase = 0;
+      while (walk.next(t)) {
+        const int half = t.n >> 1;                                   // bank rows this CTA feeds
+        const int nbox = (half + kBBoxRows - 1) / kBBoxRows;
+        const int row0 = t.mt * (2 * kTileM) + static_cast<int>(rank) * kTileM;
+        const int bcol0 = t.col0 + static_cast<int>(rank) * half;
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          ptx::mbar_wait(&ctl->empty[stage], phase ^ 1u);
+          uint8_t* sa = stage_base + stage * kPairStageBytes;
+          uint8_t* sb = sa + kABytes;
+          const uint32_t full_leader = ptx::mapa_shared(ptx::smem_u32(&ctl->full[stage]), 0);
+          if (rank == 0) ptx::mbar_arrive_expect_tx(&ctl->full[stage], 2 * (kABytes + nbox * kBBoxBytes));
+          ptx::tma_load_2d_cg2(sa, &map_x, full_leader, kb * kBlockK, row0, pol);
+          for (int b = 0; b < nbox; ++b)
+            ptx::tma_load_2d_cg2(sb + b * kBBoxBytes, &map_bank, full_leader, kb * kBlockK, bcol0 + b * kBBoxRows,
+                                 pol);
+          if (++stage == kPairStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (rank == 0 && lane == 0) {
+      TileWalker walk(p.sched, pair, p.C);
+      SubTile t;
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      while (walk.next(t)) {
+        const int buf = it & 1;
+        ptx::mbar_wait(&ctl->tmem_empty[buf], ((it >> 1) & 1) ^ 1u);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + buf * kSubN;
+        const uint32_t idesc = ptx::umma_idesc_bf16(2 * kTileM, t.n);
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          ptx::mbar_wait(&ctl->full[stage], phase);
+          ptx::tc_fence_after();
+          const uint32_t a_addr = ptx::smem_u32(stage_base + stage * kPairStageBytes);
+          const uint32_t b_addr = a_addr + kABytes;
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+            const uint64_t adesc = ptx::umma_smem_desc_sw128(a_addr + k * kUmmaK * 2);
+            const uint64_t bdesc = ptx::umma_smem_desc_sw128(b_addr + k * kUmmaK * 2);
+            ptx::umma_bf16_cg2(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          ptx::umma_commit_cg2_mc(&ctl->empty[stage], 0x3);  // frees this stage in both CTAs
+          if (++stage == kPairStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        ptx::umma_commit_cg2_mc(&ctl->tmem_full[buf], 0x3);  // accumulators of both CTAs complete
+        ++it;
+      }
+    }
+  } else {
+    // ===================== epilogue (both CTAs, own 128 rows each) =====================
+    const int quarter = warp & 3;
+    const int member = (warp - kEpiWarp0) >> 2;
+    const int row_in_tile = static_cast<int>(rank) * kTileM + quarter * 32 + lane;
+    const int epi_tid = (warp - kEpiWarp0) * 32 + lane;
+    const uint32_t qaddr = ptx::smem_u32(queue_base + epi_tid);
+    TileWalker walk(p.sched, pair, p.C);
+    SubTile t;
+    SortedList<KL> list;
+    list.init();
+    float null_acc = -INFINITY;
+    int it = 0;
+    while (walk.next(t)) {
+      const int buf = it & 1;
+      ptx::mbar_wait(&ctl->tmem_full[buf], (it >> 1) & 1);
+      ptx::tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + buf * kSubN;
+      const int64_t row = static_cast<int64_t>(t.mt) * (2 * kTileM) + row_in_tile;
+      bool seed = false;
+      if (t.first) {
+        list.init();
+        null_acc = -INFINITY;
+        seed = true;
+      }
+      for (int c0 = member * kChunk; c0 < t.nvalid; c0 += WPQ * kChunk) {
+        uint32_t r[kChunk];
+        ptx::tmem_ld_x32(taddr + c0, r);
+        ptx::tmem_ld_wait();
+        const int nv = t.nvalid - c0;
+        if (EPI == kEpiDense) {
+          if (row < p.B) {
+            float* o = p.dense_out + row * p.ldo + t.col0 + c0;
+#pragma unroll
+            for (int j = 0; j < kChunk; ++j)
+              if (j < nv) o[j] = __uint_as_float(r[j]) * p.scale;
+          }
+        } else if (EPI == kEpiTopkQueue) {
+          constexpr int kSeed = KL < 8 ? KL : 8;
+          if (seed && nv >= kChunk) {
+            SeedPrefix<KL, kSeed>::run(list, r, t.col0 + c0);
+            scan_chunk_queue<KL, kEpiThreads * 4, kSeed>(list, r, nv, t.col0 + c0, qaddr);
+          } else {
+            scan_chunk_queue<KL, kEpiThreads * 4, 0>(list, r, nv, t.col0 + c0, qaddr);
+          }
+          seed = false;
+        } else {
+#pragma unroll
+          for (int j = 0; j < kChunk; ++j) null_acc = fmaxf(null_acc, __uint_as_float(r[j]));
+        }
+      }
+      // this CTA's half of the accumulator buffer is drained: tell the leader's MMA thread
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (rank == 0) ptx::mbar_arrive(&ctl->tmem_empty[buf]);
+        else ptx::mbar_arrive_cluster(ptx::mapa_shared(ptx::smem_u32(&ctl->tmem_empty[buf]), 0));
+      }
+      if (EPI != kEpiDense && t.last && row < p.B) {
+        const int slot = (pair - p.sched.first_cta(t.mt)) * WPQ + member;
+        float* pv = p.part_val + (static_cast<int64_t>(slot) * p.B + row) * p.KL;
+        int32_t* pi = p.part_idx + (static_cast<int64_t>(slot) * p.B + row) * p.KL;
+        if (EPI == kEpiNull) {
+          pv[0] = null_acc;
+          pi[0] = -1;
+        } else {
+#pragma unroll
+          for (int k = 0; k < KL; ++k) {
+            if (k < p.KL) {
+              pv[k] = list.v[k];
+              pi[k] = list.i[k];
+            }
+          }
+        }
+      }
+      ++it;
+    }
+  }
+
+  // no CTA may exit (or free TMEM) while its partner can still signal its barriers or read its memory
+  ptx::tc_fence_before();
+  ptx::cluster_sync_all();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc_cg2(tmem_base, kTmemCols);
+  }
+}
+
+template <int EPI, int KL, int WPQ>
+int launch_one(const CUtensorMap& mx, const CUtensorMap& mb, const Params& p, cudaStream_t stream) {
+  constexpr int threads = 64 + 128 * WPQ;
+  const size_t smem = 1024 + static_cast<size_t>(kPairStages) * kPairStageBytes +
+                      (EPI == kEpiTopkQueue ? static_cast<size_t>(kChunk) * 128 * WPQ * 4 : 0) + sizeof(PairCtl);
+  auto kern = score_umma_pair_kernel<EPI, KL, WPQ>;
+  HGR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  kern<<<2 * p.sched.G, threads, smem, stream>>>(mx, mb, p);
+  HGR_CHECK_LAUNCH();
+  return HGR_OK;
+}
+
+}  // namespace
+
+int launch_pair_kernel(int epi, int KL, const CUtensorMap& mx, const CUtensorMap& mb, const Params& p,
+                       cudaStream_t stream) {
+  if (epi == kEpiDense) return launch_one<kEpiDense, 8, kPairWpq>(mx, mb, p, stream);
+  if (epi == kEpiNull) return launch_one<kEpiNull, 8, kPairWpq>(mx, mb, p, stream);
+  switch (KL) {
+    case 8: return launch_one<kEpiTopkQueue, 8, kPairWpq>(mx, mb, p, stream);
+    case 12: return launch_one<kEpiTopkQueue, 12, kPairWpq>(mx, mb, p, stream);
+    case 20: return launch_one<kEpiTopkQueue, 20, kPairWpq>(mx, mb, p, stream);
+    case 32: return launch_one<kEpiTopkQueue, 32, kPairWpq>(mx, mb, p, stream);
+  }
+  return set_error(HGR_ERR_UNSUPPORTED, "hgr_score_topk(tcgen05 pair): list length %d", KL);
+}
+
+}  // namespace umma
+}  // namespace hgr

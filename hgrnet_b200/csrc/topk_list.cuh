@@ -25,6 +25,24 @@ struct SortedList {
   }
   __device__ __forceinline__ float thr() const { return v[KL - 1]; }
 
+  // Insert into a list whose slots >= S are known to be empty (-inf): touches S slots only.  Used to seed the
+  // list from the first columns of a segment at a fraction of the cost of full-depth inserts.
+  template <int S>
+  __device__ __forceinline__ void insert_prefix(float x, int32_t id) {
+    static_assert(S >= 1 && S <= KL, "prefix length");
+#pragma unroll
+    for (int j = S - 1; j >= 1; --j) {
+      const bool above = x > v[j - 1];
+      const bool here = x > v[j];
+      v[j] = above ? v[j - 1] : (here ? x : v[j]);
+      i[j] = above ? i[j - 1] : (here ? id : i[j]);
+    }
+    if (x > v[0]) {
+      v[0] = x;
+      i[0] = id;
+    }
+  }
+
   // pre-condition: x > thr().  Fully unrolled, branch-free (predicated selects).
   __device__ __forceinline__ void insert(float x, int32_t id) {
 #pragma unroll

@@ -46,7 +46,7 @@ topk_merge_kernel(const MergeArgs a) {
     const int64_t row = row0 + r;
     if (row >= a.B) break;
     int cnt = slots;
-    if (a.use_sched) cnt = a.sched.parts(static_cast<int32_t>(row / kTileM)) * a.wpq;
+    if (a.use_sched) cnt = a.sched.parts(static_cast<int32_t>(row / a.sched.rows)) * a.wpq;
     const int n = cnt * KL;
     for (int e = threadIdx.x; e < n; e += kMergeWarps * 32) {
       const int p = e / KL, k = e - p * KL;
@@ -60,7 +60,7 @@ topk_merge_kernel(const MergeArgs a) {
   const int64_t row = row0 + warp;
   if (row < a.B) {
     int cnt = slots;
-    if (a.use_sched) cnt = a.sched.parts(static_cast<int32_t>(row / kTileM)) * a.wpq;
+    if (a.use_sched) cnt = a.sched.parts(static_cast<int32_t>(row / a.sched.rows)) * a.wpq;
     const float* lv = s_val + warp * slots * KL;
     const int32_t* li = s_idx + warp * slots * KL;
 

@@ -12,7 +12,8 @@ import torch
 
 from . import _cabi
 from ._cabi import (HGR_IMPL_AUTO, HGR_IMPL_SIMT, HGR_IMPL_TCGEN05, HGR_IMPL_TCGEN05_RELOAD,  # noqa: F401
-                    HGR_IMPL_TCGEN05_EXACT, HGR_IMPL_TCGEN05_NULL, HGR_NUM_HITS)
+                    HGR_IMPL_TCGEN05_EXACT, HGR_IMPL_TCGEN05_NULL, HGR_IMPL_TCGEN05_1CTA, HGR_IMPL_TCGEN05_1CTA_NULL,
+                    HGR_NUM_HITS)
 
 _DTYPE_CODE = {torch.float32: _cabi.HGR_F32, torch.bfloat16: _cabi.HGR_BF16, torch.float16: _cabi.HGR_F16}
 _workspaces = {}

@@ -47,10 +47,12 @@ extern "C" {
 /* implementation selector of hgr_score_topk (all compute the same result) */
 #define HGR_IMPL_AUTO 0
 #define HGR_IMPL_SIMT 1     /* CUDA-core kernel: any shape, exactness fallback and debug aid */
-#define HGR_IMPL_TCGEN05 2  /* TMA + tcgen05/TMEM kernel with fused top-k epilogue           */
-#define HGR_IMPL_TCGEN05_RELOAD 3 /* same kernel, simpler epilogue variant (kept as a cross-check) */
+#define HGR_IMPL_TCGEN05 2  /* TMA + tcgen05/TMEM CTA-pair kernel (cta_group::2) with fused top-k epilogue */
+#define HGR_IMPL_TCGEN05_RELOAD 3 /* single-CTA kernel, simplest epilogue, exact lists (kept as a cross-check) */
 #define HGR_IMPL_TCGEN05_EXACT 4  /* production kernel with speculation off: every list holds K entries */
-#define HGR_IMPL_TCGEN05_NULL 5   /* diagnostics: GEMM main loop with a trivial epilogue; outputs untouched */
+#define HGR_IMPL_TCGEN05_NULL 5   /* diagnostics: production main loop, trivial epilogue; outputs untouched */
+#define HGR_IMPL_TCGEN05_1CTA 6   /* single-CTA (cta_group::1) kernel with the production epilogue */
+#define HGR_IMPL_TCGEN05_1CTA_NULL 7 /* diagnostics: single-CTA main loop, trivial epilogue */
 /* OR-ed into `impl`: run only the GEMM + fused top-k kernel and leave the per-CTA partial lists in
  * the workspace (outputs untouched).  Lets bench.py time the dominant kernel alone for the roofline. */
 #define HGR_IMPL_FLAG_NO_MERGE 0x100

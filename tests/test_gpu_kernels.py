@@ -22,7 +22,7 @@ def _load():
     from hgrnet_b200 import ops as _ops
     ops = _ops
     IMPLS = {"simt": ops.HGR_IMPL_SIMT, "tcgen05": ops.HGR_IMPL_TCGEN05, "tcgen05_reload": ops.HGR_IMPL_TCGEN05_RELOAD,
-             "tcgen05_exact": ops.HGR_IMPL_TCGEN05_EXACT}
+             "tcgen05_exact": ops.HGR_IMPL_TCGEN05_EXACT, "tcgen05_1cta": ops.HGR_IMPL_TCGEN05_1CTA}
     yield
     torch.cuda.synchronize()
 
@@ -117,7 +117,7 @@ SHAPES = [
 ]
 
 
-@pytest.mark.parametrize("impl", ["simt", "tcgen05", "tcgen05_reload", "tcgen05_exact"])
+@pytest.mark.parametrize("impl", ["simt", "tcgen05", "tcgen05_reload", "tcgen05_exact", "tcgen05_1cta"])
 @pytest.mark.parametrize("B,C,D", SHAPES)
 def test_score_topk_matches_oracle(impl, B, C, D):
     K = 20
@@ -158,7 +158,7 @@ def test_score_topk_tie_order_is_value_desc_then_row_asc():
     w = _emb(C // 2, D, 32).repeat(2, 1)  # row c and row c + C/2 are identical
     xn = ops.normalize_rows(x.to(DEV))
     outs = []
-    for impl in ("simt", "tcgen05_exact", "tcgen05_reload", "tcgen05"):
+    for impl in ("simt", "tcgen05_exact", "tcgen05_reload", "tcgen05", "tcgen05_1cta"):
         val, idx = ops.score_topk(xn, w.to(DEV).bfloat16(), K=20, impl=IMPLS[impl])
         v, i = val.cpu(), idx.cpu().long()
         same = v[:, :-1] == v[:, 1:]
@@ -168,6 +168,7 @@ def test_score_topk_tie_order_is_value_desc_then_row_asc():
     # the two tcgen05 epilogues see bit-identical accumulators: identical lists, ties included
     assert torch.equal(outs[1][1], outs[2][1]) and torch.equal(outs[1][0], outs[2][0])
     assert torch.equal(outs[1][1], outs[3][1]) and torch.equal(outs[1][0], outs[3][0])
+    assert torch.equal(outs[1][1], outs[4][1]) and torch.equal(outs[1][0], outs[4][0])
 
 
 def test_score_topk_implementations_agree_at_cfg2_size():
