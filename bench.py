@@ -224,14 +224,16 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, n, flush=None):
+    def timed(fn, n, flush=None, begin=None):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        if begin:
+            begin()                                 # worker streams start after e0
         for i in range(n):
             fn(i)
         if flush:
-            flush()
+            flush()                                 # ... and are joined into this stream before e1
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -241,46 +243,72 @@ def run_ours(args):
             ms = float(t)
         return ms
 
-    def graphed(fn, n_variants):
-        """One CUDA graph per rotation index: a step is a single cudaGraphLaunch (no interpreter on the path)."""
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
+    def graphed(fn, n_variants, n_streams=1):
+        """One CUDA graph per rotation index, replayed round-robin on `n_streams` streams (a step is a single
+        cudaGraphLaunch, no interpreter on the path).  Returns (step, begin, end)."""
+        sts = [torch.cuda.Stream() for _ in range(n_streams)]
+        cur = torch.cuda.current_stream()
         graphs = []
-        with torch.cuda.stream(side):
-            for i in range(n_variants):
-                fn(i)                                   # warm-up outside capture (workspace, attributes)
-            side.synchronize()
-            for i in range(n_variants):
-                gr = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(gr, stream=side):
-                    fn(i)
-                graphs.append(gr)
-        torch.cuda.current_stream().wait_stream(side)
+        for st in sts:
+            st.wait_stream(cur)
+        for i in range(n_variants):
+            with torch.cuda.stream(sts[i % n_streams]):
+                fn(i)                                   # warm-up outside capture (per-stream workspace, attributes)
         torch.cuda.synchronize()
-        return lambda i: graphs[i % n_variants].replay()
+        for i in range(n_variants):
+            st = sts[i % n_streams]
+            with torch.cuda.stream(st):
+                gr = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gr, stream=st):
+                    fn(i)
+            graphs.append(gr)
+        torch.cuda.synchronize()
+
+        def step(i):
+            with torch.cuda.stream(sts[(i % n_variants) % n_streams]):
+                graphs[i % n_variants].replay()
+
+        def begin():
+            for st in sts:
+                st.wait_stream(torch.cuda.current_stream())
+
+        def end():
+            for st in sts:
+                torch.cuda.current_stream().wait_stream(st)
+        return step, begin, end
 
     cycle = n_bank * n_feat // math.gcd(n_bank, n_feat)
+    n_streams = args.streams
     l0 = _cabi.launch_count()
     step_eager(0)
     drain()
     kernels_per_step = _cabi.launch_count() - l0
-    step_resident = graphed(step_eager, cycle) if world == 1 else step_eager
 
-    # ---- device-resident throughput
+    # ---- device-resident throughput: the public streaming evaluator without host I/O
+    if world == 1:
+        es_res = model.make_eval_stream(batch=B, slots=cycle, streams=n_streams, banks=banks, host_io=False)
+        for s_ in range(cycle):
+            es_res.dev_feats[s_].copy_(feats_dev[s_ % n_feat])
+            es_res.dev_labels[s_].copy_(labels_dev[s_ % n_feat])
+        step_resident = lambda i: es_res.step(i % cycle)
+        res_begin, res_end, hits_src = es_res.begin, es_res.end, es_res.hits
+    else:
+        step_resident, res_begin, res_end, hits_src = step_eager, (lambda: None), drain, hits
     for i in range(warmup):
         step_resident(i)
-    drain()
-    hits.zero_()
+    res_end()
+    torch.cuda.synchronize()
+    hits_src.zero_()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ms = timed(step_resident, steps, drain)
+    ms = timed(step_resident, steps, res_end, res_begin)
     launches = kernels_per_step * steps
     ms_per_step = ms / steps
     value = B / (ms_per_step * 1e-3)
-    hits_resident = hits.tolist()
+    hits_resident = hits_src.tolist()
 
-    # ---- dominant kernel alone (GEMM + fused top-k, no merge): the roofline figure
+    # ---- dominant kernel alone (GEMM + fused top-k, no merge), one stream: the roofline figure
     Cs = hi - lo
     nomerge = ops.HGR_IMPL_TCGEN05 | _cabi.HGR_IMPL_FLAG_NO_MERGE
     xs = [ops.normalize_rows(f) for f in feats_dev]
@@ -288,21 +316,22 @@ def run_ours(args):
     def kern_eager(i):
         ops.score_topk(xs[i % n_feat], banks[i % n_bank], K=K, impl=nomerge)
 
-    kern_only = graphed(kern_eager, cycle)
+    kern_only, kb_, ke_ = graphed(kern_eager, cycle, 1)
     for i in range(warmup):
         kern_only(i)
-    kms = timed(kern_only, steps) / steps
+    ke_()
+    kms = timed(kern_only, steps, ke_, kb_) / steps
     flops = 2.0 * B * Cs * D
     achieved = flops / (kms * 1e-3) / 1e12
 
     # ---- sustained loop (>= ~1.5 s) so that the clock / throttle samples mean something
     n_sus = int(min(2_000_000, max(steps, 1.5 / (ms_per_step * 1e-3))))
-    sus_ms = timed(step_resident, n_sus, drain) / n_sus
+    sus_ms = timed(step_resident, n_sus, res_end, res_begin) / n_sus
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- end to end through the public API with pinned HOST buffers
     if world == 1:
-        es = model.make_eval_stream(batch=B, slots=cycle, banks=banks)     # hgrnet_b200.stream.EvalStream
+        es = model.make_eval_stream(batch=B, slots=cycle, streams=n_streams, banks=banks)   # stream.EvalStream
         for s_ in range(cycle):
             es.host_feats[s_].copy_(feats_host[s_ % n_feat])
             es.host_labels[s_].copy_(labels_host[s_ % n_feat].to(torch.int32))
@@ -318,9 +347,12 @@ def run_ours(args):
             e2e_out[0] = hits.cpu()                      # D2H read of the step's result (Hit@k counters)
 
     e2e_out = [None]
+    e2e_begin, e2e_end = (es.begin, es.end) if world == 1 else (None, None)
     for i in range(warmup):
         step_e2e(i)
-    e2e_ms = timed(step_e2e, steps) / steps
+    if e2e_end:
+        e2e_end()
+    e2e_ms = timed(step_e2e, steps, e2e_end, e2e_begin) / steps
     e2e_value = B / (e2e_ms * 1e-3)
 
     if rank == 0:
@@ -336,6 +368,7 @@ def run_ours(args):
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": wl["name"], "B": B, "C": C, "D": D, "K": K,
                        "sharding": "none" if world == 1 else "class dimension row-sharded over %d ranks, 1 all-gather/batch" % world,
+                       "streams": n_streams,
                        "l2": "inputs larger than L2: %d bank copies (%.0f MB) + %d feature batches rotated" %
                              (n_bank, n_bank * Cs * D * 2 / 1e6, n_feat)},
             "e2e": {"value": e2e_value, "unit": "images/s", "ms_per_step": e2e_ms,
@@ -363,6 +396,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=None, choices=[None, "cfg2", "cfg4", "cfg5"])
     ap.add_argument("--no-cpu-baseline", dest="no_cpu_baseline", action="store_true")
+    ap.add_argument("--streams", type=int, default=3, help="round-robin CUDA streams of the streaming evaluator")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -24,6 +24,15 @@ namespace {
 
 constexpr int kMergeWarps = 4;
 
+// monotone map fp32 -> uint32 (larger float <=> larger key) and back
+__device__ __forceinline__ uint32_t f32_order_key(float v) {
+  const uint32_t b = __float_as_uint(v);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float f32_from_order_key(uint32_t k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k);
+}
+
 // kMaxListsPerLane: 4 covers P <= 128 lists per row, 10 covers P <= 320 (one list per epilogue warp of
 // every CTA when a single row tile is spread over all 148 SMs)
 template <int kMaxListsPerLane>
@@ -90,17 +99,19 @@ topk_merge_kernel(const MergeArgs a) {
       }
       const float lbv = bv;
       const int32_t lbi = bi;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-        const int32_t oi = __shfl_xor_sync(0xffffffffu, bi, o);
-        if (ov > bv || (ov == bv && oi < bi && oi >= 0)) {
-          bv = ov;
-          bi = oi;
-        }
+      // warp arg-max with two REDUX instructions: max of an order-preserving integer image of the value, then
+      // the smallest item among the lanes that hold that value
+      const uint32_t lkey = f32_order_key(lbv);
+      const uint32_t mkey = __reduce_max_sync(0xffffffffu, lkey);
+      const uint32_t mitem =
+          __reduce_min_sync(0xffffffffu, (lkey == mkey && lbi >= 0) ? static_cast<uint32_t>(lbi) : 0xFFFFFFFFu);
+      if (mitem == 0xFFFFFFFFu) {  // every list exhausted: fewer than K candidates, the rest stays (-inf, -1)
+        kth = -INFINITY;
+        break;
       }
+      bv = f32_from_order_key(mkey);
+      bi = static_cast<int32_t>(mitem);
       kth = bv;
-      if (!(bv > -INFINITY)) break;  // fewer than K candidates: the rest stays (-inf, -1)
       // the lowest lane holding the winner advances that list
       const unsigned holders = __ballot_sync(0xffffffffu, lbv == bv && lbi == bi);
       if (lane == __ffs(holders) - 1) {

@@ -197,11 +197,12 @@ class tree_model(nn.Module):
         t = targets.to(torch.int32) if targets is not None else None
         return ops.score_topk(x, self.bank_test, col_id=self._test_index_i32, targets=t, K=K, hits=hits)
 
-    def make_eval_stream(self, batch: int, slots: int = 2, feat_dtype=torch.float32, K: int = 20, banks=None):
+    def make_eval_stream(self, batch: int, slots: int = 4, streams: int = 2, feat_dtype=torch.float32, K: int = 20,
+                         banks=None, host_io: bool = True):
         """CUDA-graph replayed eval step over pre-computed image features (hgrnet_b200.stream.EvalStream)."""
         from .stream import EvalStream
         return EvalStream(self.bank_test, col_id=self._test_index_i32, batch=batch, feat_dtype=feat_dtype, K=K,
-                          slots=slots, banks=banks)
+                          slots=slots, streams=streams, banks=banks, host_io=host_io)
 
     # ------------------------------------------------------------------ training step
     def _iterations(self, training_method, sample_strategy, target):
