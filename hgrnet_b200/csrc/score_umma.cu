@@ -162,22 +162,28 @@ score_umma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     list.init();
     float null_acc = -INFINITY;
     int it = 0;
+    EpiClock ck(p.timeline != nullptr && epi_tid == 0);
     while (walk.next(t)) {
       const int buf = it & 1;
+      ck.start();
       ptx::mbar_wait(&ctl->tmem_full[buf], (it >> 1) & 1);
       ptx::tc_fence_after();
+      ck.lap(ck.wait);
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + buf * kSubN;
       const int64_t row = static_cast<int64_t>(t.mt) * kTileM + row_in_tile;
-      bool seed = false;  // the first chunk this warp sees of a segment seeds the empty list
+      float floor_thr = -INFINITY;
       if (t.first) {
         list.init();
         null_acc = -INFINITY;
-        seed = true;
+        if (EPI == kEpiTopkQueue) floor_thr = warmup_floor<KL, WPQ>(taddr, member, t.nvalid);
+        ck.lap(ck.warm);
       }
       for (int c0 = member * kChunk; c0 < t.nvalid; c0 += WPQ * kChunk) {
         uint32_t r[kChunk];
+        ck.start();
         ptx::tmem_ld_x32(taddr + c0, r);
         ptx::tmem_ld_wait();
+        ck.lap(ck.ld);
         const int nv = t.nvalid - c0;
         if (EPI == kEpiDense) {
           if (row < p.B) {
@@ -189,14 +195,7 @@ score_umma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
         } else if (EPI == kEpiTopkReload) {
           scan_chunk_reload<KL>(list, r, nv, taddr + c0, t.col0 + c0);
         } else if (EPI == kEpiTopkQueue) {
-          constexpr int kSeed = KL < 8 ? KL : 8;
-          if (seed && nv >= kChunk) {
-            SeedPrefix<KL, kSeed>::run(list, r, t.col0 + c0);
-            scan_chunk_queue<KL, kEpiThreads * 4, kSeed>(list, r, nv, t.col0 + c0, qaddr);
-          } else {
-            scan_chunk_queue<KL, kEpiThreads * 4, 0>(list, r, nv, t.col0 + c0, qaddr);
-          }
-          seed = false;
+          scan_chunk_queue<KL, kEpiThreads * 4, 0>(list, r, nv, t.col0 + c0, qaddr, floor_thr, ck);
         } else {
 #pragma unroll
           for (int j = 0; j < kChunk; ++j) null_acc = fmaxf(null_acc, __uint_as_float(r[j]));
@@ -310,8 +309,8 @@ double overflow_bound(int K, int KL, int lists) {
 int pick_list_len(int K, int64_t B, int lists_per_row, bool allow_speculation) {
   const int exact = K <= 8 ? 8 : (K <= 12 ? 12 : (K <= 20 ? 20 : 32));
   if (!allow_speculation) return exact;
-  const int cand[2] = {8, 12};
-  for (int i = 0; i < 2; ++i) {
+  const int cand[3] = {8, 10, 12};
+  for (int i = 0; i < 3; ++i) {
     const int kl = cand[i];
     if (kl >= K) break;
     if (static_cast<double>(B) * lists_per_row * overflow_bound(K, kl, lists_per_row) < 1e-3) return kl;
@@ -330,9 +329,9 @@ bool umma_supported(int64_t B, int64_t C, int64_t D, int K) {
 
 size_t umma_score_workspace_bytes(int64_t B, int64_t C, int K) {
   // worst case over the kernel variants (single CTA / CTA pair) and the list-width policy (exact lists)
-  const int p1 = pick_sched(B, C, false).P * kWpq, p2 = pick_sched(B, C, true).P * kPairWpq;
+  const int p1 = pick_sched(B, C, false).P * kWpq, p2 = pick_sched(B, C, true).P * 2;
   const int kl = K <= 8 ? 8 : (K <= 12 ? 12 : (K <= 20 ? 20 : 32));
-  return static_cast<size_t>(p1 > p2 ? p1 : p2) * B * kl * (sizeof(float) + sizeof(int32_t)) + 64;
+  return static_cast<size_t>(p1 > p2 ? p1 : p2) * B * kl * (sizeof(float) + sizeof(int32_t)) + kWsHeaderBytes;
 }
 
 int launch_score_topk_umma(const __nv_bfloat16* X, const __nv_bfloat16* bank, const int32_t* col_id,
@@ -353,18 +352,20 @@ int launch_score_topk_umma(const __nv_bfloat16* X, const __nv_bfloat16* bank, co
   if (ws == nullptr || ws_bytes < umma_score_workspace_bytes(B, C, K))
     return set_error(HGR_ERR_WORKSPACE, "hgr_score_topk(tcgen05): workspace %zu < %zu bytes", ws_bytes,
                      umma_score_workspace_bytes(B, C, K));
-  const int wpq = variant == 1 ? 1 : (pair ? kPairWpq : kWpq);
+  const int wpq = variant == 1 ? 1 : (pair ? pair_wpq() : kWpq);
   const int lists = p.sched.P * wpq;
   const int KL = pick_list_len(K, B, lists, variant == 0 || variant == 4);
   p.KL = KL;
   p.scale = scale;
-  p.stats = static_cast<unsigned int*>(ws);                              // first 64 bytes: statistics
-  p.part_val = reinterpret_cast<float*>(static_cast<uint8_t*>(ws) + 64);
+  p.stats = static_cast<unsigned int*>(ws);                              // header: statistics, timeline stamps
+  static const bool want_timeline = getenv("HGR_TIMELINE") != nullptr;
+  p.timeline = want_timeline ? reinterpret_cast<unsigned long long*>(static_cast<uint8_t*>(ws) + 64) : nullptr;
+  p.part_val = reinterpret_cast<float*>(static_cast<uint8_t*>(ws) + kWsHeaderBytes);
   p.part_idx = reinterpret_cast<int32_t*>(p.part_val + static_cast<size_t>(lists) * B * KL);
-  if (variant == 3) return launch_pair_kernel(kEpiNull, 8, mx, mb, p, stream);
+  if (variant == 3) return launch_pair_kernel(kEpiNull, 8, wpq, mx, mb, p, stream);
   if (variant == 5) return launch_kernel<kEpiNull, 8, kWpq>(mx, mb, p, stream);
   if (pair) {
-    rc = launch_pair_kernel(kEpiTopkQueue, KL, mx, mb, p, stream);
+    rc = launch_pair_kernel(kEpiTopkQueue, KL, wpq, mx, mb, p, stream);
   } else {
 #define HGR_UMMA_CASE(KLV)                                                                            \
   case KLV:                                                                                           \
@@ -373,6 +374,7 @@ int launch_score_topk_umma(const __nv_bfloat16* X, const __nv_bfloat16* bank, co
     break
     switch (KL) {
       HGR_UMMA_CASE(8);
+      HGR_UMMA_CASE(10);
       HGR_UMMA_CASE(12);
       HGR_UMMA_CASE(20);
       HGR_UMMA_CASE(32);
@@ -418,7 +420,7 @@ int launch_logits_umma(const __nv_bfloat16* X, const __nv_bfloat16* bank, int64_
   p.scale = scale;
   p.dense_out = out;
   p.ldo = ldo;
-  if (pair) return launch_pair_kernel(kEpiDense, 8, mx, mb, p, stream);
+  if (pair) return launch_pair_kernel(kEpiDense, 8, 2, mx, mb, p, stream);
   return launch_kernel<kEpiDense, 8, kWpq>(mx, mb, p, stream);
 }
 

@@ -14,6 +14,8 @@
 // .cta_group::2); the leader's single MMA thread commits with a cluster multicast to the `empty`
 // and `tmem_full` barriers of both CTAs; the epilogue warps of both CTAs arrive on the leader's
 // `tmem_empty`.  Epilogue and work split are shared with the single-CTA kernel (umma_common.cuh).
+#include <cstdlib>
+
 #include "umma_common.cuh"
 
 namespace hgr {
@@ -50,6 +52,7 @@ score_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
   const int pair = blockIdx.x >> 1;
 
   if (blockIdx.x == 0 && threadIdx.x == 0 && p.stats != nullptr) p.stats[0] = 0;
+  if (threadIdx.x == 0) stamp(p, 0);  // kernel entry
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&map_x);
     ptx::prefetch_tensormap(&map_bank);
@@ -71,6 +74,7 @@ score_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
   ptx::cluster_sync_all();  // barriers of both CTAs initialised, TMEM allocated
   ptx::tc_fence_after();
   const uint32_t tmem_base = ctl->tmem_base;
+  if (threadIdx.x == 0) stamp(p, 1);  // set-up done (barriers, TMEM, cluster sync)
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
@@ -119,6 +123,7 @@ score_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
           ptx::mbar_wait(&ctl->full[stage], phase);
           ptx::tc_fence_after();
+          if (it == 0 && kb == 0) stamp(p, 2);  // first operands landed
           const uint32_t a_addr = ptx::smem_u32(stage_base + stage * kPairStageBytes);
           const uint32_t b_addr = a_addr + kABytes;
 #pragma unroll
@@ -136,6 +141,7 @@ score_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
         ptx::umma_commit_cg2_mc(&ctl->tmem_full[buf], 0x3);  // accumulators of both CTAs complete
         ++it;
       }
+      stamp(p, 3);  // last MMA issued
     }
   } else {
     // ===================== epilogue (both CTAs, own 128 rows each) =====================
@@ -150,22 +156,29 @@ score_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
     list.init();
     float null_acc = -INFINITY;
     int it = 0;
+    EpiClock ck(p.timeline != nullptr && epi_tid == 0);
     while (walk.next(t)) {
       const int buf = it & 1;
+      ck.start();
       ptx::mbar_wait(&ctl->tmem_full[buf], (it >> 1) & 1);
       ptx::tc_fence_after();
+      ck.lap(ck.wait);
+      if (epi_tid == 0 && it < 4) stamp(p, 4 + it);  // accumulator of sub-tile `it` ready
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + buf * kSubN;
       const int64_t row = static_cast<int64_t>(t.mt) * (2 * kTileM) + row_in_tile;
-      bool seed = false;
+      float floor_thr = -INFINITY;
       if (t.first) {
         list.init();
         null_acc = -INFINITY;
-        seed = true;
+        if (EPI == kEpiTopkQueue) floor_thr = warmup_floor<KL, WPQ>(taddr, member, t.nvalid);
+        ck.lap(ck.warm);
       }
       for (int c0 = member * kChunk; c0 < t.nvalid; c0 += WPQ * kChunk) {
         uint32_t r[kChunk];
+        ck.start();
         ptx::tmem_ld_x32(taddr + c0, r);
         ptx::tmem_ld_wait();
+        ck.lap(ck.ld);
         const int nv = t.nvalid - c0;
         if (EPI == kEpiDense) {
           if (row < p.B) {
@@ -175,14 +188,7 @@ score_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
               if (j < nv) o[j] = __uint_as_float(r[j]) * p.scale;
           }
         } else if (EPI == kEpiTopkQueue) {
-          constexpr int kSeed = KL < 8 ? KL : 8;
-          if (seed && nv >= kChunk) {
-            SeedPrefix<KL, kSeed>::run(list, r, t.col0 + c0);
-            scan_chunk_queue<KL, kEpiThreads * 4, kSeed>(list, r, nv, t.col0 + c0, qaddr);
-          } else {
-            scan_chunk_queue<KL, kEpiThreads * 4, 0>(list, r, nv, t.col0 + c0, qaddr);
-          }
-          seed = false;
+          scan_chunk_queue<KL, kEpiThreads * 4, 0>(list, r, nv, t.col0 + c0, qaddr, floor_thr, ck);
         } else {
 #pragma unroll
           for (int j = 0; j < kChunk; ++j) null_acc = fmaxf(null_acc, __uint_as_float(r[j]));
@@ -195,6 +201,7 @@ score_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
         if (rank == 0) ptx::mbar_arrive(&ctl->tmem_empty[buf]);
         else ptx::mbar_arrive_cluster(ptx::mapa_shared(ptx::smem_u32(&ctl->tmem_empty[buf]), 0));
       }
+      if (epi_tid == 0 && it < 4) stamp(p, 8 + it);  // this warp is done with sub-tile `it`
       if (EPI != kEpiDense && t.last && row < p.B) {
         const int slot = (pair - p.sched.first_cta(t.mt)) * WPQ + member;
         float* pv = p.part_val + (static_cast<int64_t>(slot) * p.B + row) * p.KL;
@@ -214,6 +221,11 @@ score_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
       }
       ++it;
     }
+    if (epi_tid == 0) stamp(p, 12);  // epilogue done
+    if (ck.on && blockIdx.x < 256) {
+      unsigned long long* tl = p.timeline + blockIdx.x * kTimelineSlots;
+      tl[16] = ck.wait, tl[17] = ck.warm, tl[18] = ck.ld, tl[19] = ck.scan, tl[20] = ck.drain;
+    }
   }
 
   // no CTA may exit (or free TMEM) while its partner can still signal its barriers or read its memory
@@ -223,6 +235,7 @@ score_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
     ptx::tc_fence_after();
     ptx::tmem_dealloc_cg2(tmem_base, kTmemCols);
   }
+  if (threadIdx.x == 32) stamp(p, 13);  // exit
 }
 
 template <int EPI, int KL, int WPQ>
@@ -239,17 +252,32 @@ int launch_one(const CUtensorMap& mx, const CUtensorMap& mb, const Params& p, cu
 
 }  // namespace
 
-int launch_pair_kernel(int epi, int KL, const CUtensorMap& mx, const CUtensorMap& mb, const Params& p,
-                       cudaStream_t stream) {
-  if (epi == kEpiDense) return launch_one<kEpiDense, 8, kPairWpq>(mx, mb, p, stream);
-  if (epi == kEpiNull) return launch_one<kEpiNull, 8, kPairWpq>(mx, mb, p, stream);
+int pair_wpq() {
+  static const int w = [] {
+    const char* e = getenv("HGR_WPQ");
+    return (e && e[0] == '1') ? 1 : 2;
+  }();
+  return w;
+}
+
+template <int WPQ>
+int launch_pair_wpq(int epi, int KL, const CUtensorMap& mx, const CUtensorMap& mb, const Params& p,
+                    cudaStream_t stream) {
+  if (epi == kEpiDense) return launch_one<kEpiDense, 8, WPQ>(mx, mb, p, stream);
+  if (epi == kEpiNull) return launch_one<kEpiNull, 8, WPQ>(mx, mb, p, stream);
   switch (KL) {
-    case 8: return launch_one<kEpiTopkQueue, 8, kPairWpq>(mx, mb, p, stream);
-    case 12: return launch_one<kEpiTopkQueue, 12, kPairWpq>(mx, mb, p, stream);
-    case 20: return launch_one<kEpiTopkQueue, 20, kPairWpq>(mx, mb, p, stream);
-    case 32: return launch_one<kEpiTopkQueue, 32, kPairWpq>(mx, mb, p, stream);
+    case 8: return launch_one<kEpiTopkQueue, 8, WPQ>(mx, mb, p, stream);
+    case 10: return launch_one<kEpiTopkQueue, 10, WPQ>(mx, mb, p, stream);
+    case 12: return launch_one<kEpiTopkQueue, 12, WPQ>(mx, mb, p, stream);
+    case 20: return launch_one<kEpiTopkQueue, 20, WPQ>(mx, mb, p, stream);
+    case 32: return launch_one<kEpiTopkQueue, 32, WPQ>(mx, mb, p, stream);
   }
   return set_error(HGR_ERR_UNSUPPORTED, "hgr_score_topk(tcgen05 pair): list length %d", KL);
+}
+
+int launch_pair_kernel(int epi, int KL, int wpq, const CUtensorMap& mx, const CUtensorMap& mb, const Params& p,
+                       cudaStream_t stream) {
+  return wpq == 2 ? launch_pair_wpq<2>(epi, KL, mx, mb, p, stream) : launch_pair_wpq<1>(epi, KL, mx, mb, p, stream);
 }
 
 }  // namespace umma

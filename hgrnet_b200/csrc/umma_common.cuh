@@ -69,6 +69,33 @@ struct Params {
   float* dense_out;    // [B][ldo]
   int64_t ldo;
   unsigned int* stats; // [0] = rows re-scanned by the merge kernel of this call (reset here)
+  unsigned long long* timeline;  // optional [CTA][16] %globaltimer stamps (HGR_TIMELINE=1), else nullptr
+};
+
+constexpr int kTimelineSlots = 24;
+constexpr int kWsHeaderBytes = 64 + 256 * kTimelineSlots * 8;  // statistics + timeline stamps in front of the partial lists
+
+__device__ __forceinline__ void stamp(const Params& p, int slot) {
+  if (p.timeline != nullptr && blockIdx.x < 256) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    p.timeline[blockIdx.x * kTimelineSlots + slot] = t;
+  }
+}
+// cycle accounting of one epilogue warp (profiling builds of the timeline only)
+struct EpiClock {
+  long long ld = 0, scan = 0, drain = 0, wait = 0, warm = 0;
+  long long t = 0;
+  bool on;
+  __device__ __forceinline__ explicit EpiClock(bool enable) : on(enable) {}
+  __device__ __forceinline__ void start() { if (on) t = clock64(); }
+  __device__ __forceinline__ void lap(long long& acc) {
+    if (on) {
+      const long long n = clock64();
+      acc += n - t;
+      t = n;
+    }
+  }
 };
 
 template <int KL>
@@ -107,12 +134,42 @@ struct SeedPrefix<KL, 0> {
 // qaddr: shared-space byte address of this thread's column of the [kChunk][epilogue threads] fp32 staging
 // array; QSTRIDE_B: bytes between consecutive entries of one thread.  Columns < JSTART are skipped (already
 // seeded into the list).
+// Warm-up floor of a segment.  A list that starts empty accepts everything, and the insert body is what the
+// epilogue pays for (ALU pipe).  Before scanning the first sub-tile of a segment the warp therefore takes one
+// cheap extra pass over its chunks of that sub-tile (TMEM is re-readable): KL interleaved running maxima, one
+// FMNMX per value, no divergence.  Their minimum tau is a value that at least KL columns of this list's stream
+// reach, i.e. a valid lower bound of the list's final KL-th entry, so everything below tau can be dropped up
+// front without touching the certificate argument (dropped <= final last entry).  Returns the largest float
+// below tau (ties with tau must still enter), or -inf when the sub-tile is too small to fill every group.
+template <int KL, int WPQ>
+__device__ __forceinline__ float warmup_floor(uint32_t taddr, int member, int nvalid) {
+  if (nvalid - member * kChunk < kChunk) return -INFINITY;  // this warp's first chunk is ragged: skip
+  float gm[KL];
+#pragma unroll
+  for (int g = 0; g < KL; ++g) gm[g] = -INFINITY;
+  for (int c0 = member * kChunk; c0 < nvalid; c0 += WPQ * kChunk) {
+    uint32_t r[kChunk];
+    ptx::tmem_ld_x32(taddr + c0, r);
+    ptx::tmem_ld_wait();
+    const int nv = nvalid - c0;
+#pragma unroll
+    for (int j = 0; j < kChunk; ++j) {
+      const float x = (nv >= kChunk || j < nv) ? __uint_as_float(r[j]) : -INFINITY;
+      gm[j % KL] = fmaxf(gm[j % KL], x);
+    }
+  }
+  float tau = gm[0];
+#pragma unroll
+  for (int g = 1; g < KL; ++g) tau = fminf(tau, gm[g]);
+  return nextafterf(tau, -INFINITY);
+}
+
 template <int KL, int QSTRIDE_B, int JSTART>
 __device__ __forceinline__ void scan_chunk_queue(SortedList<KL>& list, const uint32_t (&r)[kChunk], int nv,
-                                                 int col_chunk, uint32_t qaddr) {
+                                                 int col_chunk, uint32_t qaddr, float floor_thr, EpiClock& ck) {
   // 1) lane-private compaction of the values that beat the KL-th best at chunk entry:
   //    values go to the queue in column order, their positions into a bit mask
-  const float thr = list.thr();
+  const float thr = fmaxf(list.thr(), floor_thr);
   uint32_t m = 0;
   uint32_t wr = qaddr;
 #pragma unroll
@@ -129,6 +186,7 @@ __device__ __forceinline__ void scan_chunk_queue(SortedList<KL>& list, const uin
   // 2) dense drain: lanes walk their own queues in lock-step, so the (long) insert body runs
   //    max_lane(cnt) times instead of once per column any lane hit
   const int maxc = __reduce_max_sync(0xffffffffu, cnt);
+  ck.lap(ck.scan);
   uint32_t rd = qaddr;
   for (int e = 0; e < maxc; ++e) {
     if (e < cnt) {
@@ -139,11 +197,15 @@ __device__ __forceinline__ void scan_chunk_queue(SortedList<KL>& list, const uin
       if (x > list.thr()) list.insert(x, col_chunk + j);
     }
   }
+  ck.lap(ck.drain);
 }
 
 // CTA-pair kernel (score_umma2.cu)
-constexpr int kPairWpq = 2;  // epilogue warps per TMEM lane quarter
-int launch_pair_kernel(int epi, int KL, const CUtensorMap& mx, const CUtensorMap& mb, const Params& p,
+// wpq = epilogue warps per TMEM lane quarter (1 or 2).  The epilogue is bound by the ALU pipe (FSETP / FSEL /
+// SEL issue every other cycle per sub-partition), not by latency, so ONE warp per quarter keeping ONE list per
+// row is the cheapest arrangement: a second warp would halve each stream and pay the list warm-up twice.
+int pair_wpq();
+int launch_pair_kernel(int epi, int KL, int wpq, const CUtensorMap& mx, const CUtensorMap& mb, const Params& p,
                        cudaStream_t stream);
 
 }  // namespace umma
