@@ -1,0 +1,79 @@
+"""world_size-2 gloo test (CPU) of the host-side logic of the class-sharded head: shard bounds, the packed
+candidate record exchanged by the single all-gather, and that merging the gathered per-rank lists equals the
+oracle's global top-K.  (The CUDA merge kernel itself is covered by the -m gpu tests.)"""
+from __future__ import annotations
+
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import hgr_oracle as orc
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, B, C, D, K, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from hgrnet_b200.dist import pack_candidates, shard_bounds, unpack_gathered
+        g = torch.Generator().manual_seed(5)
+        x = torch.randn(B, D, generator=g)
+        w = torch.randn(C, D, generator=g)
+        logits = orc.forward_logits(x, orc.normalize_rows(w))          # every rank holds the full oracle logits
+        lo, hi = shard_bounds(C, world)[rank]
+        k_loc = min(K, hi - lo)
+        val = torch.full((B, K), float("-inf"))
+        idx = torch.full((B, K), -1, dtype=torch.int32)
+        if k_loc > 0:                                                   # what kernel (2) returns for this shard
+            v, i = logits[:, lo:hi].topk(k_loc, 1, True, True)
+            val[:, :k_loc], idx[:, :k_loc] = v, (i + lo).int()
+        send = pack_candidates(val, idx)
+        recv = torch.empty((world,) + tuple(send.shape), dtype=torch.int32)
+        dist.all_gather_into_tensor(recv.view(-1), send.view(-1))       # THE one collective on the data path
+        pv, pi = unpack_gathered(recv)
+        assert pv.shape == (world, B, K) and pi.dtype == torch.int32
+        assert pv.stride(0) == pi.stride(0) == 2 * B * K and pv.stride(1) == K    # merge-in-place layout
+        flat_v = pv.permute(1, 0, 2).reshape(B, world * K)
+        flat_i = pi.permute(1, 0, 2).reshape(B, world * K)
+        mv, mp_ = flat_v.topk(K, 1, True, True)
+        mi = flat_i.gather(1, mp_)
+        ov, oi = logits.topk(K, 1, True, True)
+        assert torch.equal(mv, ov) and torch.equal(mi.long(), oi)
+        if rank == 0:
+            out.put("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("B,C,K", [(33, 1001, 20), (4, 30, 20)])
+def test_sharded_candidates_merge_to_global_topk(B, C, K):
+    ctx = mp.get_context("spawn")
+    out = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, B, C, 64, K, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert out.get() == "ok"
+
+
+def test_shard_bounds_cover_the_bank_once():
+    from hgrnet_b200.dist import shard_bounds
+    for C, G in ((21841, 8), (21841, 3), (5, 8), (16, 2), (0, 4)):
+        b = shard_bounds(C, G)
+        assert len(b) == G and b[0][0] == 0 and b[-1][1] == C
+        assert all(b[i][1] == b[i + 1][0] for i in range(G - 1))
+        assert all(lo <= hi for lo, hi in b)
+    assert shard_bounds(21841, 8)[0] == (0, 2731) and shard_bounds(21841, 8)[7] == (19117, 21841)
