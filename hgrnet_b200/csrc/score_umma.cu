@@ -92,7 +92,7 @@ score_umma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     // ===================== TMA producer =====================
     if (lane == 0) {
       const uint64_t pol = ptx::policy_evict_last();
-      TileWalker walk(p.sched, cta, p.C);
+      TileWalker walk(p.sched, cta, p.C, p.rem_first);
       SubTile t;
       int stage = 0;
       uint32_t phase = 0;
@@ -117,7 +117,7 @@ score_umma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      TileWalker walk(p.sched, cta, p.C);
+      TileWalker walk(p.sched, cta, p.C, p.rem_first);
       SubTile t;
       int stage = 0;
       uint32_t phase = 0;
@@ -155,12 +155,14 @@ score_umma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     const int member = (warp - kEpiWarp0) >> 2;         // which of the WPQ warps of that quarter
     const int row_in_tile = quarter * 32 + lane;
     const int epi_tid = (warp - kEpiWarp0) * 32 + lane;
-    const uint32_t qaddr = ptx::smem_u32(queue_base + epi_tid);
-    TileWalker walk(p.sched, cta, p.C);
+    const uint32_t qaddr = ptx::smem_u32(queue_base + epi_tid * kChunk);  // private 128-byte staging row
+    const uint32_t qswz = static_cast<uint32_t>(epi_tid) & 7u;
+    TileWalker walk(p.sched, cta, p.C, p.rem_first);
     SubTile t;
     SortedList<KL> list;
     list.init();
     float null_acc = -INFINITY;
+    float floor_thr = -INFINITY;
     int it = 0;
     EpiClock ck(p.timeline != nullptr && epi_tid == 0);
     while (walk.next(t)) {
@@ -171,11 +173,13 @@ score_umma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
       ck.lap(ck.wait);
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + buf * kSubN;
       const int64_t row = static_cast<int64_t>(t.mt) * kTileM + row_in_tile;
-      float floor_thr = -INFINITY;
       if (t.first) {
         list.init();
         null_acc = -INFINITY;
-        if (EPI == kEpiTopkQueue) floor_thr = warmup_floor<KL, WPQ>(taddr, member, t.nvalid);
+        floor_thr = -INFINITY;
+      }
+      if (EPI == kEpiTopkQueue && t.seq < 2) {  // warm-up floor from the first two sub-tiles of a segment
+        floor_thr = fmaxf(floor_thr, warmup_floor<KL, WPQ>(taddr, member, t.nvalid));
         ck.lap(ck.warm);
       }
       for (int c0 = member * kChunk; c0 < t.nvalid; c0 += WPQ * kChunk) {
@@ -195,7 +199,7 @@ score_umma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
         } else if (EPI == kEpiTopkReload) {
           scan_chunk_reload<KL>(list, r, nv, taddr + c0, t.col0 + c0);
         } else if (EPI == kEpiTopkQueue) {
-          scan_chunk_queue<KL, kEpiThreads * 4, 0>(list, r, nv, t.col0 + c0, qaddr, floor_thr, ck);
+          scan_chunk_queue<KL>(list, r, nv, t.col0 + c0, qaddr, qswz, floor_thr, ck);
         } else {
 #pragma unroll
           for (int j = 0; j < kChunk; ++j) null_acc = fmaxf(null_acc, __uint_as_float(r[j]));
@@ -292,6 +296,11 @@ int common_setup(const __nv_bfloat16* X, const __nv_bfloat16* bank, int64_t B, i
   p->B = B;
   p->C = C;
   p->num_k_blocks = static_cast<int>((D + kBlockK - 1) / kBlockK);
+  static const int rem_first = [] {
+    const char* e = getenv("HGR_REM_FIRST");
+    return (e && e[0] == '1') ? 1 : 0;
+  }();
+  p->rem_first = rem_first;
   return HGR_OK;
 }
 

@@ -80,7 +80,7 @@ score_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
     // ===================== TMA producer (both CTAs) =====================
     if (lane == 0) {
       const uint64_t pol = ptx::policy_evict_last();
-      TileWalker walk(p.sched, pair, p.C);
+      TileWalker walk(p.sched, pair, p.C, p.rem_first);
       SubTile t;
       int stage = 0;
       uint32_t phase = 0;
@@ -109,7 +109,7 @@ score_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
     if (rank == 0 && lane == 0) {
-      TileWalker walk(p.sched, pair, p.C);
+      TileWalker walk(p.sched, pair, p.C, p.rem_first);
       SubTile t;
       int stage = 0;
       uint32_t phase = 0;
@@ -149,12 +149,14 @@ score_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
     const int member = (warp - kEpiWarp0) >> 2;
     const int row_in_tile = static_cast<int>(rank) * kTileM + quarter * 32 + lane;
     const int epi_tid = (warp - kEpiWarp0) * 32 + lane;
-    const uint32_t qaddr = ptx::smem_u32(queue_base + epi_tid);
-    TileWalker walk(p.sched, pair, p.C);
+    const uint32_t qaddr = ptx::smem_u32(queue_base + epi_tid * kChunk);  // private 128-byte staging row
+    const uint32_t qswz = static_cast<uint32_t>(epi_tid) & 7u;
+    TileWalker walk(p.sched, pair, p.C, p.rem_first);
     SubTile t;
     SortedList<KL> list;
     list.init();
     float null_acc = -INFINITY;
+    float floor_thr = -INFINITY;
     int it = 0;
     EpiClock ck(p.timeline != nullptr && epi_tid == 0);
     while (walk.next(t)) {
@@ -166,11 +168,13 @@ score_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
       if (epi_tid == 0 && it < 4) stamp(p, 4 + it);  // accumulator of sub-tile `it` ready
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + buf * kSubN;
       const int64_t row = static_cast<int64_t>(t.mt) * (2 * kTileM) + row_in_tile;
-      float floor_thr = -INFINITY;
       if (t.first) {
         list.init();
         null_acc = -INFINITY;
-        if (EPI == kEpiTopkQueue) floor_thr = warmup_floor<KL, WPQ>(taddr, member, t.nvalid);
+        floor_thr = -INFINITY;
+      }
+      if (EPI == kEpiTopkQueue && t.seq < 2) {  // warm-up floor from the first two sub-tiles of a segment
+        floor_thr = fmaxf(floor_thr, warmup_floor<KL, WPQ>(taddr, member, t.nvalid));
         ck.lap(ck.warm);
       }
       for (int c0 = member * kChunk; c0 < t.nvalid; c0 += WPQ * kChunk) {
@@ -188,7 +192,7 @@ score_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
               if (j < nv) o[j] = __uint_as_float(r[j]) * p.scale;
           }
         } else if (EPI == kEpiTopkQueue) {
-          scan_chunk_queue<KL, kEpiThreads * 4, 0>(list, r, nv, t.col0 + c0, qaddr, floor_thr, ck);
+          scan_chunk_queue<KL>(list, r, nv, t.col0 + c0, qaddr, qswz, floor_thr, ck);
         } else {
 #pragma unroll
           for (int j = 0; j < kChunk; ++j) null_acc = fmaxf(null_acc, __uint_as_float(r[j]));

@@ -28,6 +28,7 @@ struct SubTile {
   int nvalid;  // bank rows < C inside the sub-tile
   bool first;  // first sub-tile of a (row tile, CTA) segment
   bool last;   // last sub-tile of the segment
+  int seq;     // index of the sub-tile inside its segment
 };
 
 struct TileWalker {
@@ -35,15 +36,32 @@ struct TileWalker {
   int U;
   int64_t C;
   bool first;
-  __device__ TileWalker(const Sched& s, int cta, int64_t C_)
-      : u(s.unit_begin(cta)), u_end(s.unit_begin(cta + 1)), U(s.U), C(C_), first(true) {}
+  int seq;
+  int rem_first;
+  __device__ TileWalker(const Sched& s, int cta, int64_t C_, int rem_first_ = 1)
+      : u(s.unit_begin(cta)), u_end(s.unit_begin(cta + 1)), U(s.U), C(C_), first(true), seq(0),
+        rem_first(rem_first_) {}
+  // Sub-tiles of a segment in ascending column order; the REMAINDER (segment length mod 256 columns) comes
+  // first: a narrow sub-tile costs almost a full one on the tensor pipe (the A operand is re-streamed for
+  // every sub-tile), so it is best spent while the epilogue has nothing to drain yet, and its short epilogue
+  // frees the first accumulator buffer long before the third sub-tile needs it.
   __device__ bool next(SubTile& t) {
     if (u >= u_end) return false;
     const int mt = static_cast<int>(u / U);
     int uu = static_cast<int>(u - static_cast<int64_t>(mt) * U);
-    int nu = kSubN / kUnit;
-    if (U - uu < nu) nu = U - uu;
-    if (u_end - u < nu) nu = static_cast<int>(u_end - u);
+    constexpr int kFull = kSubN / kUnit;
+    int64_t seg = U - uu;                          // units left in this segment
+    if (u_end - u < seg) seg = u_end - u;
+    int nu;
+    if (first) {
+      const int rem = static_cast<int>(seg % kFull);
+      nu = (rem != 0 && rem_first) ? rem : (seg < kFull ? static_cast<int>(seg) : kFull);
+      seq = 0;
+    } else {
+      nu = seg < kFull ? static_cast<int>(seg) : kFull;
+      ++seq;
+    }
+    t.seq = seq;
     t.mt = mt;
     t.col0 = uu * kUnit;
     t.n = nu * kUnit;
@@ -69,7 +87,8 @@ struct Params {
   float* dense_out;    // [B][ldo]
   int64_t ldo;
   unsigned int* stats; // [0] = rows re-scanned by the merge kernel of this call (reset here)
-  unsigned long long* timeline;  // optional [CTA][16] %globaltimer stamps (HGR_TIMELINE=1), else nullptr
+  unsigned long long* timeline;  // optional [CTA][24] %globaltimer stamps (HGR_TIMELINE=1), else nullptr
+  int rem_first;       // sub-tile order inside a segment: remainder first (1) or last (0)
 };
 
 constexpr int kTimelineSlots = 24;
@@ -164,37 +183,36 @@ __device__ __forceinline__ float warmup_floor(uint32_t taddr, int member, int nv
   return nextafterf(tau, -INFINITY);
 }
 
-template <int KL, int QSTRIDE_B, int JSTART>
+// Scan one chunk of 32 accumulator columns of this thread's row.
+// row_addr: shared-space byte address of this thread's private 128-byte staging row; swz = thread id & 7.
+// 1) the 32 values are parked in the staging row with eight unconditional 128-bit stores (XOR-swizzled so
+//    that a warp's stores are conflict free) and a bit mask of the values that beat the current threshold is
+//    built with four independent OR chains -- no per-value predicated store, no pointer-bump dependency chain;
+// 2) dense drain: lanes walk their own masks in lock-step, so the (long) insert body runs max_lane(popc) times
+//    instead of once per column any lane hit; the value is re-read from the staging row by its column.
+template <int KL>
 __device__ __forceinline__ void scan_chunk_queue(SortedList<KL>& list, const uint32_t (&r)[kChunk], int nv,
-                                                 int col_chunk, uint32_t qaddr, float floor_thr, EpiClock& ck) {
-  // 1) lane-private compaction of the values that beat the KL-th best at chunk entry:
-  //    values go to the queue in column order, their positions into a bit mask
+                                                 int col_chunk, uint32_t row_addr, uint32_t swz, float floor_thr,
+                                                 EpiClock& ck) {
   const float thr = fmaxf(list.thr(), floor_thr);
-  uint32_t m = 0;
-  uint32_t wr = qaddr;
 #pragma unroll
-  for (int j = JSTART; j < kChunk; ++j) {
-    const float x = __uint_as_float(r[j]);
-    if (x > thr) {
-      ptx::st_shared_f32(wr, x);
-      wr += QSTRIDE_B;
-      m |= (1u << j);
-    }
-  }
+  for (int q = 0; q < kChunk / 4; ++q)
+    ptx::st_shared_v4(row_addr + ((static_cast<uint32_t>(q) ^ swz) << 4), r[4 * q], r[4 * q + 1], r[4 * q + 2],
+                      r[4 * q + 3]);
+  uint32_t m4[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+  for (int j = 0; j < kChunk; ++j)
+    if (__uint_as_float(r[j]) > thr) m4[j >> 3] |= (1u << j);
+  uint32_t m = (m4[0] | m4[1]) | (m4[2] | m4[3]);
   if (nv < kChunk) m &= (1u << nv) - 1u;  // ragged tail: columns >= C were zero-filled by TMA, drop them
-  const int cnt = __popc(m);
-  // 2) dense drain: lanes walk their own queues in lock-step, so the (long) insert body runs
-  //    max_lane(cnt) times instead of once per column any lane hit
-  const int maxc = __reduce_max_sync(0xffffffffu, cnt);
+  const int maxc = __reduce_max_sync(0xffffffffu, __popc(m));
   ck.lap(ck.scan);
-  uint32_t rd = qaddr;
   for (int e = 0; e < maxc; ++e) {
-    if (e < cnt) {
-      const float x = ptx::ld_shared_f32(rd);
-      rd += QSTRIDE_B;
-      const int j = __ffs(m) - 1;
+    if (m != 0u) {
+      const uint32_t j = __ffs(m) - 1;
       m &= m - 1;
-      if (x > list.thr()) list.insert(x, col_chunk + j);
+      const float x = ptx::ld_shared_f32(row_addr + (((j >> 2) ^ swz) << 4) + ((j & 3u) << 2));
+      if (x > list.thr()) list.insert(x, col_chunk + static_cast<int>(j));
     }
   }
   ck.lap(ck.drain);
