@@ -156,3 +156,21 @@ def test_get_contra_and_get_weights_surface(tmp_path, golden):
     assert ids.dtype == torch.long and ids.device.type == "cuda" and labels.shape == (16,)
     assert ids.tolist() == golden["om"][spec["name"]]["compare_idx"][0]
     assert int(labels[0]) == golden["om"][spec["name"]]["labels"][0]
+
+
+def test_main_cli_runs_eval_and_training_on_synthetic_data(tmp_path, monkeypatch, capsys):
+    """`python main.py --train False ...` / `--train True ...` with the reference's flags (README.md:48-49,64)."""
+    monkeypatch.chdir(tmp_path)
+    import importlib
+    import sys
+    sys.modules.pop("main", None)
+    main = importlib.import_module("main")
+    assert main.__file__.endswith("repo/main.py") or "reference" not in main.__file__
+    common = ["--hgr_synthetic", "6,30,200", "--folder", str(tmp_path / "o"), "--test_batch_size", "96",
+              "--batch_size", "32", "--print_freq", "4"]
+    main.main(["--train", "False", "--weights", "equal"] + common)
+    out = capsys.readouterr().out
+    assert "Direct testing." in out and "Top@1(%):" in out and "point_ratio(%):" in out
+    main.main(["--train", "True", "--epochs", "1", "--weights", "adaptive", "--out_ratio", "0.5", "--test_after_train"] + common)
+    out = capsys.readouterr().out
+    assert "loss:" in out and "Model saved." in out and "Top@20(%):" in out
