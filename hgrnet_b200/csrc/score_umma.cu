@@ -361,9 +361,15 @@ int launch_score_topk_umma(const __nv_bfloat16* X, const __nv_bfloat16* bank, co
   if (ws == nullptr || ws_bytes < umma_score_workspace_bytes(B, C, K))
     return set_error(HGR_ERR_WORKSPACE, "hgr_score_topk(tcgen05): workspace %zu < %zu bytes", ws_bytes,
                      umma_score_workspace_bytes(B, C, K));
-  const int wpq = variant == 1 ? 1 : (pair ? pair_wpq() : kWpq);
+  // the pair kernel picks its epilogue arrangement from the list length, which depends on lists/row = P * wpq
+  int wpq = variant == 1 ? 1 : kWpq;
+  int KL = pick_list_len(K, B, p.sched.P * wpq, variant == 0 || variant == 4);
+  if (pair) {
+    const int kl1 = pick_list_len(K, B, p.sched.P, variant == 0);       // one list per (row, pair)
+    wpq = pair_wpq(kl1);
+    KL = wpq == 1 ? kl1 : pick_list_len(K, B, p.sched.P * 2, variant == 0);
+  }
   const int lists = p.sched.P * wpq;
-  const int KL = pick_list_len(K, B, lists, variant == 0 || variant == 4);
   p.KL = KL;
   p.scale = scale;
   p.stats = static_cast<unsigned int*>(ws);                              // header: statistics, timeline stamps

@@ -22,13 +22,18 @@ namespace hgr {
 namespace umma {
 namespace {
 
-constexpr int kPairStages = 6;
+constexpr int kPairStagesMax = 6;
+#ifndef HGR_DEFER_DEPTH
+#define HGR_DEFER_DEPTH 64
+#endif
+constexpr int kDeferDepth = HGR_DEFER_DEPTH;                 // candidate slots per row (divided among the WPQ warps)
+constexpr int kDeferStages = kDeferDepth > 64 ? 4 : 5;      // operand stages that still fit beside the queue
 constexpr int kPairBBytes = (kSubN / 2) * kBlockK * 2;     // 16 KB: half of the bank sub-tile
 constexpr int kPairStageBytes = kABytes + kPairBBytes;     // 32 KB
 
 struct PairCtl {
-  uint64_t full[kPairStages];      // leader's copy is the one in use
-  uint64_t empty[kPairStages];     // per CTA, signalled by the leader's multicast commit
+  uint64_t full[kPairStagesMax];   // leader's copy is the one in use
+  uint64_t empty[kPairStagesMax];  // per CTA, signalled by the leader's multicast commit
   uint64_t tmem_full[2];           // per CTA, multicast commit
   uint64_t tmem_empty[2];          // leader's copy: arrivals from the epilogue warps of both CTAs
   uint32_t tmem_base;
@@ -39,7 +44,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 128 * WPQ, 1)
 score_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_bank,
                        const Params p) {
   constexpr int kEpiThreads = 128 * WPQ;
-  constexpr int kQueueBytes = EPI == kEpiTopkQueue ? kChunk * kEpiThreads * 4 : 0;
+  constexpr int kQueueDepth = kDeferDepth / WPQ;   // deferred-insert queue entries per thread
+  constexpr int kQueueBytes = EPI == kEpiTopkQueue ? kChunk * kEpiThreads * 4
+                            : EPI == kEpiTopkDefer ? (kQueueDepth + 1) * kEpiThreads * 8 : 0;
+  constexpr int kPairStages = EPI == kEpiTopkDefer ? kDeferStages : 6;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* stage_base = smem;
@@ -118,6 +126,7 @@ score_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
         const int buf = it & 1;
         ptx::mbar_wait(&ctl->tmem_empty[buf], ((it >> 1) & 1) ^ 1u);
         ptx::tc_fence_after();
+        if (it < 3) stamp(p, 21 + it);  // accumulator buffer granted for sub-tile `it`
         const uint32_t d_tmem = tmem_base + buf * kSubN;
         const uint32_t idesc = ptx::umma_idesc_bf16(2 * kTileM, t.n);
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
@@ -157,6 +166,8 @@ score_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
     list.init();
     float null_acc = -INFINITY;
     float floor_thr = -INFINITY;
+    CandQueue<kEpiThreads, kQueueDepth> cq;
+    cq.init(ptx::smem_u32(reinterpret_cast<uint2*>(queue_base) + epi_tid));
     int it = 0;
     EpiClock ck(p.timeline != nullptr && epi_tid == 0);
     while (walk.next(t)) {
@@ -177,6 +188,12 @@ score_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
         floor_thr = fmaxf(floor_thr, warmup_floor<KL, WPQ>(taddr, member, t.nvalid));
         ck.lap(ck.warm);
       }
+      float sub_thr = -INFINITY;
+      if (EPI == kEpiTopkDefer) {
+        if (t.seq == 0) floor_thr = warmup_floor<KL, WPQ>(taddr, member, t.nvalid);
+        ck.lap(ck.warm);
+        sub_thr = fmaxf(floor_thr, list.thr());   // fixed for the whole sub-tile
+      }
       for (int c0 = member * kChunk; c0 < t.nvalid; c0 += WPQ * kChunk) {
         uint32_t r[kChunk];
         ck.start();
@@ -193,6 +210,14 @@ score_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
           }
         } else if (EPI == kEpiTopkQueue) {
           scan_chunk_queue<KL>(list, r, nv, t.col0 + c0, qaddr, qswz, floor_thr, ck);
+        } else if (EPI == kEpiTopkDefer) {
+          if (cq.nearly_full()) {                 // rare: a lane collected > depth - 32 survivors
+            cand_drain<KL>(list, cq);
+            sub_thr = fmaxf(sub_thr, list.thr());
+            ck.lap(ck.drain);
+          }
+          cand_append_chunk(cq, r, nv, t.col0 + c0, sub_thr);
+          ck.lap(ck.scan);
         } else {
 #pragma unroll
           for (int j = 0; j < kChunk; ++j) null_acc = fmaxf(null_acc, __uint_as_float(r[j]));
@@ -204,6 +229,12 @@ score_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
       if (lane == 0) {
         if (rank == 0) ptx::mbar_arrive(&ctl->tmem_empty[buf]);
         else ptx::mbar_arrive_cluster(ptx::mapa_shared(ptx::smem_u32(&ctl->tmem_empty[buf]), 0));
+      }
+      if (epi_tid == 0 && it < 2) stamp(p, 14 + it);  // buffer of sub-tile `it` handed back
+      if (EPI == kEpiTopkDefer) {  // the buffer is already back with the tensor core: now pay for the inserts
+        ck.start();
+        cand_drain<KL>(list, cq);
+        ck.lap(ck.drain);
       }
       if (epi_tid == 0 && it < 4) stamp(p, 8 + it);  // this warp is done with sub-tile `it`
       if (EPI != kEpiDense && t.last && row < p.B) {
@@ -245,8 +276,9 @@ score_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
 template <int EPI, int KL, int WPQ>
 int launch_one(const CUtensorMap& mx, const CUtensorMap& mb, const Params& p, cudaStream_t stream) {
   constexpr int threads = 64 + 128 * WPQ;
-  const size_t smem = 1024 + static_cast<size_t>(kPairStages) * kPairStageBytes +
-                      (EPI == kEpiTopkQueue ? static_cast<size_t>(kChunk) * 128 * WPQ * 4 : 0) + sizeof(PairCtl);
+  constexpr size_t queue = EPI == kEpiTopkQueue ? static_cast<size_t>(kChunk) * 128 * WPQ * 4
+                         : EPI == kEpiTopkDefer ? static_cast<size_t>(kDeferDepth / WPQ + 1) * 128 * WPQ * 8 : 0;
+  const size_t smem = 1024 + static_cast<size_t>(EPI == kEpiTopkDefer ? kDeferStages : 6) * kPairStageBytes + queue + sizeof(PairCtl);
   auto kern = score_umma_pair_kernel<EPI, KL, WPQ>;
   HGR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   kern<<<2 * p.sched.G, threads, smem, stream>>>(mx, mb, p);
@@ -256,12 +288,17 @@ int launch_one(const CUtensorMap& mx, const CUtensorMap& mb, const Params& p, cu
 
 }  // namespace
 
-int pair_wpq() {
-  static const int w = [] {
+// Epilogue arrangement by list length: short speculative lists (many lists per row, ~600-column streams) are
+// dominated by list warm-up -> ONE warp per TMEM quarter, one list per row, inserts deferred off the tensor
+// core's critical path; long exact lists (few lists per row, multi-thousand-column streams) are dominated by
+// the steady-state scan -> TWO warps per quarter with the in-place queue.  HGR_WPQ / HGR_EPILOGUE override.
+int pair_wpq(int KL) {
+  static const int forced = [] {
     const char* e = getenv("HGR_WPQ");
-    return (e && e[0] == '1') ? 1 : 2;
+    return e ? (e[0] == '2' ? 2 : 1) : 0;
   }();
-  return w;
+  if (forced) return forced;
+  return KL <= 12 ? 1 : 2;
 }
 
 template <int WPQ>
@@ -269,6 +306,20 @@ int launch_pair_wpq(int epi, int KL, const CUtensorMap& mx, const CUtensorMap& m
                     cudaStream_t stream) {
   if (epi == kEpiDense) return launch_one<kEpiDense, 8, WPQ>(mx, mb, p, stream);
   if (epi == kEpiNull) return launch_one<kEpiNull, 8, WPQ>(mx, mb, p, stream);
+  static const int forced = [] {
+    const char* e = getenv("HGR_EPILOGUE");
+    return e ? (e[0] == 'q' ? 1 : 2) : 0;   // 'q' = in-place queue, 'd' = deferred inserts
+  }();
+  const bool defer = forced ? forced == 2 : (WPQ == 1);
+  if (defer) {
+    switch (KL) {
+      case 8: return launch_one<kEpiTopkDefer, 8, WPQ>(mx, mb, p, stream);
+      case 10: return launch_one<kEpiTopkDefer, 10, WPQ>(mx, mb, p, stream);
+      case 12: return launch_one<kEpiTopkDefer, 12, WPQ>(mx, mb, p, stream);
+      case 20: return launch_one<kEpiTopkDefer, 20, WPQ>(mx, mb, p, stream);
+      case 32: return launch_one<kEpiTopkDefer, 32, WPQ>(mx, mb, p, stream);
+    }
+  }
   switch (KL) {
     case 8: return launch_one<kEpiTopkQueue, 8, WPQ>(mx, mb, p, stream);
     case 10: return launch_one<kEpiTopkQueue, 10, WPQ>(mx, mb, p, stream);

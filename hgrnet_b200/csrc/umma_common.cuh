@@ -19,7 +19,7 @@ constexpr int kEpiWarp0 = 2;
 constexpr int kTmemCols = 512;
 constexpr int kChunk = 32;                          // accumulator columns per tcgen05.ld
 
-enum EpiMode { kEpiDense = 0, kEpiTopkReload = 1, kEpiTopkQueue = 2, kEpiNull = 3 };
+enum EpiMode { kEpiDense = 0, kEpiTopkReload = 1, kEpiTopkQueue = 2, kEpiNull = 3, kEpiTopkDefer = 4 };
 
 struct SubTile {
   int mt;      // row tile
@@ -218,11 +218,63 @@ __device__ __forceinline__ void scan_chunk_queue(SortedList<KL>& list, const uin
   ck.lap(ck.drain);
 }
 
+// ---- deferred-insert epilogue -------------------------------------------------------------------------------
+// The accumulator buffer is only needed while its values are FILTERED; the (ALU-bound) sorted inserts can run
+// from shared memory afterwards.  So a sub-tile is scanned against a threshold that is fixed for the whole
+// sub-tile (warm-up floor / the list's current KL-th value), survivors are appended as (value, column) pairs
+// to a per-thread queue, the TMEM buffer is handed back to the MMA warp at once, and only then is the queue
+// drained into the list -- in lock-step over one dense batch per sub-tile, while the tensor core already works
+// two sub-tiles ahead.  The epilogue leaves the critical path of the MMAs entirely.
+template <int NTHR, int DEPTH>
+struct CandQueue {
+  uint32_t base;  // shared-space byte address of entry 0 of this thread; entries are NTHR * 8 bytes apart
+  uint32_t wr;    // next free entry
+  __device__ __forceinline__ void init(uint32_t b) { base = wr = b; }
+  __device__ __forceinline__ int count() const { return static_cast<int>((wr - base) / (NTHR * 8)); }
+  // true when one more chunk could overflow some lane's queue
+  __device__ __forceinline__ bool nearly_full() const {
+    return __reduce_max_sync(0xffffffffu, count()) > DEPTH - kChunk;
+  }
+};
+
+// Branch-free append: every value is stored at the write cursor, the cursor only advances for survivors (the
+// next store overwrites a non-survivor).  Inline-asm stores inside an `if` would be compiled as 32 divergent
+// branches per chunk.  The queue therefore has DEPTH + 1 entries per thread (the last store may be a dud).
+template <int NTHR, int DEPTH>
+__device__ __forceinline__ void cand_append_chunk(CandQueue<NTHR, DEPTH>& q, const uint32_t (&r)[kChunk], int nv,
+                                                  int col_chunk, float thr) {
+  uint32_t wr = q.wr;
+#pragma unroll
+  for (int j = 0; j < kChunk; ++j) {
+    const bool pass = (__uint_as_float(r[j]) > thr) && (nv >= kChunk || j < nv);  // ragged tail: drop columns >= C
+    ptx::st_shared_v2(wr, r[j], static_cast<uint32_t>(col_chunk + j));
+    wr += pass ? NTHR * 8 : 0;
+  }
+  q.wr = wr;
+}
+
+template <int KL, int NTHR, int DEPTH>
+__device__ __forceinline__ void cand_drain(SortedList<KL>& list, CandQueue<NTHR, DEPTH>& q) {
+  const int cnt = q.count();
+  const int maxc = __reduce_max_sync(0xffffffffu, cnt);
+  uint32_t rd = q.base;
+  for (int e = 0; e < maxc; ++e) {
+    if (e < cnt) {
+      uint32_t xb, col;
+      ptx::ld_shared_v2(rd, xb, col);
+      rd += NTHR * 8;
+      const float x = __uint_as_float(xb);
+      if (x > list.thr()) list.insert(x, static_cast<int32_t>(col));
+    }
+  }
+  q.wr = q.base;
+}
+
 // CTA-pair kernel (score_umma2.cu)
 // wpq = epilogue warps per TMEM lane quarter (1 or 2).  The epilogue is bound by the ALU pipe (FSETP / FSEL /
 // SEL issue every other cycle per sub-partition), not by latency, so ONE warp per quarter keeping ONE list per
 // row is the cheapest arrangement: a second warp would halve each stream and pay the list warm-up twice.
-int pair_wpq();
+int pair_wpq(int KL);
 int launch_pair_kernel(int epi, int KL, int wpq, const CUtensorMap& mx, const CUtensorMap& mb, const Params& p,
                        cudaStream_t stream);
 

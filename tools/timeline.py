@@ -15,7 +15,7 @@ def emb(n, d, seed):
 
 
 names = ["entry", "setup", "first_full", "last_mma_issued", "acc0", "acc1", "acc2", "acc3", "epi0", "epi1", "epi2", "epi3",
-         "epi_done", "exit", "-", "-"]
+         "epi_done", "exit", "release0", "release1", "-", "-", "-", "-", "-", "mma_grant0", "mma_grant1", "mma_grant2"]
 for (B, C, D, impl, tag) in ((512, 21841, 1024, ops.HGR_IMPL_TCGEN05 | _cabi.HGR_IMPL_FLAG_NO_MERGE, "prod"),
                              (512, 21841, 1024, ops.HGR_IMPL_TCGEN05_NULL, "null"),
                              (512, 2731, 1024, ops.HGR_IMPL_TCGEN05_NULL, "null-small")):
