@@ -161,6 +161,8 @@ def run_ours(args):
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("HGR_RESERVE_SMS", "8")    # leave SMs for NCCL / merge to overlap the GEMM
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if world != args.gpus:
         if args.gpus > 1 and world == 1:
@@ -417,7 +419,11 @@ def run_ours(args):
         }
         print(json.dumps(line))
     if world > 1:
-        dist.destroy_process_group()
+        # CUDA graphs hold NCCL kernels: tear down without destroy_process_group (which can block on them)
+        sys.stdout.flush()
+        torch.cuda.synchronize()
+        dist.barrier()
+        os._exit(0)
     return 0
 
 

@@ -282,8 +282,21 @@ int launch_kernel(const CUtensorMap& mx, const CUtensorMap& mb, const Params& p,
   return HGR_OK;
 }
 
+// SMs left free for concurrently running small kernels (NCCL, merge, normalise of neighbouring batches): the
+// persistent GEMM CTAs take a whole SM each (shared memory), so anything else can only overlap on SMs it does
+// not occupy.  HGR_RESERVE_SMS (default 0) trades that many SMs of GEMM throughput for the overlap.
+int usable_sms() {
+  static const int reserve = [] {
+    const char* e = getenv("HGR_RESERVE_SMS");
+    const int r = e ? atoi(e) : 0;
+    return r < 0 ? 0 : r;
+  }();
+  const int n = num_sms() - reserve;
+  return n < 2 ? 2 : n;
+}
+
 Sched pick_sched(int64_t B, int64_t C, bool pair) {
-  return pair ? make_sched(B, C, num_sms() / 2, 2 * kTileM) : make_sched(B, C, num_sms(), kTileM);
+  return pair ? make_sched(B, C, usable_sms() / 2, 2 * kTileM) : make_sched(B, C, usable_sms(), kTileM);
 }
 
 int common_setup(const __nv_bfloat16* X, const __nv_bfloat16* bank, int64_t B, int64_t C, int64_t D, bool pair,
