@@ -161,8 +161,6 @@ def run_ours(args):
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
-    if world > 1:
-        os.environ.setdefault("HGR_RESERVE_SMS", "8")    # leave SMs for NCCL / merge to overlap the GEMM
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if world != args.gpus:
         if args.gpus > 1 and world == 1:

@@ -27,7 +27,10 @@ constexpr int kPairStagesMax = 6;
 #define HGR_DEFER_DEPTH 64
 #endif
 constexpr int kDeferDepth = HGR_DEFER_DEPTH;                 // candidate slots per row (divided among the WPQ warps)
-constexpr int kDeferStages = kDeferDepth > 64 ? 4 : 5;      // operand stages that still fit beside the queue
+// Operand stages: as many 32 KB stages as fit beside the epilogue's staging memory (measured: 4 stages cost
+// ~2 us of main loop at cfg 2, and leaving room for co-resident small kernels bought nothing).
+constexpr int kDeferStages = kDeferDepth > 64 ? 4 : 5;
+constexpr int kOtherStages = 6;
 constexpr int kPairBBytes = (kSubN / 2) * kBlockK * 2;     // 16 KB: half of the bank sub-tile
 constexpr int kPairStageBytes = kABytes + kPairBBytes;     // 32 KB
 
@@ -47,7 +50,7 @@ score_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
   constexpr int kQueueDepth = kDeferDepth / WPQ;   // deferred-insert queue entries per thread
   constexpr int kQueueBytes = EPI == kEpiTopkQueue ? kChunk * kEpiThreads * 4
                             : EPI == kEpiTopkDefer ? (kQueueDepth + 1) * kEpiThreads * 8 : 0;
-  constexpr int kPairStages = EPI == kEpiTopkDefer ? kDeferStages : 6;
+  constexpr int kPairStages = EPI == kEpiTopkDefer ? kDeferStages : kOtherStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* stage_base = smem;
@@ -278,7 +281,7 @@ int launch_one(const CUtensorMap& mx, const CUtensorMap& mb, const Params& p, cu
   constexpr int threads = 64 + 128 * WPQ;
   constexpr size_t queue = EPI == kEpiTopkQueue ? static_cast<size_t>(kChunk) * 128 * WPQ * 4
                          : EPI == kEpiTopkDefer ? static_cast<size_t>(kDeferDepth / WPQ + 1) * 128 * WPQ * 8 : 0;
-  const size_t smem = 1024 + static_cast<size_t>(EPI == kEpiTopkDefer ? kDeferStages : 6) * kPairStageBytes + queue + sizeof(PairCtl);
+  const size_t smem = 1024 + static_cast<size_t>(EPI == kEpiTopkDefer ? kDeferStages : kOtherStages) * kPairStageBytes + queue + sizeof(PairCtl);
   auto kern = score_umma_pair_kernel<EPI, KL, WPQ>;
   HGR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   kern<<<2 * p.sched.G, threads, smem, stream>>>(mx, mb, p);

@@ -146,8 +146,8 @@ class ShardedEvalStream:
         x = ops.normalize_rows(self.dev_feats[s])
         bank = self.banks[s % len(self.banks)]
         if bank.shape[0] > 0:
-            val, idx = ops.score_topk(x, bank, id_base=self.id_base, K=self.K)
-            pack_candidates(val, idx, self.send[s])
+            # results go straight into the send record (no pack copies)
+            ops.score_topk(x, bank, id_base=self.id_base, K=self.K, out=(self.send[s][0].view(torch.float32), self.send[s][1]))
         else:
             self.send[s][0].copy_(torch.full((self.B, self.K), float("-inf"), device=self.device).view(torch.int32))
             self.send[s][1].fill_(-1)

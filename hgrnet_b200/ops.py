@@ -98,7 +98,8 @@ def normalize_rows(x: torch.Tensor, out_dtype=torch.bfloat16, return_norm: bool 
 
 def score_topk(X: torch.Tensor, bank: torch.Tensor, *, col_id: Optional[torch.Tensor] = None, id_base: int = 0,
                targets: Optional[torch.Tensor] = None, K: int = 20, scale: float = 1.0,
-               hits: Optional[torch.Tensor] = None, impl: int = HGR_IMPL_AUTO) -> Tuple[torch.Tensor, torch.Tensor]:
+               hits: Optional[torch.Tensor] = None, impl: int = HGR_IMPL_AUTO,
+               out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None) -> Tuple[torch.Tensor, torch.Tensor]:
     """Fused logits + per-row sorted top-K (+ Hit@k accumulation into ``hits``).
 
     model/clip_tree.py:331 + main.py:136-147.  Returns ``(val [B,K] fp32, idx [B,K] int32 node ids)``.
@@ -120,8 +121,14 @@ def score_topk(X: torch.Tensor, bank: torch.Tensor, *, col_id: Optional[torch.Te
             raise ValueError("targets must have one entry per image row")
     if hits is not None:
         hits = _require(hits, "hits", torch.int64)
-    val = torch.empty((B, K), dtype=torch.float32, device=X.device)
-    idx = torch.empty((B, K), dtype=torch.int32, device=X.device)
+    if out is not None:
+        val, idx = out
+        if val.shape != (B, K) or idx.shape != (B, K) or val.dtype != torch.float32 or idx.dtype != torch.int32 \
+                or not val.is_contiguous() or not idx.is_contiguous():
+            raise ValueError("out must be contiguous (float32 [B,K], int32 [B,K])")
+    else:
+        val = torch.empty((B, K), dtype=torch.float32, device=X.device)
+        idx = torch.empty((B, K), dtype=torch.int32, device=X.device)
     nbytes = lib.hgr_score_topk_workspace_bytes(B, C, D, K)
     ws = _workspace(nbytes, X.device)
     _cabi.check(lib.hgr_score_topk(_ptr(X), _ptr(bank), _ptr(col_id), id_base, _ptr(targets), B, C, D,
