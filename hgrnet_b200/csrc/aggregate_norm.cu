@@ -153,6 +153,67 @@ aggregate_normalize_kernel(const TIn* __restrict__ E, int D8, const int32_t* __r
   }
 }
 
+// Identity CSR (row r = {src}, weight 1): the plain row normalise of update_classifier / forward.  No
+// accumulators besides the row itself, TWO rows per warp in flight, 2+ CTAs per SM: enough bytes in flight to
+// approach the HBM roofline on the 21,841-row bank.
+template <typename TIn, typename TOut, int MAXV>
+__global__ void __launch_bounds__(256, 2)
+normalize_rows_kernel(const TIn* __restrict__ E, int D8, const int32_t* __restrict__ row_map, int64_t n_out,
+                      TOut* __restrict__ out, float* __restrict__ out_norm) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  const int64_t D = static_cast<int64_t>(D8) * 8;
+  for (int64_t row = warp0; row < n_out; row += 2 * nwarps) {
+    const int64_t row2 = row + nwarps;
+    const bool has2 = row2 < n_out;
+    const int64_t s1 = row_map ? row_map[row] : row;
+    const int64_t s2 = has2 ? (row_map ? row_map[row2] : row2) : s1;
+    float a[MAXV][8], b[MAXV][8];
+#pragma unroll
+    for (int v = 0; v < MAXV; ++v) {
+      const int idx = lane + 32 * v;
+      if (idx < D8) {
+        Vec8<TIn>::load(E + s1 * D + idx * 8, a[v]);
+        Vec8<TIn>::load(E + s2 * D + idx * 8, b[v]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) a[v][e] = b[v][e] = 0.f;
+      }
+    }
+    float ssa = 0.f, ssb = 0.f;
+#pragma unroll
+    for (int v = 0; v < MAXV; ++v)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        ssa = fmaf(a[v][e], a[v][e], ssa);
+        ssb = fmaf(b[v][e], b[v][e], ssb);
+      }
+    ssa = warp_sum(ssa);
+    ssb = warp_sum(ssb);
+    const float na = sqrtf(ssa), nb = sqrtf(ssb);
+    if (out_norm && lane == 0) {
+      out_norm[row] = na;
+      if (has2) out_norm[row2] = nb;
+    }
+#pragma unroll
+    for (int v = 0; v < MAXV; ++v) {
+      const int idx = lane + 32 * v;
+      if (idx < D8) {
+        float o[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = __fdiv_rn(a[v][e], na);
+        Vec8<TOut>::store(out + row * D + idx * 8, o);
+        if (has2) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) o[e] = __fdiv_rn(b[v][e], nb);
+          Vec8<TOut>::store(out + row2 * D + idx * 8, o);
+        }
+      }
+    }
+  }
+}
+
 // Any D (multiple of 8): two passes over the gathered rows, nothing kept in registers.
 template <typename TIn, typename TOut>
 __global__ void __launch_bounds__(256)
@@ -215,6 +276,17 @@ int dispatch(const void* E, int64_t D, const int32_t* rowptr, const int32_t* col
   const int blocks = static_cast<int>(want < cap ? (want < 1 ? 1 : want) : cap);
   const TIn* e = static_cast<const TIn*>(E);
   TOut* o = static_cast<TOut*>(out);
+  if (rowptr == nullptr && D8 <= 128) {  // identity CSR: the specialised row normalise
+    const int64_t capn = static_cast<int64_t>(num_sms()) * 4;
+    const int64_t wantn = (n_out + 2 * rows_per_block - 1) / (2 * rows_per_block);
+    const int nb = static_cast<int>(wantn < capn ? (wantn < 1 ? 1 : wantn) : capn);
+    if (D8 <= 32) normalize_rows_kernel<TIn, TOut, 1><<<nb, threads, 0, stream>>>(e, D8, row_map, n_out, o, out_norm);
+    else if (D8 <= 64) normalize_rows_kernel<TIn, TOut, 2><<<nb, threads, 0, stream>>>(e, D8, row_map, n_out, o, out_norm);
+    else if (D8 <= 96) normalize_rows_kernel<TIn, TOut, 3><<<nb, threads, 0, stream>>>(e, D8, row_map, n_out, o, out_norm);
+    else normalize_rows_kernel<TIn, TOut, 4><<<nb, threads, 0, stream>>>(e, D8, row_map, n_out, o, out_norm);
+    HGR_CHECK_LAUNCH();
+    return HGR_OK;
+  }
 #define HGR_AGG_LAUNCH(MAXV)                                                                           \
   aggregate_normalize_kernel<TIn, TOut, MAXV><<<blocks, threads, 0, stream>>>(e, D8, rowptr, col, w,  \
                                                                                row_map, n_out, o, out_norm)

@@ -27,6 +27,8 @@ constexpr int kPairStagesMax = 6;
 #define HGR_DEFER_DEPTH 64
 #endif
 constexpr int kDeferDepth = HGR_DEFER_DEPTH;                 // candidate slots per row (divided among the WPQ warps)
+// per-thread queue depth: (depth + 1) * 128 * WPQ * 8 bytes must fit beside 5 operand stages
+__host__ __device__ constexpr int defer_depth(int wpq) { return wpq == 1 ? kDeferDepth : kDeferDepth / wpq - 1; }
 // Operand stages: as many 32 KB stages as fit beside the epilogue's staging memory (measured: 4 stages cost
 // ~2 us of main loop at cfg 2, and leaving room for co-resident small kernels bought nothing).
 constexpr int kDeferStages = kDeferDepth > 64 ? 4 : 5;
@@ -47,7 +49,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 128 * WPQ, 1)
 score_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_bank,
                        const Params p) {
   constexpr int kEpiThreads = 128 * WPQ;
-  constexpr int kQueueDepth = kDeferDepth / WPQ;   // deferred-insert queue entries per thread
+  constexpr int kQueueDepth = defer_depth(WPQ);    // deferred-insert queue entries per thread (+1 dud slot)
   constexpr int kQueueBytes = EPI == kEpiTopkQueue ? kChunk * kEpiThreads * 4
                             : EPI == kEpiTopkDefer ? (kQueueDepth + 1) * kEpiThreads * 8 : 0;
   constexpr int kPairStages = EPI == kEpiTopkDefer ? kDeferStages : kOtherStages;
@@ -73,7 +75,8 @@ score_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
     }
     for (int b = 0; b < 2; ++b) {
       ptx::mbar_init(&ctl->tmem_full[b], 1);
-      ptx::mbar_init(&ctl->tmem_empty[b], 2 * (kEpiThreads / 32));
+      // deferred epilogue: the WPQ warps of a quarter take whole sub-tiles in turn, so 4 warps per CTA arrive
+      ptx::mbar_init(&ctl->tmem_empty[b], EPI == kEpiTopkDefer ? 2 * 4 : 2 * (kEpiThreads / 32));
     }
     ptx::fence_mbar_init();
   }
@@ -175,69 +178,99 @@ score_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
     EpiClock ck(p.timeline != nullptr && epi_tid == 0);
     while (walk.next(t)) {
       const int buf = it & 1;
-      ck.start();
-      ptx::mbar_wait(&ctl->tmem_full[buf], (it >> 1) & 1);
-      ptx::tc_fence_after();
-      ck.lap(ck.wait);
-      if (epi_tid == 0 && it < 4) stamp(p, 4 + it);  // accumulator of sub-tile `it` ready
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + buf * kSubN;
       const int64_t row = static_cast<int64_t>(t.mt) * (2 * kTileM) + row_in_tile;
       if (t.first) {
         list.init();
         null_acc = -INFINITY;
         floor_thr = -INFINITY;
       }
-      if (EPI == kEpiTopkQueue && t.seq < 2) {  // warm-up floor from the first two sub-tiles of a segment
-        floor_thr = fmaxf(floor_thr, warmup_floor<KL, WPQ>(taddr, member, t.nvalid));
-        ck.lap(ck.warm);
-      }
-      float sub_thr = -INFINITY;
-      if (EPI == kEpiTopkDefer) {
-        if (t.seq == 0) floor_thr = warmup_floor<KL, WPQ>(taddr, member, t.nvalid);
-        ck.lap(ck.warm);
-        sub_thr = fmaxf(floor_thr, list.thr());   // fixed for the whole sub-tile
-      }
-      for (int c0 = member * kChunk; c0 < t.nvalid; c0 += WPQ * kChunk) {
-        uint32_t r[kChunk];
-        ck.start();
-        ptx::tmem_ld_x32(taddr + c0, r);
-        ptx::tmem_ld_wait();
-        ck.lap(ck.ld);
-        const int nv = t.nvalid - c0;
-        if (EPI == kEpiDense) {
-          if (row < p.B) {
-            float* o = p.dense_out + row * p.ldo + t.col0 + c0;
-#pragma unroll
-            for (int j = 0; j < kChunk; ++j)
-              if (j < nv) o[j] = __uint_as_float(r[j]) * p.scale;
-          }
-        } else if (EPI == kEpiTopkQueue) {
-          scan_chunk_queue<KL>(list, r, nv, t.col0 + c0, qaddr, qswz, floor_thr, ck);
-        } else if (EPI == kEpiTopkDefer) {
-          if (cq.nearly_full()) {                 // rare: a lane collected > depth - 32 survivors
-            cand_drain<KL>(list, cq);
-            sub_thr = fmaxf(sub_thr, list.thr());
-            ck.lap(ck.drain);
-          }
-          cand_append_chunk(cq, r, nv, t.col0 + c0, sub_thr);
-          ck.lap(ck.scan);
-        } else {
-#pragma unroll
-          for (int j = 0; j < kChunk; ++j) null_acc = fmaxf(null_acc, __uint_as_float(r[j]));
+      // deferred epilogue: this warp owns every WPQ-th sub-tile of the segment (all its chunks); otherwise the
+      // WPQ warps of a quarter split the chunks of every sub-tile
+      const bool mine = (EPI != kEpiTopkDefer) || (t.seq % WPQ == member);
+      // every warp observes every phase of the barrier in order (a skipped phase would alias on the parity bit);
+      // waiting for a sub-tile it does not own costs nothing: its next own sub-tile completes later anyway
+      ck.start();
+      ptx::mbar_wait(&ctl->tmem_full[buf], (it >> 1) & 1);
+      ptx::tc_fence_after();
+      ck.lap(ck.wait);
+      if (mine) {
+        if (epi_tid == 0 && it < 4) stamp(p, 4 + it);  // accumulator of sub-tile `it` ready
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + buf * kSubN;
+        if (EPI == kEpiTopkQueue && t.seq < 2) {  // warm-up floor from the first two sub-tiles of a segment
+          floor_thr = fmaxf(floor_thr, warmup_floor<KL, WPQ>(taddr, member, t.nvalid));
+          ck.lap(ck.warm);
         }
-      }
-      // this CTA's half of the accumulator buffer is drained: tell the leader's MMA thread
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if (rank == 0) ptx::mbar_arrive(&ctl->tmem_empty[buf]);
-        else ptx::mbar_arrive_cluster(ptx::mapa_shared(ptx::smem_u32(&ctl->tmem_empty[buf]), 0));
-      }
-      if (epi_tid == 0 && it < 2) stamp(p, 14 + it);  // buffer of sub-tile `it` handed back
-      if (EPI == kEpiTopkDefer) {  // the buffer is already back with the tensor core: now pay for the inserts
-        ck.start();
-        cand_drain<KL>(list, cq);
-        ck.lap(ck.drain);
+        float sub_thr = -INFINITY;
+        if (EPI == kEpiTopkDefer) {
+          if (t.seq < WPQ) floor_thr = warmup_floor<KL, 1>(taddr, 0, t.nvalid);  // this warp's first sub-tile
+          ck.lap(ck.warm);
+          sub_thr = fmaxf(floor_thr, list.thr());   // fixed for the whole sub-tile
+        }
+        const int c_begin = EPI == kEpiTopkDefer ? 0 : member * kChunk;
+        const int c_step = EPI == kEpiTopkDefer ? kChunk : WPQ * kChunk;
+        for (int c0 = c_begin; c0 < t.nvalid; c0 += c_step) {
+          uint32_t r[kChunk];
+          ck.start();
+          ptx::tmem_ld_x32(taddr + c0, r);
+          ptx::tmem_ld_wait();
+          ck.lap(ck.ld);
+          const int nv = t.nvalid - c0;
+          if (EPI == kEpiDense) {
+            if (row < p.B) {
+              float* o = p.dense_out + row * p.ldo + t.col0 + c0;
+#pragma unroll
+              for (int j = 0; j < kChunk; ++j)
+                if (j < nv) o[j] = __uint_as_float(r[j]) * p.scale;
+            }
+          } else if (EPI == kEpiTopkQueue) {
+            scan_chunk_queue<KL>(list, r, nv, t.col0 + c0, qaddr, qswz, floor_thr, ck);
+          } else if (EPI == kEpiTopkDefer) {
+            if (kQueueDepth >= 2 * kChunk) {
+              // deep queue: make room for a whole chunk up front (rare), then append without bounds checks
+              if (__reduce_max_sync(0xffffffffu, cq.count()) > kQueueDepth - kChunk) {
+                ck.lap(ck.scan);
+                cand_drain<KL>(list, cq);
+                sub_thr = fmaxf(sub_thr, list.thr());
+                ck.lap(ck.drain);
+              }
+              cand_append_chunk_roomy(cq, r, nv, t.col0 + c0, sub_thr);
+              ck.lap(ck.scan);
+              continue;
+            }
+            const uint32_t wr0 = cq.wr;
+            if (!cand_append_chunk(cq, r, nv, t.col0 + c0, sub_thr)) {  // a lane ran out of slots (rare):
+              cq.wr = wr0;                                              // rewind, insert what is queued,
+              ck.lap(ck.scan);
+              cand_drain<KL>(list, cq);                                 // tighten the threshold and redo the chunk
+              sub_thr = fmaxf(sub_thr, list.thr());
+              ck.lap(ck.drain);
+              if (!cand_append_chunk(cq, r, nv, t.col0 + c0, sub_thr)) {
+                // more survivors in ONE chunk than the queue holds (list still warming up): insert straight
+                // from TMEM, column by column
+                cq.wr = cq.base;
+                scan_chunk_reload<KL>(list, r, nv, taddr + c0, t.col0 + c0);
+                sub_thr = fmaxf(sub_thr, list.thr());
+              }
+            }
+            ck.lap(ck.scan);
+          } else {
+#pragma unroll
+            for (int j = 0; j < kChunk; ++j) null_acc = fmaxf(null_acc, __uint_as_float(r[j]));
+          }
+        }
+        // this CTA's half of the accumulator buffer is drained: tell the leader's MMA thread
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (rank == 0) ptx::mbar_arrive(&ctl->tmem_empty[buf]);
+          else ptx::mbar_arrive_cluster(ptx::mapa_shared(ptx::smem_u32(&ctl->tmem_empty[buf]), 0));
+        }
+        if (epi_tid == 0 && it < 2) stamp(p, 14 + it);  // buffer of sub-tile `it` handed back
+        if (EPI == kEpiTopkDefer) {  // the buffer is already back with the tensor core: now pay for the inserts
+          ck.start();
+          cand_drain<KL>(list, cq);
+          ck.lap(ck.drain);
+        }
       }
       if (epi_tid == 0 && it < 4) stamp(p, 8 + it);  // this warp is done with sub-tile `it`
       if (EPI != kEpiDense && t.last && row < p.B) {
@@ -280,7 +313,7 @@ template <int EPI, int KL, int WPQ>
 int launch_one(const CUtensorMap& mx, const CUtensorMap& mb, const Params& p, cudaStream_t stream) {
   constexpr int threads = 64 + 128 * WPQ;
   constexpr size_t queue = EPI == kEpiTopkQueue ? static_cast<size_t>(kChunk) * 128 * WPQ * 4
-                         : EPI == kEpiTopkDefer ? static_cast<size_t>(kDeferDepth / WPQ + 1) * 128 * WPQ * 8 : 0;
+                         : EPI == kEpiTopkDefer ? static_cast<size_t>(defer_depth(WPQ) + 1) * 128 * WPQ * 8 : 0;
   const size_t smem = 1024 + static_cast<size_t>(EPI == kEpiTopkDefer ? kDeferStages : kOtherStages) * kPairStageBytes + queue + sizeof(PairCtl);
   auto kern = score_umma_pair_kernel<EPI, KL, WPQ>;
   HGR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));

@@ -230,23 +230,40 @@ struct CandQueue {
   uint32_t base;  // shared-space byte address of entry 0 of this thread; entries are NTHR * 8 bytes apart
   uint32_t wr;    // next free entry
   __device__ __forceinline__ void init(uint32_t b) { base = wr = b; }
+  __device__ __forceinline__ uint32_t limit() const { return base + DEPTH * NTHR * 8; }  // the dud slot
   __device__ __forceinline__ int count() const { return static_cast<int>((wr - base) / (NTHR * 8)); }
-  // true when one more chunk could overflow some lane's queue
-  __device__ __forceinline__ bool nearly_full() const {
-    return __reduce_max_sync(0xffffffffu, count()) > DEPTH - kChunk;
-  }
 };
 
 // Branch-free append: every value is stored at the write cursor, the cursor only advances for survivors (the
-// next store overwrites a non-survivor).  Inline-asm stores inside an `if` would be compiled as 32 divergent
-// branches per chunk.  The queue therefore has DEPTH + 1 entries per thread (the last store may be a dud).
+// next store overwrites a non-survivor) and saturates at the last slot, which therefore only ever holds duds.
+// (Inline-asm stores inside an `if` would be compiled as 32 divergent branches per chunk.)  The queue has
+// DEPTH + 1 entries per thread.  Returns false when some lane of the warp ran out of slots: the caller then
+// rewinds, drains and appends the same chunk again.
 template <int NTHR, int DEPTH>
-__device__ __forceinline__ void cand_append_chunk(CandQueue<NTHR, DEPTH>& q, const uint32_t (&r)[kChunk], int nv,
+__device__ __forceinline__ bool cand_append_chunk(CandQueue<NTHR, DEPTH>& q, const uint32_t (&r)[kChunk], int nv,
                                                   int col_chunk, float thr) {
   uint32_t wr = q.wr;
+  const uint32_t lim = q.limit();
 #pragma unroll
   for (int j = 0; j < kChunk; ++j) {
     const bool pass = (__uint_as_float(r[j]) > thr) && (nv >= kChunk || j < nv);  // ragged tail: drop columns >= C
+    ptx::st_shared_v2(wr, r[j], static_cast<uint32_t>(col_chunk + j));
+    wr += pass ? NTHR * 8 : 0;
+    wr = wr < lim ? wr : lim;
+  }
+  q.wr = wr;
+  return !__any_sync(0xffffffffu, wr >= lim);
+}
+
+// Same without the per-value saturation (one op less on the cursor's dependency chain): the caller guarantees
+// room for a whole chunk (count <= DEPTH - 32 in every lane).
+template <int NTHR, int DEPTH>
+__device__ __forceinline__ void cand_append_chunk_roomy(CandQueue<NTHR, DEPTH>& q, const uint32_t (&r)[kChunk],
+                                                        int nv, int col_chunk, float thr) {
+  uint32_t wr = q.wr;
+#pragma unroll
+  for (int j = 0; j < kChunk; ++j) {
+    const bool pass = (__uint_as_float(r[j]) > thr) && (nv >= kChunk || j < nv);
     ptx::st_shared_v2(wr, r[j], static_cast<uint32_t>(col_chunk + j));
     wr += pass ? NTHR * 8 : 0;
   }

@@ -116,6 +116,7 @@ class tree_model(nn.Module):
         self.zsl_weights: Optional[torch.Tensor] = None   # [N, D] bf16 class bank
         self.bank_test: Optional[torch.Tensor] = None     # [C, D] bf16 rows of test_index
         self._rng = random  # Python's global RNG, as the reference (clip_tree.py:82,134,189)
+        self._contra_cache = {}  # depth window -> candidate set (sampling.contra_topk)
 
     # ------------------------------------------------------------------ checkpoint
     def save(self, opts, epoch):
@@ -125,7 +126,8 @@ class tree_model(nn.Module):
     # ------------------------------------------------------------------ sampling / weights
     def _contra_ids(self, method, target, depth=None, parents=None):
         if method == "topk":
-            return contra_topk(self.d2n, target, depth, parents, self.opts.k, self.opts.num_compare, self._rng)
+            return contra_topk(self.d2n, target, depth, parents, self.opts.k, self.opts.num_compare, self._rng,
+                               cache=self._contra_cache)
         if method == "random":
             return contra_random(self._train_ids_host, target, self.opts.num_compare, self._rng)
         if method == "brothers":
@@ -225,10 +227,15 @@ class tree_model(nn.Module):
         return its
 
     @staticmethod
-    def _iteration_weight(recipe, lw):
+    def _iteration_weight(recipe, lw, memo=None):
         w = None
         for (method, n, pos) in recipe:
-            f = level_weights(method, n, lw)[pos]
+            vec = memo.get((method, n)) if memo is not None else None
+            if vec is None:
+                vec = level_weights(method, n, lw)
+                if memo is not None:
+                    memo[(method, n)] = vec
+            f = vec[pos]
             w = f if w is None else w * f
         return w
 
@@ -251,7 +258,8 @@ class tree_model(nn.Module):
             set_col.extend(pos_of[i] for i in ids)
             set_ptr[t + 1] = len(set_col)
         lw_host = self._layer_weight_host()
-        weight_host = torch.stack([self._iteration_weight(r, lw_host) for _, _, r in its]).float()
+        memo = {}
+        weight_host = torch.stack([self._iteration_weight(r, lw_host, memo) for _, _, r in its]).float()
         meta = torch.from_numpy(np.concatenate([set_ptr, np.asarray(set_col, np.int32),
                                                 np.asarray([p for _, p, _ in its], np.int32)])).to(self.device)
         d_set_ptr, d_set_col, d_label = meta[:T + 1], meta[T + 1:T + 1 + len(set_col)], meta[T + 1 + len(set_col):]
@@ -285,7 +293,8 @@ class tree_model(nn.Module):
         lw_param = getattr(self, "layer_weight", None)
         if lw_param is not None and lw_param.requires_grad and self.opts.weights == "adaptive":
             lw_leaf = lw_host.clone().requires_grad_(True)
-            w_again = torch.stack([self._iteration_weight(r, lw_leaf) for _, _, r in its])
+            memo = {}
+            w_again = torch.stack([self._iteration_weight(r, lw_leaf, memo) for _, _, r in its])
             ((loss_host / weight_host).detach() * w_again).sum().backward()            # d loss_t / d w_t = CE_t
             g = lw_leaf.grad.to(lw_param.device, lw_param.dtype)
             lw_param.grad = g if lw_param.grad is None else lw_param.grad + g

@@ -12,21 +12,33 @@ from __future__ import annotations
 import copy
 import math
 import random as _random
-from typing import List, Sequence, Tuple
+from typing import List, Optional, Sequence, Tuple
 
 
 def contra_topk(d2n, target: int, depth: int, parents: Sequence[int], k: int, num_compare: int,
-                rng=_random) -> Tuple[List[int], int]:
-    """model/clip_tree.py:116-141.  Returns ``(compare_idx, label_position)``."""
+                rng=_random, cache: Optional[dict] = None) -> Tuple[List[int], int]:
+    """model/clip_tree.py:116-141.  Returns ``(compare_idx, label_position)``.
+
+    ``cache`` (optional dict owned by the caller) memoises the candidate SET of a depth window: it only depends
+    on ``(low, depth)``, and a set built from the same insertion sequence has the same iteration order, so the
+    list handed to ``random.sample`` -- and therefore the draw -- is exactly what rebuilding it every call
+    (as the reference does, :125-131) would give.  At 21,841 nodes this is ~95 % of the step's host time.
+    """
     low = min(d2n.keys())
     if depth - k > low:
         low = depth - k
-    candi: List[int] = []
-    for d in range(low, depth):
-        candi.extend(d2n[d])
-    if depth == 0:
-        candi.extend(d2n[depth])
-    compare_idx = list(set(candi) - set(parents))
+    key = (low, depth)
+    candi_set = cache.get(key) if cache is not None else None
+    if candi_set is None:
+        candi: List[int] = []
+        for d in range(low, depth):
+            candi.extend(d2n[d])
+        if depth == 0:
+            candi.extend(d2n[depth])
+        candi_set = set(candi)
+        if cache is not None:
+            cache[key] = candi_set
+    compare_idx = list(candi_set - set(parents))
     if len(compare_idx) > num_compare:
         compare_idx = rng.sample(compare_idx, num_compare)
     if target not in compare_idx:

@@ -1,0 +1,153 @@
+"""Measurements of the rows of SURVEY.md section 8d that are not the bench.py headline:
+
+* cfg 3 -- one OM training step of the head (B=256, D=1024, 12-level 21,841-node hierarchy, out 0.25 / in 0.5,
+  adaptive weights, --k 1, num_compare 256, deepest-level target): `tree_model.train_batch` (kernel 1 + dense
+  logits + fused masked CE, all T iterations in one launch) vs the reference's per-iteration torch loop on the
+  same GPU and on the host CPU;
+* kernel (3) alone: microseconds and achieved GB/s against the HBM roofline (algorithmic bytes 8*B*U);
+* kernel (1) at bank size (21,841 x 1024): achieved GB/s, identity CSR and a chain-aggregated CSR.
+Prints one JSON object; run on the GPU box.
+"""
+import json
+import os
+import random
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+
+from hgrnet_b200 import ops
+from hgrnet_b200.flags import parse_args
+from hgrnet_b200.head import tree_model
+from hgrnet_b200.hierarchy import WORDNET_LIKE_21841, synthetic_hierarchy
+from hgrnet_b200.levels import level_weights
+from hgrnet_b200.synthetic import TableEncoder, node_id_tokens, synthetic_embeddings
+
+DEV = "cuda:0"
+HBM = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))["hbm_gbs"] \
+    if os.path.exists(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")) else 6650.0
+
+
+def events(fn, n, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n * 1e3  # us
+
+
+def torch_loop_step(model, img, target, device):
+    """The reference's OM loop (clip_tree.py:222-281) with stock torch ops on `device` (fp32)."""
+    from oracle import hgr_oracle as orc
+    enc = model.clip_model
+    img_feats = enc.encode_image(img)
+    img_n = img_feats / img_feats.norm(dim=-1, keepdim=True)
+    img_ = img_n.detach().clone().requires_grad_(True)
+    lw = model.layer_weight.detach() if hasattr(model, "layer_weight") else None
+    ce = torch.nn.CrossEntropyLoss()
+    losses = []
+    for (k_loop, m_loop, p_out, depth, parents_in, n_out, n_in) in orc.om_schedule(model.c2p, target, model.opts.out_ratio, model.opts.in_ratio):
+        ids, labels = orc.get_contra_topk(model.d2n, p_out, img.shape[0], depth, parents_in, model.opts.k, model.opts.num_compare)
+        tf = enc.encode_text(model.node_tokens[torch.tensor(ids, device=device)])
+        tf = tf / tf.norm(dim=-1, keepdim=True)
+        logits = (img_ @ tf.t()) * enc.logit_scale.exp()
+        w_in = orc.get_weights(model.opts.weights, n_in, lw.cpu() if lw is not None else None)
+        w_out = orc.get_weights(model.opts.weights, n_out, lw.cpu() if lw is not None else None)
+        loss_j = ce(logits, torch.tensor(labels, device=device)) * float(w_in[m_loop]) * float(w_out[k_loop])
+        loss_j.backward()
+        losses.append(loss_j.item())
+    img_feats.backward(img_.grad)
+    return sum(losses), len(losses)
+
+
+def main():
+    out = {}
+    hier = synthetic_hierarchy(WORDNET_LIKE_21841, seed=1)
+    N, D, B = len(hier), 1024, 256
+    table = synthetic_embeddings(N, D, 1, normalize=False)
+    opts = parse_args([])
+    opts.device, opts.folder = 0, "/tmp/hgr_om_bench"
+    model = tree_model(opts, hier.nodes, hier.nodes, clip_model=TableEncoder(table).to(DEV), hierarchy=hier,
+                       node_tokens=node_id_tokens(N))
+    target = N - 1                                     # deepest level: chain of 12 -> T = 17
+    img = synthetic_embeddings(B, D, 5, normalize=False).to(DEV).requires_grad_(True)
+    targets = torch.full((B,), target, dtype=torch.long, device=DEV)
+
+    def ours():
+        random.seed(0)
+        return model.train_batch(img, targets, "OM", "topk")
+
+    loss = ours()
+    T = len(model.last_losses)
+    random.seed(0)
+    ref_loss, T_ref = torch_loop_step(model, img, target, DEV)
+    us_ours = events(ours, 30)
+    us_loop = events(lambda: (random.seed(0), torch_loop_step(model, img, target, DEV)), 10)
+    # host CPU (reference torch ops, fp32)
+    model_cpu_enc = TableEncoder(table)
+    class _M:  # duck-typed view of the model on the CPU
+        pass
+    m = _M()
+    m.clip_model, m.c2p, m.d2n, m.opts, m.node_tokens = model_cpu_enc, model.c2p, model.d2n, model.opts, model.node_tokens.cpu()
+    m.layer_weight = model.layer_weight.detach().cpu()
+    img_cpu = img.detach().cpu().requires_grad_(True)
+    random.seed(0)
+    torch_loop_step(m, img_cpu, target, "cpu")
+    t0 = time.perf_counter()
+    for _ in range(3):
+        random.seed(0)
+        torch_loop_step(m, img_cpu, target, "cpu")
+    us_cpu = (time.perf_counter() - t0) / 3 * 1e6
+    out["om_step_cfg3"] = {"B": B, "D": D, "T": T, "loss_ours": loss, "loss_torch_loop": ref_loss,
+                           "us_per_step_ours": us_ours, "us_per_step_torch_loop_gpu": us_loop,
+                           "us_per_step_torch_loop_cpu": us_cpu, "cpu_threads": torch.get_num_threads(),
+                           "speedup_vs_gpu_loop": us_loop / us_ours, "speedup_vs_cpu": us_cpu / us_ours,
+                           "note": "encoders are table look-ups here, so this is the head alone (the reference's step is dominated by encode_text)"}
+
+    # ---- kernel (3) alone at cfg-3 shape: union of T=17 sets of <=257 classes
+    rng = np.random.RandomState(0)
+    U = 3000
+    logits = torch.randn(B, U, device=DEV) * 3
+    sets = [rng.permutation(U)[:257] for _ in range(17)]
+    set_ptr = torch.tensor(np.concatenate([[0], np.cumsum([len(s) for s in sets])]).astype(np.int32), device=DEV)
+    set_col = torch.tensor(np.concatenate(sets).astype(np.int32), device=DEV)
+    lp = torch.tensor(rng.randint(0, 257, 17).astype(np.int32), device=DEV)
+    w = torch.rand(17, device=DEV)
+    us_ce = events(lambda: ops.masked_ce(logits, set_ptr, set_col, lp, w), 200)
+    bytes_ce = 8.0 * B * U
+    out["masked_ce_kernel"] = {"B": B, "U": U, "T": 17, "us": us_ce, "algorithmic_bytes": bytes_ce,
+                               "achieved_GBs": bytes_ce / (us_ce * 1e-6) / 1e9, "hbm_peak_GBs": HBM,
+                               "frac": bytes_ce / (us_ce * 1e-6) / 1e9 / HBM,
+                               "note": "2 launches (CE + loss reduce); latency-bound at this size"}
+
+    # ---- kernel (1) at bank size
+    E = synthetic_embeddings(N, D, 2, normalize=False).to(DEV)
+    us_id = events(lambda: ops.aggregate_normalize(E), 100)
+    b_id = N * D * 4 + N * D * 2
+    Eb = E.bfloat16()
+    us_id16 = events(lambda: ops.aggregate_normalize(Eb), 100)
+    b_id16 = N * D * 2 * 2
+    rp, col, wt = hier.chain_csr(0.25, lambda n: level_weights("increasing", n).numpy())
+    t = lambda a: torch.from_numpy(a).to(DEV)
+    rp_d, col_d, w_d = t(rp), t(col), t(wt)
+    us_ch = events(lambda: ops.aggregate_normalize(Eb, rp_d, col_d, w_d), 100)
+    nnz = int(rp[-1])
+    b_ch = 2 * N * D * 2 + 4 * (nnz + N + 1) + 4 * nnz       # compulsory: every source row once + output + CSR
+    out["aggregate_normalize_bank"] = {
+        "N": N, "D": D, "hbm_peak_GBs": HBM,
+        "identity_fp32_in": {"us": us_id, "bytes": b_id, "GBs": b_id / us_id / 1e3, "frac": b_id / us_id / 1e3 / HBM},
+        "identity_bf16_in": {"us": us_id16, "bytes": b_id16, "GBs": b_id16 / us_id16 / 1e3, "frac": b_id16 / us_id16 / 1e3 / HBM},
+        "chain_csr_bf16_in": {"us": us_ch, "nnz": nnz, "compulsory_bytes": b_ch, "GBs": b_ch / us_ch / 1e3,
+                              "frac": b_ch / us_ch / 1e3 / HBM, "gathered_GBs": (nnz * D * 2 + N * D * 2) / us_ch / 1e3}}
+    print(json.dumps(out, indent=1))
+
+
+if __name__ == "__main__":
+    main()
