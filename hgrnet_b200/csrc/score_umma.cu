@@ -331,8 +331,8 @@ double overflow_bound(int K, int KL, int lists) {
 int pick_list_len(int K, int64_t B, int lists_per_row, bool allow_speculation) {
   const int exact = K <= 8 ? 8 : (K <= 12 ? 12 : (K <= 20 ? 20 : 32));
   if (!allow_speculation) return exact;
-  const int cand[3] = {8, 10, 12};
-  for (int i = 0; i < 3; ++i) {
+  const int cand[4] = {8, 10, 12, 16};
+  for (int i = 0; i < 4; ++i) {
     const int kl = cand[i];
     if (kl >= K) break;
     if (static_cast<double>(B) * lists_per_row * overflow_bound(K, kl, lists_per_row) < 1e-3) return kl;
@@ -404,6 +404,7 @@ int launch_score_topk_umma(const __nv_bfloat16* X, const __nv_bfloat16* bank, co
       HGR_UMMA_CASE(8);
       HGR_UMMA_CASE(10);
       HGR_UMMA_CASE(12);
+      HGR_UMMA_CASE(16);
       HGR_UMMA_CASE(20);
       HGR_UMMA_CASE(32);
       default:

@@ -202,7 +202,7 @@ score_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
         }
         float sub_thr = -INFINITY;
         if (EPI == kEpiTopkDefer) {
-          if (t.seq < WPQ) floor_thr = warmup_floor<KL, 1>(taddr, 0, t.nvalid);  // this warp's first sub-tile
+          if (t.seq < WPQ) floor_thr = warmup_floor_pairs<KL>(taddr, t.nvalid);  // this warp's first sub-tile
           ck.lap(ck.warm);
           sub_thr = fmaxf(floor_thr, list.thr());   // fixed for the whole sub-tile
         }
@@ -233,7 +233,8 @@ score_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
                 sub_thr = fmaxf(sub_thr, list.thr());
                 ck.lap(ck.drain);
               }
-              cand_append_chunk_roomy(cq, r, nv, t.col0 + c0, sub_thr);
+              if (nv >= kChunk) cand_append_chunk_roomy<true>(cq, r, nv, t.col0 + c0, sub_thr);
+              else cand_append_chunk_roomy<false>(cq, r, nv, t.col0 + c0, sub_thr);
               ck.lap(ck.scan);
               continue;
             }
@@ -334,7 +335,7 @@ int pair_wpq(int KL) {
     return e ? (e[0] == '2' ? 2 : 1) : 0;
   }();
   if (forced) return forced;
-  return KL <= 12 ? 1 : 2;
+  return KL <= 16 ? 1 : 2;
 }
 
 template <int WPQ>
@@ -352,6 +353,7 @@ int launch_pair_wpq(int epi, int KL, const CUtensorMap& mx, const CUtensorMap& m
       case 8: return launch_one<kEpiTopkDefer, 8, WPQ>(mx, mb, p, stream);
       case 10: return launch_one<kEpiTopkDefer, 10, WPQ>(mx, mb, p, stream);
       case 12: return launch_one<kEpiTopkDefer, 12, WPQ>(mx, mb, p, stream);
+      case 16: return launch_one<kEpiTopkDefer, 16, WPQ>(mx, mb, p, stream);
       case 20: return launch_one<kEpiTopkDefer, 20, WPQ>(mx, mb, p, stream);
       case 32: return launch_one<kEpiTopkDefer, 32, WPQ>(mx, mb, p, stream);
     }
@@ -360,6 +362,7 @@ int launch_pair_wpq(int epi, int KL, const CUtensorMap& mx, const CUtensorMap& m
     case 8: return launch_one<kEpiTopkQueue, 8, WPQ>(mx, mb, p, stream);
     case 10: return launch_one<kEpiTopkQueue, 10, WPQ>(mx, mb, p, stream);
     case 12: return launch_one<kEpiTopkQueue, 12, WPQ>(mx, mb, p, stream);
+    case 16: return launch_one<kEpiTopkQueue, 16, WPQ>(mx, mb, p, stream);
     case 20: return launch_one<kEpiTopkQueue, 20, WPQ>(mx, mb, p, stream);
     case 32: return launch_one<kEpiTopkQueue, 32, WPQ>(mx, mb, p, stream);
   }

@@ -183,6 +183,36 @@ __device__ __forceinline__ float warmup_floor(uint32_t taddr, int member, int nv
   return nextafterf(tau, -INFINITY);
 }
 
+// Tighter variant: G = KL / 2 interleaved groups, each tracking its TWO largest values (3 FMNMX per value).
+// tau = the smallest runner-up: at least 2 * G = KL columns reach it, so it is as valid a floor as the one above,
+// but it sits much closer to the true KL-th value (for KL = 8 over 256 columns ~14 values survive it instead of
+// ~21, and the worst lane of a warp -- what the lock-step drain pays for -- ~26 instead of ~42).  Full chunks
+// only: a ragged tail chunk is simply left out (any subset of the stream gives a valid bound).
+template <int KL>
+__device__ __forceinline__ float warmup_floor_pairs(uint32_t taddr, int nvalid) {
+  constexpr int G = KL / 2;
+  static_assert(KL % 2 == 0 && G >= 1, "pair floor needs an even list length");
+  if (nvalid < kChunk) return -INFINITY;
+  float hi[G], lo[G];
+#pragma unroll
+  for (int g = 0; g < G; ++g) hi[g] = lo[g] = -INFINITY;
+  for (int c0 = 0; c0 + kChunk <= nvalid; c0 += kChunk) {
+    uint32_t r[kChunk];
+    ptx::tmem_ld_x32(taddr + c0, r);
+    ptx::tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < kChunk; ++j) {
+      const float x = __uint_as_float(r[j]);
+      lo[j % G] = fmaxf(lo[j % G], fminf(hi[j % G], x));
+      hi[j % G] = fmaxf(hi[j % G], x);
+    }
+  }
+  float tau = lo[0];
+#pragma unroll
+  for (int g = 1; g < G; ++g) tau = fminf(tau, lo[g]);
+  return nextafterf(tau, -INFINITY);
+}
+
 // Scan one chunk of 32 accumulator columns of this thread's row.
 // row_addr: shared-space byte address of this thread's private 128-byte staging row; swz = thread id & 7.
 // 1) the 32 values are parked in the staging row with eight unconditional 128-bit stores (XOR-swizzled so
@@ -257,13 +287,16 @@ __device__ __forceinline__ bool cand_append_chunk(CandQueue<NTHR, DEPTH>& q, con
 
 // Same without the per-value saturation (one op less on the cursor's dependency chain): the caller guarantees
 // room for a whole chunk (count <= DEPTH - 32 in every lane).
-template <int NTHR, int DEPTH>
+template <bool FULL, int NTHR, int DEPTH>
 __device__ __forceinline__ void cand_append_chunk_roomy(CandQueue<NTHR, DEPTH>& q, const uint32_t (&r)[kChunk],
                                                         int nv, int col_chunk, float thr) {
   uint32_t wr = q.wr;
+  // store-all / advance-on-pass: every value is written at the cursor and the next store overwrites a
+  // non-survivor.  (Predicating the store and the bump in PTX instead -- no write for a non-survivor -- measured
+  // 70 % SLOWER: the store's address then hangs on a 2-instruction predicated chain per value.)
 #pragma unroll
   for (int j = 0; j < kChunk; ++j) {
-    const bool pass = (__uint_as_float(r[j]) > thr) && (nv >= kChunk || j < nv);
+    const bool pass = (__uint_as_float(r[j]) > thr) && (FULL || j < nv);
     ptx::st_shared_v2(wr, r[j], static_cast<uint32_t>(col_chunk + j));
     wr += pass ? NTHR * 8 : 0;
   }
@@ -275,14 +308,16 @@ __device__ __forceinline__ void cand_drain(SortedList<KL>& list, CandQueue<NTHR,
   const int cnt = q.count();
   const int maxc = __reduce_max_sync(0xffffffffu, cnt);
   uint32_t rd = q.base;
+  // the next entry is fetched while the current one is inserted (one warp per scheduler: nothing else would hide
+  // the shared-memory latency); reading one entry past a lane's count stays inside its DEPTH + 1 slots
+  uint32_t xb, col;
+  ptx::ld_shared_v2(rd, xb, col);
   for (int e = 0; e < maxc; ++e) {
-    if (e < cnt) {
-      uint32_t xb, col;
-      ptx::ld_shared_v2(rd, xb, col);
-      rd += NTHR * 8;
-      const float x = __uint_as_float(xb);
-      if (x > list.thr()) list.insert(x, static_cast<int32_t>(col));
-    }
+    const float x = e < cnt ? __uint_as_float(xb) : -INFINITY;
+    const int32_t c = static_cast<int32_t>(col);
+    rd += NTHR * 8;
+    ptx::ld_shared_v2(rd, xb, col);
+    if (x > list.thr()) list.insert(x, c);
   }
   q.wr = q.base;
 }
