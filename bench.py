@@ -296,7 +296,7 @@ def run_ours(args):
     else:
         from hgrnet_b200.dist import ShardedEvalStream
         G_STEPS = 8
-        ses = ShardedEvalStream(banks[0], lo, batch=B, K=K, steps=G_STEPS, banks=banks)
+        ses = ShardedEvalStream(banks[0], lo, batch=B, K=K, steps=G_STEPS, banks=banks, exchange=args.exchange)
         for s_ in range(G_STEPS):
             ses.dev_feats[s_].copy_(feats_dev[s_ % n_feat])
             ses.dev_labels[s_].copy_(labels_dev[s_ % n_feat])
@@ -320,7 +320,7 @@ def run_ours(args):
     launches = kernels_per_step * steps
     ms_per_step = ms / steps
     value = B / (ms_per_step * 1e-3)
-    hits_resident = hits_src.tolist()
+    hits_resident = (ses.all_reduce_hits() if world > 1 else hits_src).tolist()   # p2p: per-rank row blocks, summed once
 
     # ---- dominant kernel alone (GEMM + fused top-k, no merge), one stream: the roofline figure
     Cs = hi - lo
@@ -330,11 +330,21 @@ def run_ours(args):
     def kern_eager(i):
         ops.score_topk(xs[i % n_feat], banks[i % n_bank], K=K, impl=nomerge)
 
-    kern_only, kb_, ke_ = graphed(kern_eager, cycle, 1)
-    for i in range(warmup):
-        kern_only(i)
-    ke_()
-    kms = timed(kern_only, steps, ke_, kb_) / steps
+    # ONE graph holding `cycle` back-to-back launches (rotating inputs): a launch's duration, not a graph launch's
+    kst = torch.cuda.Stream()
+    kst.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(kst):
+        kern_eager(0)
+        kst.synchronize()
+        kgraph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(kgraph, stream=kst):
+            for i in range(cycle):
+                kern_eager(i)
+    torch.cuda.current_stream().wait_stream(kst)
+    n_rep = max(3, steps // cycle)
+    for i in range(max(1, warmup // cycle)):
+        kgraph.replay()
+    kms = timed(lambda i: kgraph.replay(), n_rep) / (n_rep * cycle)
     flops = 2.0 * B * Cs * D
     achieved = flops / (kms * 1e-3) / 1e12
 
@@ -396,11 +406,16 @@ def run_ours(args):
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak" if world == 1 else "strong",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": wl["name"], "B": B, "C": C, "D": D, "K": K,
-                       "sharding": "none" if world == 1 else "class dimension row-sharded over %d ranks, 1 all-gather/batch" % world,
+                       "sharding": "none" if world == 1 else "class dimension row-sharded over %d ranks" % world,
                        "streams": n_streams if world == 1 else 1,
                        "pipeline": ("EvalStream: 1 CUDA graph per batch on %d round-robin streams" % n_streams) if world == 1
-                                   else ("ShardedEvalStream: 8 batches per %s, all-gather of batch i overlaps GEMM of batch i+1"
-                                         % ("CUDA graph" if multi_graph else "eager issue")),
+                                   else ("ShardedEvalStream: 8 batches per %s; %s" % (
+                                       "CUDA graph" if multi_graph else "eager issue",
+                                       "peer-memory exchange: final lists stored into the row owner's buffer over NVLink, "
+                                       "flag-ordered, owner merges its rows (no collective on the data path)"
+                                       if args.exchange == "p2p" else
+                                       "NCCL all-gather of batch i overlaps the GEMM of batch i+1")),
+                       "exchange": None if world == 1 else args.exchange,
                        "l2": "inputs larger than L2: %d bank copies (%.0f MB) + %d feature batches rotated" %
                              (n_bank, n_bank * Cs * D * 2 / 1e6, n_feat)},
             "e2e": {"value": e2e_value, "unit": "images/s", "ms_per_step": e2e_ms,
@@ -410,7 +425,13 @@ def run_ours(args):
             "sustained": {"value": B / (sus_ms * 1e-3), "unit": "images/s", "steps": n_sus, "ms_per_step": sus_ms},
             "hits": hits_resident,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s",
-                         "frac": achieved / tf_peak, "traffic": None, "kernel": "score_umma_kernel (GEMM + fused top-20)",
+                         "frac": achieved / tf_peak,
+                         # DRAM bytes of one launch from the committed `ncu --set full` capture of this workload
+                         # (profiles/r01_ncu_full_summary.md); compulsory bytes = bank + features + lists
+                         "traffic": NCU_DRAM_BYTES.get((B, Cs, D)),
+                         "traffic_unit": "bytes/launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)",
+                         "compulsory_bytes": Cs * D * 2 + B * D * 2,
+                         "kernel": "score_umma_pair_kernel (TMA + tcgen05 GEMM + fused top-20)",
                          "kernel_ms": kms, "flops_per_launch": flops, "peak_source": peak_src},
             "cpu_baseline": cpu,
             "clocks": clocks,
@@ -425,6 +446,11 @@ def run_ours(args):
     return 0
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel, keyed by (B, C_local, D);
+# from the ncu --set full captures summarised under profiles/ (a profiler cannot run inside the timed region)
+NCU_DRAM_BYTES = {(512, 21841, 1024): 45825792 + 50688}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -433,6 +459,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=None, choices=[None, "cfg2", "cfg4", "cfg5"])
     ap.add_argument("--no-cpu-baseline", dest="no_cpu_baseline", action="store_true")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="N > 1: peer-memory exchange (default) or NCCL all-gather of the per-rank candidate lists")
     ap.add_argument("--streams", type=int, default=3, help="round-robin CUDA streams of the streaming evaluator")
     args = ap.parse_args()
     if args.impl == "reference":

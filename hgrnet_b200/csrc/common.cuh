@@ -62,6 +62,17 @@ int launch_aggregate_normalize(const void* E, int e_dtype, int64_t n_src, int64_
 //    partial lists of each CTA segment).  When KL < K the lists are SPECULATIVE (narrower than K); the merge
 //    certifies every row (a full list whose last entry still beats the merged K-th value may hide candidates)
 //    and re-scans uncertified rows exactly on the CUDA cores, for which it needs X / bank.
+// Row-block scatter of the final lists: rows [g * block_rows, (g + 1) * block_rows) go to val[g] / idx[g] (each a
+// dense [block_rows, K] array).  The pointers may be PEER memory (another GPU's exchange buffer mapped over NVLink):
+// the class-sharded head writes every rank's candidates straight into the buffers of the rank that owns the rows.
+constexpr int kMaxScatterBlocks = 16;
+struct OutScatter {
+  int n_blocks = 0;
+  int64_t block_rows = 0;
+  float* val[kMaxScatterBlocks];
+  int32_t* idx[kMaxScatterBlocks];
+};
+
 struct MergeArgs {
   const float* part_val;
   const int32_t* part_idx;
@@ -82,6 +93,7 @@ struct MergeArgs {
   int64_t C;
   int D8;
   unsigned int* rescan_count;  // optional statistics: number of rows re-scanned
+  OutScatter scatter;          // n_blocks > 0: replaces topk_val / topk_idx
 };
 int launch_topk_merge(const MergeArgs& args, cudaStream_t stream);
 
@@ -89,7 +101,8 @@ size_t simt_score_workspace_bytes(int64_t B, int64_t C, int K);
 int launch_score_topk_simt(const __nv_bfloat16* X, const __nv_bfloat16* bank, const int32_t* col_id,
                            int32_t id_base, const int32_t* targets, int64_t B, int64_t C, int64_t D,
                            float scale, int K, void* ws, size_t ws_bytes, float* topk_val,
-                           int32_t* topk_idx, int64_t* hits, cudaStream_t stream);
+                           int32_t* topk_idx, int64_t* hits, cudaStream_t stream,
+                           const OutScatter* scatter = nullptr);
 int launch_logits_simt(const __nv_bfloat16* X, const __nv_bfloat16* bank, int64_t B, int64_t C,
                        int64_t D, float scale, float* out, int64_t ldo, cudaStream_t stream);
 
@@ -99,7 +112,11 @@ int launch_score_topk_umma(const __nv_bfloat16* X, const __nv_bfloat16* bank, co
                            int32_t id_base, const int32_t* targets, int64_t B, int64_t C, int64_t D,
                            float scale, int K, void* ws, size_t ws_bytes, float* topk_val,
                            int32_t* topk_idx, int64_t* hits, int variant, bool skip_merge,
-                           cudaStream_t stream);
+                           cudaStream_t stream, const OutScatter* scatter = nullptr);
+
+// cross-GPU sequencing of the peer-memory exchange (topk_merge.cu)
+int launch_peer_signal(uint32_t* const* flags, int n, uint32_t* seq, cudaStream_t stream);
+int launch_peer_wait(const uint32_t* flags, int n, uint32_t* seq, cudaStream_t stream);
 int launch_logits_umma(const __nv_bfloat16* X, const __nv_bfloat16* bank, int64_t B, int64_t C,
                        int64_t D, float scale, float* out, int64_t ldo, cudaStream_t stream);
 

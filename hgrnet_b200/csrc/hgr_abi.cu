@@ -80,15 +80,16 @@ size_t hgr_score_topk_workspace_bytes(int64_t B, int64_t C, int64_t D, int K) {
   return (a > b ? a : b) + 16;
 }
 
-int hgr_score_topk(const void* X, const void* bank, const int32_t* col_id, int32_t id_base, const int32_t* targets,
-                   int64_t B, int64_t C, int64_t D, float scale, int K, void* workspace, size_t workspace_bytes,
-                   float* topk_val, int32_t* topk_idx, int64_t* hits, int impl, void* stream) {
+static int score_topk_impl(const void* X, const void* bank, const int32_t* col_id, int32_t id_base, const int32_t* targets,
+                           int64_t B, int64_t C, int64_t D, float scale, int K, void* workspace, size_t workspace_bytes,
+                           float* topk_val, int32_t* topk_idx, int64_t* hits, int impl, void* stream,
+                           const OutScatter* scatter) {
   HGR_CHECK_ARG(B >= 0 && C >= 0, "hgr_score_topk: negative size");
   HGR_CHECK_ARG(D > 0 && D % 8 == 0, "hgr_score_topk: D = %lld must be a positive multiple of 8", (long long)D);
   HGR_CHECK_ARG(K >= 1 && K <= HGR_TOPK_MAX, "hgr_score_topk: K = %d outside [1, %d]", K, HGR_TOPK_MAX);
   HGR_CHECK_ARG(scale > 0.f, "hgr_score_topk: scale must be > 0 (top-k order is taken on unscaled cosines)");
   if (B == 0) return HGR_OK;
-  HGR_CHECK_ARG(topk_val && topk_idx, "hgr_score_topk: null output");
+  HGR_CHECK_ARG(scatter || (topk_val && topk_idx), "hgr_score_topk: null output");
   HGR_CHECK_ARG(C == 0 || (X && bank), "hgr_score_topk: null X/bank");
   HGR_CHECK_ARG(aligned16(X) && aligned16(bank) && aligned16(workspace), "hgr_score_topk: X/bank/workspace must be 16-byte aligned");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -101,6 +102,7 @@ int hgr_score_topk(const void* X, const void* bank, const int32_t* col_id, int32
     m.scale = 1.f;
     m.topk_val = topk_val;
     m.topk_idx = topk_idx;
+    if (scatter) m.scatter = *scatter;
     return launch_topk_merge(m, s);
   }
   const bool skip_merge = (impl & HGR_IMPL_FLAG_NO_MERGE) != 0;
@@ -111,13 +113,87 @@ int hgr_score_topk(const void* X, const void* bank, const int32_t* col_id, int32
     const int variant = which - HGR_IMPL_TCGEN05;  // see launch_score_topk_umma
     return launch_score_topk_umma(static_cast<const __nv_bfloat16*>(X), static_cast<const __nv_bfloat16*>(bank), col_id,
                                   id_base, targets, B, C, D, scale, K, workspace, workspace_bytes, topk_val, topk_idx,
-                                  hits, variant, skip_merge || variant == 3 || variant == 5, s);
+                                  hits, variant, skip_merge || variant == 3 || variant == 5, s, scatter);
   }
   if (which == HGR_IMPL_SIMT)
     return launch_score_topk_simt(static_cast<const __nv_bfloat16*>(X), static_cast<const __nv_bfloat16*>(bank), col_id,
                                   id_base, targets, B, C, D, scale, K, workspace, workspace_bytes, topk_val, topk_idx,
-                                  hits, s);
+                                  hits, s, scatter);
   return set_error(HGR_ERR_BAD_ARG, "hgr_score_topk: unknown impl %d", impl);
+}
+
+int hgr_score_topk(const void* X, const void* bank, const int32_t* col_id, int32_t id_base, const int32_t* targets,
+                   int64_t B, int64_t C, int64_t D, float scale, int K, void* workspace, size_t workspace_bytes,
+                   float* topk_val, int32_t* topk_idx, int64_t* hits, int impl, void* stream) {
+  return score_topk_impl(X, bank, col_id, id_base, targets, B, C, D, scale, K, workspace, workspace_bytes, topk_val,
+                         topk_idx, hits, impl, stream, nullptr);
+}
+
+int hgr_score_topk_scatter(const void* X, const void* bank, const int32_t* col_id, int32_t id_base, int64_t B, int64_t C,
+                           int64_t D, float scale, int K, void* workspace, size_t workspace_bytes, int64_t block_rows,
+                           int n_blocks, float* const* val_blocks, int32_t* const* idx_blocks, int impl, void* stream) {
+  HGR_CHECK_ARG(n_blocks >= 1 && n_blocks <= kMaxScatterBlocks, "hgr_score_topk_scatter: n_blocks = %d outside [1, %d]",
+                n_blocks, kMaxScatterBlocks);
+  HGR_CHECK_ARG(block_rows >= 1 && block_rows * n_blocks >= B, "hgr_score_topk_scatter: %d blocks of %lld rows do not cover B = %lld",
+                n_blocks, (long long)block_rows, (long long)B);
+  HGR_CHECK_ARG(val_blocks && idx_blocks, "hgr_score_topk_scatter: null block tables");
+  HGR_CHECK_ARG((impl & HGR_IMPL_FLAG_NO_MERGE) == 0, "hgr_score_topk_scatter: NO_MERGE makes no sense here");
+  OutScatter sc;
+  sc.n_blocks = n_blocks;
+  sc.block_rows = block_rows;
+  for (int g = 0; g < n_blocks; ++g) {
+    HGR_CHECK_ARG(val_blocks[g] && idx_blocks[g], "hgr_score_topk_scatter: null block %d", g);
+    sc.val[g] = val_blocks[g];
+    sc.idx[g] = idx_blocks[g];
+  }
+  return score_topk_impl(X, bank, col_id, id_base, nullptr, B, C, D, scale, K, workspace, workspace_bytes, nullptr, nullptr,
+                         nullptr, impl, stream, &sc);
+}
+
+int hgr_peer_alloc(size_t bytes, void** ptr, unsigned char* handle) {
+  HGR_CHECK_ARG(ptr && handle && bytes > 0, "hgr_peer_alloc: bad argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == HGR_IPC_HANDLE_BYTES, "IPC handle size");
+  void* p = nullptr;
+  HGR_CHECK_CUDA(cudaMalloc(&p, bytes));
+  HGR_CHECK_CUDA(cudaMemset(p, 0, bytes));
+  HGR_CHECK_CUDA(cudaDeviceSynchronize());
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) {
+    cudaFree(p);
+    return set_error(HGR_ERR_CUDA, "hgr_peer_alloc: cudaIpcGetMemHandle: %s", cudaGetErrorString(e));
+  }
+  memcpy(handle, &h, sizeof(h));
+  *ptr = p;
+  return HGR_OK;
+}
+
+int hgr_peer_open(const unsigned char* handle, void** ptr) {
+  HGR_CHECK_ARG(ptr && handle, "hgr_peer_open: bad argument");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof(h));
+  HGR_CHECK_CUDA(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return HGR_OK;
+}
+
+int hgr_peer_close(void* ptr) {
+  if (ptr) HGR_CHECK_CUDA(cudaIpcCloseMemHandle(ptr));
+  return HGR_OK;
+}
+
+int hgr_peer_free(void* ptr) {
+  if (ptr) HGR_CHECK_CUDA(cudaFree(ptr));
+  return HGR_OK;
+}
+
+int hgr_peer_signal(uint32_t* const* flags, int n, uint32_t* seq, void* stream) {
+  HGR_CHECK_ARG(flags && seq, "hgr_peer_signal: null pointer");
+  return launch_peer_signal(flags, n, seq, static_cast<cudaStream_t>(stream));
+}
+
+int hgr_peer_wait(const uint32_t* flags, int n, uint32_t* seq, void* stream) {
+  HGR_CHECK_ARG(flags && seq, "hgr_peer_wait: null pointer");
+  return launch_peer_wait(flags, n, seq, static_cast<cudaStream_t>(stream));
 }
 
 int hgr_topk_merge(const float* part_val, const int32_t* part_idx, int64_t P, int64_t B, int K, int64_t part_stride,

@@ -96,7 +96,7 @@ size_t simt_score_workspace_bytes(int64_t B, int64_t C, int K) {
 int launch_score_topk_simt(const __nv_bfloat16* X, const __nv_bfloat16* bank, const int32_t* col_id,
                            int32_t id_base, const int32_t* targets, int64_t B, int64_t C, int64_t D, float scale,
                            int K, void* ws, size_t ws_bytes, float* topk_val, int32_t* topk_idx, int64_t* hits,
-                           cudaStream_t stream) {
+                           cudaStream_t stream, const OutScatter* scatter) {
   const int S = pick_splits(B, C);
   const size_t need = simt_score_workspace_bytes(B, C, K);
   if (ws_bytes < need || ws == nullptr)
@@ -136,6 +136,7 @@ int launch_score_topk_simt(const __nv_bfloat16* X, const __nv_bfloat16* bank, co
   m.topk_val = topk_val;
   m.topk_idx = topk_idx;
   m.hits = hits;
+  if (scatter) m.scatter = *scatter;
   return launch_topk_merge(m, stream);
 }
 

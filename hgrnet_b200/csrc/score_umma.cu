@@ -359,7 +359,7 @@ size_t umma_score_workspace_bytes(int64_t B, int64_t C, int K) {
 int launch_score_topk_umma(const __nv_bfloat16* X, const __nv_bfloat16* bank, const int32_t* col_id,
                            int32_t id_base, const int32_t* targets, int64_t B, int64_t C, int64_t D, float scale,
                            int K, void* ws, size_t ws_bytes, float* topk_val, int32_t* topk_idx, int64_t* hits,
-                           int variant, bool skip_merge, cudaStream_t stream) {
+                           int variant, bool skip_merge, cudaStream_t stream, const OutScatter* scatter) {
   // variants: 0 = production: CTA-pair kernel, queue epilogue, speculative lists when provably safe
   //           1 = single-CTA kernel, reload epilogue, 1 warp/quarter, exact lists (cross-check)
   //           2 = production kernel with exact lists (no speculation)
@@ -435,6 +435,7 @@ int launch_score_topk_umma(const __nv_bfloat16* X, const __nv_bfloat16* bank, co
   m.C = C;
   m.D8 = static_cast<int>(D / 8);
   m.rescan_count = p.stats;
+  if (scatter) m.scatter = *scatter;
   return launch_topk_merge(m, stream);
 }
 

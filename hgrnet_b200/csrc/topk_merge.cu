@@ -33,6 +33,56 @@ __device__ __forceinline__ float f32_from_order_key(uint32_t k) {
   return __uint_as_float((k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k);
 }
 
+// Tail shared by both merge kernels.  Lane r holds rank r of the merged list (my_v, my_i = bank row or -1).
+// `doubt`: some lane saw a full speculative list that ends at or above the merged K-th value -> the row is
+// re-scanned exactly on the CUDA cores.  Then: bank row -> node id, scale, store (dense or row-block scatter),
+// Hit@k.
+__device__ __forceinline__ void finish_row(const MergeArgs& a, int64_t row, int lane, float my_v, int32_t my_i,
+                                           bool doubt, int* s_hits) {
+  const int K = a.K;
+  if (a.KL < K && __any_sync(0xffffffffu, doubt)) {
+    if (lane == 0 && a.rescan_count) atomicAdd(a.rescan_count, 1u);
+    SortedList<HGR_TOPK_MAX> full;
+    full.init();
+    scan_row_range<HGR_TOPK_MAX>(reinterpret_cast<const uint4*>(a.X) + row * a.D8,
+                                 reinterpret_cast<const uint4*>(a.bank), 0, a.C, a.D8, lane, full);
+    my_v = -INFINITY;
+    my_i = -1;
+#pragma unroll
+    for (int k = 0; k < HGR_TOPK_MAX; ++k) {
+      if (lane == k) {
+        my_v = full.v[k];
+        my_i = full.i[k];
+      }
+    }
+  }
+  int32_t gid = -1;
+  if (lane < K && my_i >= 0) gid = a.col_id ? a.col_id[my_i] : a.id_base + my_i;
+  if (lane < K) {
+    float* ov = a.topk_val;
+    int32_t* oi = a.topk_idx;
+    int64_t orow = row;
+    if (a.scatter.n_blocks > 0) {  // row-block scatter (possibly into peer memory)
+      const int64_t g = row / a.scatter.block_rows;
+      ov = a.scatter.val[g];
+      oi = a.scatter.idx[g];
+      orow = row - g * a.scatter.block_rows;
+    }
+    ov[orow * K + lane] = my_i >= 0 ? my_v * a.scale : -INFINITY;
+    oi[orow * K + lane] = gid;
+  }
+  if (a.hits && a.targets) {
+    const int32_t target = a.targets[row];
+    const unsigned m = __ballot_sync(0xffffffffu, lane < K && gid >= 0 && gid == target);
+    if (lane == 0 && m != 0 && target >= 0) {
+      const int pos = __ffs(m) - 1;
+#pragma unroll
+      for (int c = 0; c < HGR_NUM_HITS; ++c)
+        if (pos < hit_cut(c)) atomicAdd(&s_hits[c], 1);
+    }
+  }
+}
+
 // kMaxListsPerLane: 4 covers P <= 128 lists per row, 10 covers P <= 320 (one list per epilogue warp of
 // every CTA when a single row tile is spread over all 148 SMs)
 template <int kMaxListsPerLane>
@@ -133,48 +183,16 @@ topk_merge_kernel(const MergeArgs a) {
       }
     }
 
+    bool doubt = false;
     if (KL < K) {
       // certificate for speculative (narrow) lists
-      bool doubt = false;
 #pragma unroll
       for (int q = 0; q < kMaxListsPerLane; ++q) {
         const int p = lane + 32 * q;
         if (p < cnt && li[p * KL + KL - 1] >= 0 && lv[p * KL + KL - 1] >= kth) doubt = true;
       }
-      if (__any_sync(0xffffffffu, doubt)) {
-        if (lane == 0 && a.rescan_count) atomicAdd(a.rescan_count, 1u);
-        SortedList<HGR_TOPK_MAX> full;
-        full.init();
-        scan_row_range<HGR_TOPK_MAX>(reinterpret_cast<const uint4*>(a.X) + row * a.D8,
-                                     reinterpret_cast<const uint4*>(a.bank), 0, a.C, a.D8, lane, full);
-        my_v = -INFINITY;
-        my_i = -1;
-#pragma unroll
-        for (int k = 0; k < HGR_TOPK_MAX; ++k) {
-          if (lane == k) {
-            my_v = full.v[k];
-            my_i = full.i[k];
-          }
-        }
-      }
     }
-
-    int32_t gid = -1;
-    if (lane < K && my_i >= 0) gid = a.col_id ? a.col_id[my_i] : a.id_base + my_i;
-    if (lane < K) {
-      a.topk_val[row * K + lane] = my_i >= 0 ? my_v * a.scale : -INFINITY;
-      a.topk_idx[row * K + lane] = gid;
-    }
-    if (a.hits && a.targets) {
-      const int32_t target = a.targets[row];
-      const unsigned m = __ballot_sync(0xffffffffu, lane < K && gid >= 0 && gid == target);
-      if (lane == 0 && m != 0 && target >= 0) {
-        const int pos = __ffs(m) - 1;
-#pragma unroll
-        for (int c = 0; c < HGR_NUM_HITS; ++c)
-          if (pos < hit_cut(c)) atomicAdd(&s_hits[c], 1);
-      }
-    }
+    finish_row(a, row, lane, my_v, my_i, doubt, s_hits);
   }
   __syncthreads();
   if (a.hits && threadIdx.x < HGR_NUM_HITS && s_hits[threadIdx.x] != 0)
@@ -182,7 +200,197 @@ topk_merge_kernel(const MergeArgs a) {
               static_cast<unsigned long long>(s_hits[threadIdx.x]));
 }
 
+// ---- selection merge (few candidates per row) -----------------------------------------------------------------
+// When a row has at most 32 * NPL candidates in all its lists, the K rounds of the P-way merge above (two warp
+// reductions, a ballot and a dependent shared-memory read per round) are replaced by a SELECTION: every lane keeps
+// NPL candidates in registers as order-preserving integer keys, the K-th largest key is found by bisection (one
+// compare per candidate and one REDUX.ADD per step, ~24 steps for cosines), ties at the cut are resolved by
+// ascending item, and the <= K winners are compacted and ranked by counting.  ~4x fewer instructions per row; the
+// result is the same (value desc, item asc) order.
+template <int NPL>
+__global__ void __launch_bounds__(kMergeWarps * 32)
+topk_select_kernel(const MergeArgs a) {
+  __shared__ int s_hits[HGR_NUM_HITS];
+  __shared__ unsigned long long s_win[kMergeWarps][32];
+  if (threadIdx.x < HGR_NUM_HITS) s_hits[threadIdx.x] = 0;
+  __syncthreads();
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int KL = a.KL, K = a.K;
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * kMergeWarps + warp;
+  const int64_t pstride = a.part_stride > 0 ? a.part_stride : a.B * KL;
+  if (row < a.B) {
+    int cnt = static_cast<int>(a.P);
+    if (a.use_sched) cnt = a.sched.parts(static_cast<int32_t>(row / a.sched.rows)) * a.wpq;
+    const int N = cnt * KL;
+
+    uint32_t key[NPL];   // 0 = empty slot; larger key <=> larger value
+    int32_t item[NPL];
+    bool tail[NPL];      // last entry of a full list (certificate)
+    float val[NPL];
+    // all loads first, unconditionally (an out-of-range slot re-reads entry 0): 2 * NPL independent requests in
+    // flight instead of a chain of dependent L2 round trips
+#pragma unroll
+    for (int s = 0; s < NPL; ++s) {
+      const int e = lane + 32 * s;
+      const int p = e < N ? e / KL : 0, k = e < N ? e - p * KL : 0;
+      const int64_t g = N > 0 ? p * pstride + row * KL + k : 0;
+      item[s] = (N > 0) ? __ldg(a.part_idx + g) : -1;
+      val[s] = (N > 0) ? __ldg(a.part_val + g) : 0.f;
+      tail[s] = (k == KL - 1);
+    }
+#pragma unroll
+    for (int s = 0; s < NPL; ++s) {
+      const bool ok = (lane + 32 * s < N) && item[s] >= 0;
+      key[s] = ok ? f32_order_key(val[s]) : 0u;
+      item[s] = ok ? item[s] : -1;
+      tail[s] = ok && tail[s];
+    }
+    uint32_t kmax = 0, kmin = 0xFFFFFFFFu;
+    int nvalid = 0;
+#pragma unroll
+    for (int s = 0; s < NPL; ++s) {
+      kmax = key[s] > kmax ? key[s] : kmax;
+      kmin = (key[s] != 0 && key[s] < kmin) ? key[s] : kmin;
+      nvalid += key[s] != 0;
+    }
+    kmax = __reduce_max_sync(0xffffffffu, kmax);
+    kmin = __reduce_min_sync(0xffffffffu, kmin);
+    nvalid = __reduce_add_sync(0xffffffffu, nvalid);
+    const int ksel = nvalid < K ? nvalid : K;
+
+    float my_v = -INFINITY;
+    int32_t my_i = -1;
+    bool doubt = false;
+    if (ksel > 0) {
+      // largest T with #{key >= T} >= ksel
+      uint32_t lo = kmin, hi = kmax;
+      while (lo < hi) {
+        const uint32_t mid = lo + ((hi - lo + 1) >> 1);
+        int c = 0;
+#pragma unroll
+        for (int s = 0; s < NPL; ++s) c += key[s] >= mid;
+        c = __reduce_add_sync(0xffffffffu, c);
+        if (c >= ksel) lo = mid;
+        else hi = mid - 1;
+      }
+      const uint32_t T = lo;
+      bool sel[NPL];
+      int above = 0;
+#pragma unroll
+      for (int s = 0; s < NPL; ++s) {
+        sel[s] = key[s] > T;
+        above += sel[s];
+        if (tail[s] && key[s] >= T) doubt = true;
+      }
+      above = __reduce_add_sync(0xffffffffu, above);
+      for (int need = ksel - above; need > 0; --need) {  // ties at the cut: ascending item
+        uint32_t best = 0xFFFFFFFFu;
+#pragma unroll
+        for (int s = 0; s < NPL; ++s)
+          if (key[s] == T && !sel[s] && static_cast<uint32_t>(item[s]) < best) best = static_cast<uint32_t>(item[s]);
+        best = __reduce_min_sync(0xffffffffu, best);
+#pragma unroll
+        for (int s = 0; s < NPL; ++s)
+          if (key[s] == T && !sel[s] && static_cast<uint32_t>(item[s]) == best) sel[s] = true;
+      }
+      // compact the winners (one per lane), rank them by counting on (key desc, item asc)
+      int base = 0;
+#pragma unroll
+      for (int s = 0; s < NPL; ++s) {
+        const unsigned b = __ballot_sync(0xffffffffu, sel[s]);
+        if (sel[s]) {
+          const int pos = base + __popc(b & ((1u << lane) - 1u));
+          if (pos < 32)
+            s_win[warp][pos] = (static_cast<unsigned long long>(key[s]) << 32) | static_cast<uint32_t>(~item[s]);
+        }
+        base += __popc(b);
+      }
+      __syncwarp();
+      unsigned long long mine = 0;
+      int rank = 0;
+      if (lane < ksel) {
+        mine = s_win[warp][lane];
+        for (int j = 0; j < ksel; ++j) rank += s_win[warp][j] > mine;
+      }
+      __syncwarp();
+      if (lane < ksel) s_win[warp][rank] = mine;
+      __syncwarp();
+      if (lane < ksel) {
+        const unsigned long long w = s_win[warp][lane];
+        my_v = f32_from_order_key(static_cast<uint32_t>(w >> 32));
+        my_i = static_cast<int32_t>(~static_cast<uint32_t>(w));
+      }
+    }
+    finish_row(a, row, lane, my_v, my_i, doubt, s_hits);
+  }
+  __syncthreads();
+  if (a.hits && threadIdx.x < HGR_NUM_HITS && s_hits[threadIdx.x] != 0)
+    atomicAdd(reinterpret_cast<unsigned long long*>(a.hits) + threadIdx.x,
+              static_cast<unsigned long long>(s_hits[threadIdx.x]));
+}
+
+// ---- cross-GPU sequencing of the peer-memory exchange ---------------------------------------------------------
+// Every rank keeps `n` flag words (one per producer rank) in its exchange buffer.  After the kernel that wrote its
+// candidates into the peers' buffers, a rank launches peer_signal: thread g stores the rank's running sequence
+// number into ITS flag word on rank g (system-scope release; the scatter kernel finished before, stream order).
+// Before merging, a rank launches peer_wait: thread g spins (system-scope acquire) until producer g's flag has
+// reached the consumer's own running sequence number.  Both counters live in device memory and advance by one per
+// launch, so the pair can be captured in a CUDA graph and replayed.
+struct PeerFlags {
+  uint32_t* p[kMaxScatterBlocks];
+};
+
+__global__ void peer_signal_kernel(const PeerFlags flags, int n, uint32_t* seq) {
+  __shared__ uint32_t s_v;
+  if (threadIdx.x == 0) s_v = ++(*seq);
+  __syncthreads();
+  if (static_cast<int>(threadIdx.x) < n) {
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flags.p[threadIdx.x]), "r"(s_v) : "memory");
+  }
+}
+
+__global__ void peer_wait_kernel(const uint32_t* flags, int n, uint32_t* seq) {
+  __shared__ uint32_t s_v;
+  if (threadIdx.x == 0) s_v = ++(*seq);
+  __syncthreads();
+  if (static_cast<int>(threadIdx.x) < n) {
+    const uint32_t want = s_v;
+    unsigned long long t0 = 0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+      uint32_t got;
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(got) : "l"(flags + threadIdx.x) : "memory");
+      if (static_cast<int32_t>(got - want) >= 0) break;
+      unsigned long long t1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      if (t1 - t0 > 4000000000ull) {  // 4 s: a peer died or the schedules diverged -- fail loudly, never hang the GPU
+        printf("hgr peer_wait: producer %d stuck at %u, waiting for %u\n", static_cast<int>(threadIdx.x), got, want);
+        __trap();
+      }
+      __nanosleep(200);
+    }
+  }
+}
+
 }  // namespace
+
+int launch_peer_signal(uint32_t* const* flags, int n, uint32_t* seq, cudaStream_t stream) {
+  if (n < 1 || n > kMaxScatterBlocks) return set_error(HGR_ERR_BAD_ARG, "peer signal: %d ranks outside [1, %d]", n, kMaxScatterBlocks);
+  PeerFlags f{};
+  for (int g = 0; g < n; ++g) f.p[g] = flags[g];
+  peer_signal_kernel<<<1, 32, 0, stream>>>(f, n, seq);
+  HGR_CHECK_LAUNCH();
+  return HGR_OK;
+}
+
+int launch_peer_wait(const uint32_t* flags, int n, uint32_t* seq, cudaStream_t stream) {
+  if (n < 1 || n > kMaxScatterBlocks) return set_error(HGR_ERR_BAD_ARG, "peer wait: %d ranks outside [1, %d]", n, kMaxScatterBlocks);
+  peer_wait_kernel<<<1, 32, 0, stream>>>(flags, n, seq);
+  HGR_CHECK_LAUNCH();
+  return HGR_OK;
+}
 
 int launch_topk_merge(const MergeArgs& args, cudaStream_t stream) {
   if (args.B == 0 || args.K == 0) return HGR_OK;
@@ -192,9 +400,18 @@ int launch_topk_merge(const MergeArgs& args, cudaStream_t stream) {
     return set_error(HGR_ERR_UNSUPPORTED, "topk merge: K = %d / KL = %d unsupported", args.K, args.KL);
   if (args.KL < args.K && (args.X == nullptr || args.bank == nullptr))
     return set_error(HGR_ERR_BAD_ARG, "topk merge: speculative lists need X / bank for the exact re-scan");
+  const int blocks = static_cast<int>((args.B + kMergeWarps - 1) / kMergeWarps);
+  const int64_t cand = args.P * args.KL;  // candidates per row (upper bound)
+  static const bool force_pway = getenv("HGR_MERGE_PWAY") != nullptr;
+  if (cand <= 320 && !force_pway) {
+    if (cand <= 128) topk_select_kernel<4><<<blocks, kMergeWarps * 32, 0, stream>>>(args);
+    else if (cand <= 192) topk_select_kernel<6><<<blocks, kMergeWarps * 32, 0, stream>>>(args);
+    else topk_select_kernel<10><<<blocks, kMergeWarps * 32, 0, stream>>>(args);
+    HGR_CHECK_LAUNCH();
+    return HGR_OK;
+  }
   const size_t smem = static_cast<size_t>(kMergeWarps) * args.P * args.KL * 8;
   if (smem > 200 * 1024) return set_error(HGR_ERR_UNSUPPORTED, "topk merge: %zu bytes of lists per CTA", smem);
-  const int blocks = static_cast<int>((args.B + kMergeWarps - 1) / kMergeWarps);
   if (args.P <= 128) {
     if (smem > 48 * 1024)
       HGR_CHECK_CUDA(cudaFuncSetAttribute(topk_merge_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -99,18 +99,136 @@ class ShardedScorer:
         return out
 
 
+class _RawCuda:
+    """Zero-copy torch view of a raw device allocation (``torch.as_tensor`` reads ``__cuda_array_interface__``)."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+def exchange_layout(B: int, K: int, world: int, slots: int):
+    """Byte layout of one rank's exchange buffer: a 256-byte header (one flag word per producer rank), then per
+    slot the value lists ``[world, block_rows, K]`` fp32 followed by the id lists ``[world, block_rows, K]`` int32."""
+    block_rows = (B + world - 1) // world
+    part = block_rows * K * 4
+    slot_bytes = 2 * world * part
+    return {"block_rows": block_rows, "part_bytes": part, "slot_bytes": slot_bytes, "header": 256,
+            "total": 256 + slots * slot_bytes}
+
+
+class PeerExchange:
+    """Peer-memory exchange of the class-sharded head (no collective call on the data path).
+
+    Rank ``g`` owns image rows ``[g * block_rows, (g + 1) * block_rows)``.  Every rank allocates one exchange buffer
+    (``hgr_peer_alloc``), the CUDA IPC handles are swapped once through ``torch.distributed`` and every peer buffer
+    is mapped into this process (``hgr_peer_open``).  Per batch a rank's scoring kernel then writes its local top-K
+    of row block ``g`` directly into list ``rank`` of rank ``g``'s buffer over NVLink (``hgr_score_topk_scatter``)
+    and raises its flag there (``hgr_peer_signal``); the owner waits for all ``world`` flags (``hgr_peer_wait``) and
+    merges its ``world`` lists per row (``hgr_topk_merge``).  ``slots`` batches can be in flight.
+    """
+
+    def __init__(self, B: int, K: int, device, group=None, slots: int = 4, _bases=None, _rank=None, _world=None):
+        self.device = torch.device(device)
+        self.group = group
+        if _bases is None:
+            self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+            self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        else:                                  # several logical ranks inside one process (single-GPU tests)
+            self.world, self.rank = _world, _rank
+        if self.world > 16:
+            raise ValueError("PeerExchange supports up to 16 ranks (HGR_MAX_PEERS)")
+        self.B, self.K, self.slots = B, K, slots
+        self.lay = exchange_layout(B, K, self.world, slots)
+        self.block_rows = self.lay["block_rows"]
+        self.lo = min(B, self.rank * self.block_rows)
+        self.hi = min(B, self.lo + self.block_rows)
+        self._opened = []
+        if _bases is not None:
+            self.bases = list(_bases)
+            self._own = None
+        else:
+            with torch.cuda.device(self.device):
+                own, handle = ops.peer_alloc(self.lay["total"])
+                self._own = own
+                if self.world > 1:
+                    handles = [None] * self.world
+                    dist.all_gather_object(handles, handle, group=group)
+                    self.bases = []
+                    for g in range(self.world):
+                        if g == self.rank:
+                            self.bases.append(own)
+                        else:
+                            self.bases.append(ops.peer_open(handles[g]))
+                            self._opened.append(self.bases[-1])
+                else:
+                    self.bases = [own]
+        self.local = torch.as_tensor(_RawCuda(self.bases[self.rank], self.lay["total"]), device=self.device)
+        self.seq = torch.zeros(2, dtype=torch.int32, device=self.device)   # [signals sent, waits done]
+        self.flag_ptrs = [b + 4 * self.rank for b in self.bases]
+
+    # -- addresses -------------------------------------------------------------------------------------------
+    def _slot_base(self, base: int, slot: int) -> int:
+        return base + self.lay["header"] + slot * self.lay["slot_bytes"]
+
+    def block_ptrs(self, slot: int):
+        """Where THIS rank's lists of row block g go: list ``rank`` of rank g's slot."""
+        part, world = self.lay["part_bytes"], self.world
+        val = [self._slot_base(b, slot) + self.rank * part for b in self.bases]
+        idx = [self._slot_base(b, slot) + world * part + self.rank * part for b in self.bases]
+        return val, idx
+
+    def local_parts(self, slot: int):
+        """(value pointer, id pointer, element stride) of the ``world`` lists received for my rows."""
+        base = self._slot_base(self.bases[self.rank], slot)
+        return base, base + self.world * self.lay["part_bytes"], self.block_rows * self.K
+
+    # -- per batch -------------------------------------------------------------------------------------------
+    def scatter(self, x_norm: torch.Tensor, bank: torch.Tensor, id_base: int, slot: int, col_id=None) -> None:
+        val, idx = self.block_ptrs(slot)
+        ops.score_topk_scatter(x_norm, bank, val, idx, self.block_rows, col_id=col_id, id_base=id_base, K=self.K)
+        ops.peer_signal(self.flag_ptrs, self.seq[0:1])
+
+    def merge(self, slot: int, targets: Optional[torch.Tensor], hits: Optional[torch.Tensor], out=None):
+        """Final top-K (+ hits) of MY rows ``[lo, hi)``; ``targets`` holds the labels of the whole batch."""
+        ops.peer_wait(self.bases[self.rank], self.world, self.seq[1:2])
+        n = self.hi - self.lo
+        if n <= 0:
+            return None
+        pv, pi, stride = self.local_parts(slot)
+        t = targets[self.lo:self.hi] if targets is not None else None
+        return ops.topk_merge_raw(pv, pi, self.world, n, self.K, stride, self.device, targets=t, hits=hits, out=out)
+
+    def close(self) -> None:
+        for p in self._opened:
+            ops.peer_close(p)
+        self._opened = []
+        if self._own is not None:
+            ops.peer_free(self._own)
+            self._own = None
+
+
 class ShardedEvalStream:
     """Software-pipelined, CUDA-graph captured class-sharded eval steps (one process per GPU).
 
-    One graph holds ``steps`` consecutive batches.  Inside it the compute stream runs
-    ``normalise -> fused score/top-K on the local shard -> pack`` of batch i+1 BEFORE it waits for the all-gather
-    of batch i (issued on NCCL's stream), so the exchange and the merge of a batch overlap the GEMM of the next;
-    collectives stay in batch order on NCCL's single stream, on every rank.  A replay is one ``cudaGraphLaunch``
-    for ``steps`` batches: no interpreter and no per-batch launch latency on the path.
+    One graph holds ``steps`` consecutive batches.  Two exchanges:
+
+    * ``exchange="p2p"`` (default): ``PeerExchange`` -- the scoring kernel's final lists go straight into the row
+      owner's buffer over NVLink, a flag word per producer orders them; the owner merges ITS rows only (1/world of
+      the merge work, 1/world of the bytes of an all-gather, no collective kernel competing for SMs).  The merge of
+      batch i is issued after the scoring of batch i+1, so the flags have long arrived when it runs.  Results
+      (``val`` / ``idx``) cover rows ``[row_lo, row_hi)``; ``hits`` counts those rows -- sum it over ranks at the end
+      (``all_reduce_hits``: the one collective of an evaluation).
+    * ``exchange="nccl"``: ``normalise -> score -> all_gather_into_tensor`` (NCCL stream) ``-> merge`` of all rows
+      on every rank, the gather of batch i overlapping the GEMM of batch i+1.
+
+    A replay is one ``cudaGraphLaunch`` for ``steps`` batches: no interpreter, no per-batch launch latency.
     """
 
     def __init__(self, bank_shard: torch.Tensor, id_base: int, *, batch: int, K: int = 20, steps: int = 8,
-                 feat_dtype=torch.float32, banks=None, group=None, use_graph: bool = True):
+                 feat_dtype=torch.float32, banks=None, group=None, use_graph: bool = True, exchange: str = "p2p"):
+        if exchange not in ("p2p", "nccl"):
+            raise ValueError("exchange must be 'p2p' or 'nccl'")
+        self.exchange = exchange
         self.device = bank_shard.device
         self.banks = list(banks) if banks is not None else [bank_shard]
         self.id_base, self.K, self.B, self.steps, self.group = id_base, K, batch, steps, group
@@ -118,11 +236,25 @@ class ShardedEvalStream:
         D = bank_shard.shape[1]
         self.dev_feats = [torch.empty((batch, D), dtype=feat_dtype, device=self.device) for _ in range(steps)]
         self.dev_labels = [torch.zeros((batch,), dtype=torch.int32, device=self.device) for _ in range(steps)]
-        self.send = [torch.empty((2, batch, K), dtype=torch.int32, device=self.device) for _ in range(steps)]
-        self.recv = [torch.empty((self.world, 2, batch, K), dtype=torch.int32, device=self.device) for _ in range(steps)]
         self.hits = ops.new_hits(self.device)
         self.val = [None] * steps
         self.idx = [None] * steps
+        self.row_lo, self.row_hi = 0, batch
+        if exchange == "p2p":
+            self.slots = 4
+            if steps % self.slots:
+                raise ValueError("steps must be a multiple of %d" % self.slots)
+            self.px = PeerExchange(batch, K, self.device, group=group, slots=self.slots)
+            self.row_lo, self.row_hi = self.px.lo, self.px.hi
+            n_my = max(0, self.row_hi - self.row_lo)
+            self.val = [torch.empty((n_my, K), dtype=torch.float32, device=self.device) for _ in range(steps)]
+            self.idx = [torch.empty((n_my, K), dtype=torch.int32, device=self.device) for _ in range(steps)]
+            if self.world > 1:
+                dist.barrier(group=group)          # every buffer is mapped everywhere before the first store
+        else:
+            self.send = [torch.empty((2, batch, K), dtype=torch.int32, device=self.device) for _ in range(steps)]
+            self.recv = [torch.empty((self.world, 2, batch, K), dtype=torch.int32, device=self.device)
+                         for _ in range(steps)]
         self.graph = None
         self.stream = torch.cuda.Stream(device=self.device)
         self.stream.wait_stream(torch.cuda.current_stream(self.device))
@@ -145,6 +277,9 @@ class ShardedEvalStream:
     def _local(self, s: int):
         x = ops.normalize_rows(self.dev_feats[s])
         bank = self.banks[s % len(self.banks)]
+        if self.exchange == "p2p":
+            self.px.scatter(x, bank, self.id_base, s % self.slots)
+            return None
         if bank.shape[0] > 0:
             # results go straight into the send record (no pack copies)
             ops.score_topk(x, bank, id_base=self.id_base, K=self.K, out=(self.send[s][0].view(torch.float32), self.send[s][1]))
@@ -158,6 +293,9 @@ class ShardedEvalStream:
         return None
 
     def _merge(self, s: int, work):
+        if self.exchange == "p2p":
+            self.px.merge(s % self.slots, self.dev_labels[s], self.hits, out=(self.val[s], self.idx[s]))
+            return
         if work is not None:
             work.wait()
         pv, pi = unpack_gathered(self.recv[s])
@@ -178,3 +316,12 @@ class ShardedEvalStream:
             self.graph.replay()
         else:
             self._issue()
+
+    def all_reduce_hits(self) -> torch.Tensor:
+        """Hit@k counters of the whole batch stream.  With the peer exchange every rank counted its own rows, so
+        the counters are summed over ranks (the single collective of an evaluation); the NCCL exchange already
+        counts all rows on every rank."""
+        h = self.hits.clone()
+        if self.exchange == "p2p" and self.world > 1:
+            dist.all_reduce(h, group=self.group)
+        return h

@@ -162,6 +162,86 @@ def topk_merge(part_val: torch.Tensor, part_idx: torch.Tensor, *, targets: Optio
     return val, idx
 
 
+def topk_merge_raw(part_val_ptr: int, part_idx_ptr: int, P: int, B: int, K: int, part_stride: int, device, *,
+                   targets: Optional[torch.Tensor] = None, hits: Optional[torch.Tensor] = None,
+                   out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """``topk_merge`` on raw device pointers (lists that live in a peer-exchange buffer, see ``dist.PeerExchange``)."""
+    lib = _cabi.load()
+    if targets is not None:
+        targets = _require(targets, "targets", torch.int32)
+    if hits is not None:
+        hits = _require(hits, "hits", torch.int64)
+    if out is None:
+        out = (torch.empty((B, K), dtype=torch.float32, device=device), torch.empty((B, K), dtype=torch.int32, device=device))
+    _cabi.check(lib.hgr_topk_merge(part_val_ptr, part_idx_ptr, P, B, K, part_stride, _ptr(targets), _ptr(out[0]),
+                                   _ptr(out[1]), _ptr(hits), _stream()))
+    return out
+
+
+def score_topk_scatter(X: torch.Tensor, bank: torch.Tensor, val_block_ptrs, idx_block_ptrs, block_rows: int, *,
+                       col_id: Optional[torch.Tensor] = None, id_base: int = 0, K: int = 20, scale: float = 1.0,
+                       impl: int = HGR_IMPL_AUTO) -> None:
+    """``score_topk`` whose final lists of rows ``[g*block_rows, (g+1)*block_rows)`` are written to the dense
+    ``[block_rows, K]`` arrays at ``val_block_ptrs[g]`` / ``idx_block_ptrs[g]`` (device pointers, local or peer)."""
+    import ctypes
+    lib = _cabi.load()
+    X = _require(X, "X", torch.bfloat16)
+    bank = _require(bank, "bank", torch.bfloat16)
+    B, D = X.shape
+    C = bank.shape[0]
+    if col_id is not None:
+        col_id = _require(col_id, "col_id", torch.int32)
+    n = len(val_block_ptrs)
+    if len(idx_block_ptrs) != n:
+        raise ValueError("val/idx block tables disagree")
+    vt = (ctypes.c_void_p * n)(*val_block_ptrs)
+    it = (ctypes.c_void_p * n)(*idx_block_ptrs)
+    nbytes = lib.hgr_score_topk_workspace_bytes(B, C, D, K)
+    ws = _workspace(nbytes, X.device)
+    _cabi.check(lib.hgr_score_topk_scatter(_ptr(X), _ptr(bank), _ptr(col_id), id_base, B, C, D, float(scale), K,
+                                           _ptr(ws), ws.numel(), block_rows, n, vt, it, impl, _stream()))
+
+
+def peer_alloc(nbytes: int) -> Tuple[int, bytes]:
+    """cudaMalloc'd, zeroed exchange buffer on the current device + its CUDA IPC handle."""
+    import ctypes
+    lib = _cabi.load()
+    ptr = ctypes.c_void_p()
+    handle = (ctypes.c_ubyte * 64)()
+    _cabi.check(lib.hgr_peer_alloc(nbytes, ctypes.byref(ptr), handle))
+    return int(ptr.value), bytes(handle)
+
+
+def peer_open(handle: bytes) -> int:
+    import ctypes
+    lib = _cabi.load()
+    ptr = ctypes.c_void_p()
+    buf = (ctypes.c_ubyte * 64)(*handle)
+    _cabi.check(lib.hgr_peer_open(buf, ctypes.byref(ptr)))
+    return int(ptr.value)
+
+
+def peer_close(ptr: int) -> None:
+    _cabi.check(_cabi.load().hgr_peer_close(ptr))
+
+
+def peer_free(ptr: int) -> None:
+    _cabi.check(_cabi.load().hgr_peer_free(ptr))
+
+
+def peer_signal(flag_ptrs, seq: torch.Tensor) -> None:
+    """Publish this rank's next sequence number (``seq`` is a 1-element int32 device counter) to ``flag_ptrs``."""
+    import ctypes
+    n = len(flag_ptrs)
+    ft = (ctypes.c_void_p * n)(*flag_ptrs)
+    _cabi.check(_cabi.load().hgr_peer_signal(ft, n, _ptr(seq), _stream()))
+
+
+def peer_wait(flags_ptr: int, n: int, seq: torch.Tensor) -> None:
+    """Advance the consumer counter ``seq`` and wait until the ``n`` local flag words have reached it."""
+    _cabi.check(_cabi.load().hgr_peer_wait(flags_ptr, n, _ptr(seq), _stream()))
+
+
 def logits_dense(X: torch.Tensor, bank: torch.Tensor, scale: float = 1.0, impl: int = HGR_IMPL_AUTO,
                  out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """``scale * X @ bank.T`` in fp32 (model/clip_tree.py:331 / :263) on the tcgen05 main loop."""

@@ -126,6 +126,38 @@ int hgr_topk_merge(const float* part_val, const int32_t* part_idx, int64_t P, in
                    int64_t* hits, void* stream);
 
 /*
+ * ---- class-sharded head over PEER MEMORY (one process per GPU, NVLink / NVSwitch) ----------------------------
+ * The reference is single-GPU (main.py:226); SURVEY.md section 8e shards the class bank row-wise over G ranks.
+ * Every rank scores the whole image batch against its shard; image rows are owned block-wise
+ * (rank g owns rows [g * block_rows, (g + 1) * block_rows)), and a rank's local top-K of a row is written by the
+ * producing kernel straight into the OWNER's exchange buffer over NVLink -- no collective call and no staging
+ * copy on the data path.  The owner merges its G lists per row (hgr_topk_merge) and counts Hit@k for its rows.
+ *
+ * hgr_peer_alloc / hgr_peer_open   cudaMalloc'd (zeroed) exchange buffer + its 64-byte CUDA IPC handle; a peer
+ *                                  process maps it with hgr_peer_open (peer access is enabled on first use).
+ * hgr_score_topk_scatter           hgr_score_topk whose final [B, K] lists go, block of rows by block of rows, to
+ *                                  val_blocks[g] / idx_blocks[g] (HOST arrays of n_blocks device pointers, local
+ *                                  or peer); no hit counting (a hit needs the merged, global rank).
+ * hgr_peer_signal                  after the scatter: publish this rank's next sequence number (device counter
+ *                                  *seq, incremented by the kernel) to flags[g] (one word on every rank g).
+ * hgr_peer_wait                    before the merge: increment the consumer's own device counter *seq and spin
+ *                                  until all n local flag words have reached it.  Traps (never hangs) after 4 s.
+ * Both counters advance once per launch, so a signal/wait pair can live in a replayed CUDA graph.
+ */
+#define HGR_IPC_HANDLE_BYTES 64
+#define HGR_MAX_PEERS 16
+int hgr_peer_alloc(size_t bytes, void** ptr, unsigned char* handle /* [HGR_IPC_HANDLE_BYTES] */);
+int hgr_peer_open(const unsigned char* handle, void** ptr);
+int hgr_peer_close(void* ptr);
+int hgr_peer_free(void* ptr);
+int hgr_score_topk_scatter(const void* X, const void* bank, const int32_t* col_id, int32_t id_base, int64_t B,
+                           int64_t C, int64_t D, float scale, int K, void* workspace, size_t workspace_bytes,
+                           int64_t block_rows, int n_blocks, float* const* val_blocks,
+                           int32_t* const* idx_blocks, int impl, void* stream);
+int hgr_peer_signal(uint32_t* const* flags, int n, uint32_t* seq, void* stream);
+int hgr_peer_wait(const uint32_t* flags, int n, uint32_t* seq, void* stream);
+
+/*
  * Dense logits, out[b, c] = scale * <X[b], bank[c]>, fp32, leading dimension ldo >= C.
  * Same TMA/tcgen05 main loop as hgr_score_topk with a plain store epilogue.  Keeps
  * tree_model.forward()'s contract (model/clip_tree.py:328-333: returns [B, N] logits) for

@@ -1,0 +1,80 @@
+"""Peer-memory exchange of the class-sharded head (hgr_score_topk_scatter / hgr_peer_signal / hgr_peer_wait):
+G logical ranks inside ONE process on ONE GPU -- the kernels cannot tell a local pointer from a peer mapping, so
+the whole data path (row-block scatter, flags, owner-side merge, Hit@k per row block) is covered without NVLink.
+The real multi-process / multi-GPU run is tests/test_gpu_dist.py."""
+from __future__ import annotations
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _emb(n, d, seed):
+    x = torch.randn(n, d, generator=torch.Generator().manual_seed(seed))
+    return (x / x.norm(dim=-1, keepdim=True)).to(torch.bfloat16)
+
+
+@pytest.mark.parametrize("B,C,D,G", [(512, 21841, 1024, 8), (130, 1000, 256, 3), (64, 40, 64, 4), (5, 300, 128, 8)])
+def test_scatter_exchange_matches_single_gpu(B, C, D, G):
+    from hgrnet_b200 import ops
+    from hgrnet_b200.dist import PeerExchange, exchange_layout, shard_bounds
+    dev = torch.device("cuda", 0)
+    K = 20
+    x = _emb(B, D, 1).to(dev)
+    w = _emb(C, D, 2).to(dev)
+    targets = torch.randint(0, C, (B,), generator=torch.Generator().manual_seed(3)).int().to(dev)
+    h_ref = ops.new_hits(dev)
+    rv, ri = ops.score_topk(x, w, targets=targets, K=K, hits=h_ref)
+
+    lay = exchange_layout(B, K, G, 4)
+    bufs = [ops.peer_alloc(lay["total"])[0] for _ in range(G)]
+    try:
+        ranks = [PeerExchange(B, K, dev, slots=4, _bases=bufs, _rank=r, _world=G) for r in range(G)]
+        bounds = shard_bounds(C, G)
+        hits = ops.new_hits(dev)
+        for rep in range(6):                      # more batches than slots: the sequence counters keep advancing
+            slot = rep % 4
+            for r, px in enumerate(ranks):        # every rank scores its class shard and scatters to the owners
+                lo, hi = bounds[r]
+                px.scatter(x, w[lo:hi].contiguous(), lo, slot)
+            outs = [px.merge(slot, targets, hits) for px in ranks]
+        torch.cuda.synchronize()
+        val = torch.cat([o[0] for o in outs if o is not None])
+        idx = torch.cat([o[1] for o in outs if o is not None])
+        assert torch.equal(idx, ri), "row-block scatter + owner merge differs from the single-GPU result"
+        assert torch.equal(val, rv)
+        assert hits.tolist() == [6 * h for h in h_ref.tolist()]
+        assert [int(px.seq[0]) for px in ranks] == [6] * G and [int(px.seq[1]) for px in ranks] == [6] * G
+    finally:
+        torch.cuda.synchronize()
+        for b in bufs:
+            ops.peer_free(b)
+
+
+def test_peer_wait_passes_only_after_all_signals():
+    """The wait kernel of a consumer must not complete before every producer has signalled."""
+    from hgrnet_b200 import ops
+    from hgrnet_b200.dist import PeerExchange, exchange_layout
+    dev = torch.device("cuda", 0)
+    G, B, K = 3, 12, 20
+    lay = exchange_layout(B, K, G, 4)
+    bufs = [ops.peer_alloc(lay["total"])[0] for _ in range(G)]
+    try:
+        ranks = [PeerExchange(B, K, dev, _bases=bufs, _rank=r, _world=G) for r in range(G)]
+        side = torch.cuda.Stream()
+        done = torch.cuda.Event()
+        with torch.cuda.stream(side):
+            ops.peer_wait(bufs[0], G, ranks[0].seq[1:2])      # consumer 0 waits on a side stream
+            done.record()
+        ops.peer_signal(ranks[0].flag_ptrs, ranks[0].seq[0:1])
+        ops.peer_signal(ranks[1].flag_ptrs, ranks[1].seq[0:1])
+        torch.cuda.current_stream().synchronize()
+        assert not done.query(), "wait returned although producer 2 has not signalled"
+        ops.peer_signal(ranks[2].flag_ptrs, ranks[2].seq[0:1])
+        side.synchronize()
+        assert done.query()
+    finally:
+        torch.cuda.synchronize()
+        for b in bufs:
+            ops.peer_free(b)
