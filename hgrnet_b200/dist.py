@@ -225,7 +225,8 @@ class ShardedEvalStream:
     """
 
     def __init__(self, bank_shard: torch.Tensor, id_base: int, *, batch: int, K: int = 20, steps: int = 8,
-                 feat_dtype=torch.float32, banks=None, group=None, use_graph: bool = True, exchange: str = "p2p"):
+                 feat_dtype=torch.float32, banks=None, group=None, use_graph: bool = True, exchange: str = "p2p",
+                 channels: int = 2):
         if exchange not in ("p2p", "nccl"):
             raise ValueError("exchange must be 'p2p' or 'nccl'")
         self.exchange = exchange
@@ -242,9 +243,13 @@ class ShardedEvalStream:
         self.row_lo, self.row_hi = 0, batch
         if exchange == "p2p":
             self.slots = 4
-            if steps % self.slots:
-                raise ValueError("steps must be a multiple of %d" % self.slots)
-            self.px = PeerExchange(batch, K, self.device, group=group, slots=self.slots)
+            # `channels` independent exchanges (own flags, counters, slots), one CUDA stream each: batch s runs on
+            # channel s % channels, so the normalise / merge kernels of one batch fill the SMs the persistent GEMM
+            # of the neighbouring batch leaves idle at its edges
+            self.channels = max(1, min(channels, steps))
+            self.pxs = [PeerExchange(batch, K, self.device, group=group, slots=self.slots) for _ in range(self.channels)]
+            self.px = self.pxs[0]
+            self.side = [torch.cuda.Stream(device=self.device) for _ in range(self.channels)]
             self.row_lo, self.row_hi = self.px.lo, self.px.hi
             n_my = max(0, self.row_hi - self.row_lo)
             self.val = [torch.empty((n_my, K), dtype=torch.float32, device=self.device) for _ in range(steps)]
@@ -278,7 +283,7 @@ class ShardedEvalStream:
         x = ops.normalize_rows(self.dev_feats[s])
         bank = self.banks[s % len(self.banks)]
         if self.exchange == "p2p":
-            self.px.scatter(x, bank, self.id_base, s % self.slots)
+            self.pxs[s % self.channels].scatter(x, bank, self.id_base, (s // self.channels) % self.slots)
             return None
         if bank.shape[0] > 0:
             # results go straight into the send record (no pack copies)
@@ -294,7 +299,8 @@ class ShardedEvalStream:
 
     def _merge(self, s: int, work):
         if self.exchange == "p2p":
-            self.px.merge(s % self.slots, self.dev_labels[s], self.hits, out=(self.val[s], self.idx[s]))
+            self.pxs[s % self.channels].merge((s // self.channels) % self.slots, self.dev_labels[s], self.hits,
+                                              out=(self.val[s], self.idx[s]))
             return
         if work is not None:
             work.wait()
@@ -302,6 +308,8 @@ class ShardedEvalStream:
         self.val[s], self.idx[s] = ops.topk_merge(pv, pi, targets=self.dev_labels[s], hits=self.hits)
 
     def _issue(self):
+        if self.exchange == "p2p":
+            return self._issue_p2p()
         prev = None
         for s in range(self.steps):
             work = self._local(s)
@@ -309,6 +317,23 @@ class ShardedEvalStream:
                 self._merge(*prev)
             prev = (s, work)
         self._merge(*prev)
+
+    def _issue_p2p(self):
+        """Fork the current stream into the channel streams, batch s on channel s % channels, join again (inside a
+        capture this becomes a graph with `channels` parallel branches)."""
+        main = torch.cuda.current_stream(self.device)
+        fork = torch.cuda.Event()
+        fork.record(main)
+        for st in self.side:
+            st.wait_event(fork)
+        for s in range(self.steps):
+            with torch.cuda.stream(self.side[s % self.channels]):
+                self._local(s)
+                self._merge(s, None)
+        for st in self.side:
+            join = torch.cuda.Event()
+            join.record(st)
+            main.wait_event(join)
 
     def run(self):
         """Score the ``steps`` batches currently in ``dev_feats`` / ``dev_labels`` (enqueue only)."""

@@ -16,8 +16,8 @@ for C in (10921, 5461, 2731):
     banks = [emb(C, D, 2 + i).cuda() for i in range(nb)]
     feats = [torch.randn(B, D, device="cuda") for _ in range(4)]
     xs = [ops.normalize_rows(f) for f in feats]
-    for exchange in ("p2p", "nccl"):
-        ses = ShardedEvalStream(banks[0], 0, batch=B, K=K, steps=8, banks=banks, exchange=exchange)
+    for exchange, ch in (("p2p", 1), ("p2p", 2), ("p2p", 3), ("nccl", 1)):
+        ses = ShardedEvalStream(banks[0], 0, batch=B, K=K, steps=8, banks=banks, exchange=exchange, channels=ch)
         for s in range(8):
             ses.dev_feats[s].copy_(feats[s % 4])
         for _ in range(3):
@@ -29,7 +29,7 @@ for C in (10921, 5461, 2731):
             ses.run()
         e1.record()
         torch.cuda.synchronize()
-        print("C=%d %s pipeline: %.2f us/step" % (C, exchange, e0.elapsed_time(e1) / 160 * 1e3), flush=True)
+        print("C=%d %s x%d pipeline: %.2f us/step" % (C, exchange, ch, e0.elapsed_time(e1) / 160 * 1e3), flush=True)
     NM = _cabi.HGR_IMPL_FLAG_NO_MERGE
     print("  normalize      %.2f us" % timeit(lambda i: ops.normalize_rows(feats[i % 4])))
     print("  score no-merge %.2f us" % timeit(lambda i: ops.score_topk(xs[i % 4], banks[i % nb], K=K, impl=ops.HGR_IMPL_TCGEN05 | NM)))
