@@ -16,7 +16,7 @@ for C in (10921, 5461, 2731):
     banks = [emb(C, D, 2 + i).cuda() for i in range(nb)]
     feats = [torch.randn(B, D, device="cuda") for _ in range(4)]
     xs = [ops.normalize_rows(f) for f in feats]
-    for exchange, ch in (("p2p", 1), ("p2p", 2), ("p2p", 3), ("nccl", 1)):
+    for exchange, ch in (("p2p", 1), ("p2p", 2), ("p2p", 3), ("p2p", 4), ("nccl", 1)):
         ses = ShardedEvalStream(banks[0], 0, batch=B, K=K, steps=8, banks=banks, exchange=exchange, channels=ch)
         for s in range(8):
             ses.dev_feats[s].copy_(feats[s % 4])
