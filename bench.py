@@ -362,6 +362,17 @@ def run_ours(args):
 
         def step_e2e(i):
             es.step(i % cycle)       # graph: H2D feats+labels -> normalise -> score/top-20/Hit@k -> D2H hit counters
+    elif args.exchange == "p2p":
+        # host-fed sharded evaluator: per batch every rank copies ITS block of image rows (+ labels) from pinned
+        # host memory, NVLink replicates the normalised rows, Hit@k counters are read back after every batch
+        ses_h = ShardedEvalStream(banks[0], lo, batch=B, K=K, steps=G_STEPS, banks=banks, host_io=True)
+        for s_ in range(G_STEPS):
+            ses_h.host_feats[s_].copy_(feats_host[s_ % n_feat][ses_h.row_lo:ses_h.row_hi])
+            ses_h.host_labels[s_].copy_(labels_host[s_ % n_feat][ses_h.row_lo:ses_h.row_hi].to(torch.int32))
+
+        def step_e2e(i):
+            if i % G_STEPS == 0:
+                ses_h.run()
     else:
         def step_e2e(i):
             f = feats_host[i % n_feat].to(dev, non_blocking=True)
@@ -419,7 +430,11 @@ def run_ours(args):
                        "l2": "inputs larger than L2: %d bank copies (%.0f MB) + %d feature batches rotated" %
                              (n_bank, n_bank * Cs * D * 2 / 1e6, n_feat)},
             "e2e": {"value": e2e_value, "unit": "images/s", "ms_per_step": e2e_ms,
-                    "h2d_bytes_per_step": B * D * 4 + B * (4 if world == 1 else 8), "d2h_bytes_per_step": 5 * 8},
+                    # whole job: with the peer exchange every image row crosses PCIe once (on the rank that owns it);
+                    # with the NCCL exchange every rank copies the whole batch
+                    "h2d_bytes_per_step": (B * D * 4 + B * 4) if (world == 1 or args.exchange == "p2p")
+                                          else world * (B * D * 4 + B * 8),
+                    "d2h_bytes_per_step": 5 * 8 * world},
             "e2e_fp16_features": e2e16,
             "gpu_launches": int(launches),
             "sustained": {"value": B / (sus_ms * 1e-3), "unit": "images/s", "steps": n_sus, "ms_per_step": sus_ms},

@@ -214,6 +214,52 @@ normalize_rows_kernel(const TIn* __restrict__ E, int D8, const int32_t* __restri
   }
 }
 
+// Row normalise with BROADCAST stores: row r of the local block lands at row (row0 + r) of every destination
+// (bf16 [*, D] arrays; local or peer memory).  Feature ingest of the class-sharded head: every rank copies only
+// its own block of image rows from the host, and the normalised A operand is replicated over NVLink by the
+// producing kernel (16-byte stores, 512 contiguous bytes per warp instruction).
+struct BcastDst {
+  __nv_bfloat16* p[16];
+};
+template <typename TIn, int MAXV>
+__global__ void __launch_bounds__(256)
+normalize_bcast_kernel(const TIn* __restrict__ E, int D8, int64_t n_rows, int64_t row0, BcastDst dst, int n_dst) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  const int64_t D = static_cast<int64_t>(D8) * 8;
+  for (int64_t row = warp0; row < n_rows; row += nwarps) {
+    float a[MAXV][8];
+#pragma unroll
+    for (int v = 0; v < MAXV; ++v) {
+      const int idx = lane + 32 * v;
+      if (idx < D8) {
+        Vec8<TIn>::load(E + row * D + idx * 8, a[v]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) a[v][e] = 0.f;
+      }
+    }
+    float ss = 0.f;
+#pragma unroll
+    for (int v = 0; v < MAXV; ++v)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) ss = fmaf(a[v][e], a[v][e], ss);
+    ss = warp_sum(ss);
+    const float n = sqrtf(ss);
+#pragma unroll
+    for (int v = 0; v < MAXV; ++v) {
+      const int idx = lane + 32 * v;
+      if (idx < D8) {
+        float o[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = __fdiv_rn(a[v][e], n);
+        for (int g = 0; g < n_dst; ++g) Vec8<__nv_bfloat16>::store(dst.p[g] + (row0 + row) * D + idx * 8, o);
+      }
+    }
+  }
+}
+
 // Any D (multiple of 8): two passes over the gathered rows, nothing kept in registers.
 template <typename TIn, typename TOut>
 __global__ void __launch_bounds__(256)
@@ -304,6 +350,34 @@ int dispatch(const void* E, int64_t D, const int32_t* rowptr, const int32_t* col
 }
 
 }  // namespace
+
+template <typename TIn>
+static int dispatch_bcast(const void* E, int64_t D, int64_t n_rows, int64_t row0, int n_dst, void* const* dst,
+                          cudaStream_t stream) {
+  BcastDst d{};
+  for (int g = 0; g < n_dst; ++g) d.p[g] = static_cast<__nv_bfloat16*>(dst[g]);
+  const int D8 = static_cast<int>(D / 8);
+  const int64_t want = (n_rows + 7) / 8;
+  const int64_t cap = static_cast<int64_t>(num_sms()) * 4;
+  const int nb = static_cast<int>(want < cap ? (want < 1 ? 1 : want) : cap);
+  const TIn* e = static_cast<const TIn*>(E);
+  if (D8 <= 32) normalize_bcast_kernel<TIn, 1><<<nb, 256, 0, stream>>>(e, D8, n_rows, row0, d, n_dst);
+  else if (D8 <= 64) normalize_bcast_kernel<TIn, 2><<<nb, 256, 0, stream>>>(e, D8, n_rows, row0, d, n_dst);
+  else if (D8 <= 96) normalize_bcast_kernel<TIn, 3><<<nb, 256, 0, stream>>>(e, D8, n_rows, row0, d, n_dst);
+  else normalize_bcast_kernel<TIn, 4><<<nb, 256, 0, stream>>>(e, D8, n_rows, row0, d, n_dst);
+  HGR_CHECK_LAUNCH();
+  return HGR_OK;
+}
+
+int launch_normalize_bcast(const void* E, int e_dtype, int64_t n_rows, int64_t D, int64_t row0, int n_dst,
+                           void* const* dst, cudaStream_t stream) {
+  if (n_rows == 0) return HGR_OK;
+  if (D > 1024) return set_error(HGR_ERR_UNSUPPORTED, "hgr_normalize_rows_bcast: D = %lld > 1024", (long long)D);
+  if (e_dtype == HGR_F32) return dispatch_bcast<float>(E, D, n_rows, row0, n_dst, dst, stream);
+  if (e_dtype == HGR_F16) return dispatch_bcast<__half>(E, D, n_rows, row0, n_dst, dst, stream);
+  if (e_dtype == HGR_BF16) return dispatch_bcast<__nv_bfloat16>(E, D, n_rows, row0, n_dst, dst, stream);
+  return set_error(HGR_ERR_UNSUPPORTED, "hgr_normalize_rows_bcast: dtype %d not supported", e_dtype);
+}
 
 int launch_aggregate_normalize(const void* E, int e_dtype, int64_t n_src, int64_t D, const int32_t* rowptr,
                                const int32_t* col, const float* w, const int32_t* row_map, int64_t n_out,

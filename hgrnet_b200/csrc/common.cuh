@@ -114,6 +114,9 @@ int launch_score_topk_umma(const __nv_bfloat16* X, const __nv_bfloat16* bank, co
                            int32_t* topk_idx, int64_t* hits, int variant, bool skip_merge,
                            cudaStream_t stream, const OutScatter* scatter = nullptr);
 
+int launch_normalize_bcast(const void* E, int e_dtype, int64_t n_rows, int64_t D, int64_t row0, int n_dst,
+                           void* const* dst, cudaStream_t stream);
+
 // cross-GPU sequencing of the peer-memory exchange (topk_merge.cu)
 int launch_peer_signal(uint32_t* const* flags, int n, uint32_t* seq, cudaStream_t stream);
 int launch_peer_wait(const uint32_t* flags, int n, uint32_t* seq, cudaStream_t stream);

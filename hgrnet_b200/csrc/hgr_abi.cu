@@ -186,6 +186,20 @@ int hgr_peer_free(void* ptr) {
   return HGR_OK;
 }
 
+int hgr_normalize_rows_bcast(const void* E, int e_dtype, int64_t n_rows, int64_t D, int64_t row0, int n_dst,
+                             void* const* dst, void* stream) {
+  HGR_CHECK_ARG(n_rows >= 0 && row0 >= 0, "hgr_normalize_rows_bcast: negative size");
+  HGR_CHECK_ARG(D > 0 && D % 8 == 0, "hgr_normalize_rows_bcast: D = %lld must be a positive multiple of 8", (long long)D);
+  HGR_CHECK_ARG(n_dst >= 1 && n_dst <= kMaxScatterBlocks, "hgr_normalize_rows_bcast: n_dst = %d outside [1, %d]", n_dst,
+                kMaxScatterBlocks);
+  if (n_rows == 0) return HGR_OK;
+  HGR_CHECK_ARG(E && dst, "hgr_normalize_rows_bcast: null pointer");
+  for (int g = 0; g < n_dst; ++g)
+    HGR_CHECK_ARG(dst[g] && aligned16(dst[g]), "hgr_normalize_rows_bcast: destination %d null or not 16-byte aligned", g);
+  HGR_CHECK_ARG(aligned16(E), "hgr_normalize_rows_bcast: E must be 16-byte aligned");
+  return launch_normalize_bcast(E, e_dtype, n_rows, D, row0, n_dst, dst, static_cast<cudaStream_t>(stream));
+}
+
 int hgr_peer_signal(uint32_t* const* flags, int n, uint32_t* seq, void* stream) {
   HGR_CHECK_ARG(flags && seq, "hgr_peer_signal: null pointer");
   return launch_peer_signal(flags, n, seq, static_cast<cudaStream_t>(stream));

@@ -106,14 +106,21 @@ class _RawCuda:
         self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
 
 
-def exchange_layout(B: int, K: int, world: int, slots: int):
-    """Byte layout of one rank's exchange buffer: a 256-byte header (one flag word per producer rank), then per
-    slot the value lists ``[world, block_rows, K]`` fp32 followed by the id lists ``[world, block_rows, K]`` int32."""
+X_SLOTS = 2  # feature-ingest slots per exchange (two batches of a channel in flight are provably enough)
+
+
+def exchange_layout(B: int, K: int, world: int, slots: int, D: int = 0):
+    """Byte layout of one rank's exchange buffer: a 256-byte header (list flags: one word per producer rank at
+    byte 0, feature flags at byte 64), then per slot the value lists ``[world, block_rows, K]`` fp32 followed by
+    the id lists ``[world, block_rows, K]`` int32 and, when ``D`` is given, ``X_SLOTS`` replicas of the normalised
+    image features ``[B, D]`` bf16 (feature ingest, see ``PeerExchange.ingest``)."""
     block_rows = (B + world - 1) // world
     part = block_rows * K * 4
     slot_bytes = 2 * world * part
+    x_off = (256 + slots * slot_bytes + 255) // 256 * 256
+    x_bytes = (B * D * 2 + 255) // 256 * 256
     return {"block_rows": block_rows, "part_bytes": part, "slot_bytes": slot_bytes, "header": 256,
-            "total": 256 + slots * slot_bytes}
+            "x_off": x_off, "x_bytes": x_bytes, "total": x_off + (X_SLOTS * x_bytes if D else 0)}
 
 
 class PeerExchange:
@@ -127,7 +134,8 @@ class PeerExchange:
     merges its ``world`` lists per row (``hgr_topk_merge``).  ``slots`` batches can be in flight.
     """
 
-    def __init__(self, B: int, K: int, device, group=None, slots: int = 4, _bases=None, _rank=None, _world=None):
+    def __init__(self, B: int, K: int, device, group=None, slots: int = 4, D: int = 0, _bases=None, _rank=None,
+                 _world=None):
         self.device = torch.device(device)
         self.group = group
         if _bases is None:
@@ -137,8 +145,8 @@ class PeerExchange:
             self.world, self.rank = _world, _rank
         if self.world > 16:
             raise ValueError("PeerExchange supports up to 16 ranks (HGR_MAX_PEERS)")
-        self.B, self.K, self.slots = B, K, slots
-        self.lay = exchange_layout(B, K, self.world, slots)
+        self.B, self.K, self.slots, self.D = B, K, slots, D
+        self.lay = exchange_layout(B, K, self.world, slots, D)
         self.block_rows = self.lay["block_rows"]
         self.lo = min(B, self.rank * self.block_rows)
         self.hi = min(B, self.lo + self.block_rows)
@@ -163,8 +171,9 @@ class PeerExchange:
                 else:
                     self.bases = [own]
         self.local = torch.as_tensor(_RawCuda(self.bases[self.rank], self.lay["total"]), device=self.device)
-        self.seq = torch.zeros(2, dtype=torch.int32, device=self.device)   # [signals sent, waits done]
+        self.seq = torch.zeros(4, dtype=torch.int32, device=self.device)   # lists: [sent, waited]; features: same
         self.flag_ptrs = [b + 4 * self.rank for b in self.bases]
+        self.xflag_ptrs = [b + 64 + 4 * self.rank for b in self.bases]
 
     # -- addresses -------------------------------------------------------------------------------------------
     def _slot_base(self, base: int, slot: int) -> int:
@@ -182,20 +191,43 @@ class PeerExchange:
         base = self._slot_base(self.bases[self.rank], slot)
         return base, base + self.world * self.lay["part_bytes"], self.block_rows * self.K
 
+    # -- feature ingest ----------------------------------------------------------------------------------------
+    def x_ptrs(self, xslot: int):
+        return [b + self.lay["x_off"] + xslot * self.lay["x_bytes"] for b in self.bases]
+
+    def x_view(self, xslot: int) -> torch.Tensor:
+        """The local replica of the normalised features of a slot, ``[B, D]`` bf16."""
+        off = self.lay["x_off"] + xslot * self.lay["x_bytes"]
+        return self.local[off:off + self.B * self.D * 2].view(torch.bfloat16).view(self.B, self.D)
+
+    def ingest(self, feats_block: torch.Tensor, xslot: int) -> torch.Tensor:
+        """``feats_block``: MY rows ``[hi - lo, D]`` of the batch (any float dtype).  Normalises them, stores them
+        into every rank's replica over NVLink, waits until all ``world`` blocks have arrived here and returns the
+        complete normalised batch ``[B, D]`` bf16 (a view of the exchange buffer)."""
+        if not self.D:
+            raise ValueError("PeerExchange was built without a feature area (D = 0)")
+        if self.hi > self.lo:
+            ops.normalize_rows_bcast(feats_block, self.lo, self.x_ptrs(xslot))
+        ops.peer_signal(self.xflag_ptrs, self.seq[2:3])
+        ops.peer_wait(self.bases[self.rank] + 64, self.world, self.seq[3:4])
+        return self.x_view(xslot)
+
     # -- per batch -------------------------------------------------------------------------------------------
     def scatter(self, x_norm: torch.Tensor, bank: torch.Tensor, id_base: int, slot: int, col_id=None) -> None:
         val, idx = self.block_ptrs(slot)
         ops.score_topk_scatter(x_norm, bank, val, idx, self.block_rows, col_id=col_id, id_base=id_base, K=self.K)
         ops.peer_signal(self.flag_ptrs, self.seq[0:1])
 
-    def merge(self, slot: int, targets: Optional[torch.Tensor], hits: Optional[torch.Tensor], out=None):
-        """Final top-K (+ hits) of MY rows ``[lo, hi)``; ``targets`` holds the labels of the whole batch."""
+    def merge(self, slot: int, targets: Optional[torch.Tensor], hits: Optional[torch.Tensor], out=None,
+              targets_local: bool = False):
+        """Final top-K (+ hits) of MY rows ``[lo, hi)``; ``targets`` holds the labels of the whole batch (or of my
+        rows only with ``targets_local``)."""
         ops.peer_wait(self.bases[self.rank], self.world, self.seq[1:2])
         n = self.hi - self.lo
         if n <= 0:
             return None
         pv, pi, stride = self.local_parts(slot)
-        t = targets[self.lo:self.hi] if targets is not None else None
+        t = None if targets is None else (targets if targets_local else targets[self.lo:self.hi])
         return ops.topk_merge_raw(pv, pi, self.world, n, self.K, stride, self.device, targets=t, hits=hits, out=out)
 
     def close(self) -> None:
@@ -226,17 +258,20 @@ class ShardedEvalStream:
 
     def __init__(self, bank_shard: torch.Tensor, id_base: int, *, batch: int, K: int = 20, steps: int = 8,
                  feat_dtype=torch.float32, banks=None, group=None, use_graph: bool = True, exchange: str = "p2p",
-                 channels: int = 4):
+                 channels: int = 4, host_io: bool = False):
         if exchange not in ("p2p", "nccl"):
             raise ValueError("exchange must be 'p2p' or 'nccl'")
-        self.exchange = exchange
+        if host_io and exchange != "p2p":
+            raise ValueError("host_io needs the peer-memory exchange")
+        self.exchange, self.host_io = exchange, host_io
         self.device = bank_shard.device
         self.banks = list(banks) if banks is not None else [bank_shard]
         self.id_base, self.K, self.B, self.steps, self.group = id_base, K, batch, steps, group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         D = bank_shard.shape[1]
-        self.dev_feats = [torch.empty((batch, D), dtype=feat_dtype, device=self.device) for _ in range(steps)]
-        self.dev_labels = [torch.zeros((batch,), dtype=torch.int32, device=self.device) for _ in range(steps)]
+        if not host_io:
+            self.dev_feats = [torch.empty((batch, D), dtype=feat_dtype, device=self.device) for _ in range(steps)]
+            self.dev_labels = [torch.zeros((batch,), dtype=torch.int32, device=self.device) for _ in range(steps)]
         self.hits = ops.new_hits(self.device)
         self.val = [None] * steps
         self.idx = [None] * steps
@@ -247,13 +282,24 @@ class ShardedEvalStream:
             # channel s % channels, so the normalise / merge kernels of one batch fill the SMs the persistent GEMM
             # of the neighbouring batch leaves idle at its edges
             self.channels = max(1, min(channels, steps))
-            self.pxs = [PeerExchange(batch, K, self.device, group=group, slots=self.slots) for _ in range(self.channels)]
+            self.pxs = [PeerExchange(batch, K, self.device, group=group, slots=self.slots, D=D if host_io else 0)
+                        for _ in range(self.channels)]
             self.px = self.pxs[0]
             self.side = [torch.cuda.Stream(device=self.device) for _ in range(self.channels)]
             self.row_lo, self.row_hi = self.px.lo, self.px.hi
             n_my = max(0, self.row_hi - self.row_lo)
             self.val = [torch.empty((n_my, K), dtype=torch.float32, device=self.device) for _ in range(steps)]
             self.idx = [torch.empty((n_my, K), dtype=torch.int32, device=self.device) for _ in range(steps)]
+            if host_io:
+                # feature ingest: this rank copies only ITS rows (and their labels) from pinned host memory; the
+                # normalised rows reach the other ranks over NVLink (PeerExchange.ingest); Hit@k counters go back
+                # to the host after every batch
+                pin = dict(pin_memory=True)
+                self.host_feats = [torch.zeros((n_my, D), dtype=feat_dtype, **pin) for _ in range(steps)]
+                self.host_labels = [torch.zeros((n_my,), dtype=torch.int32, **pin) for _ in range(steps)]
+                self.host_hits = [torch.zeros((ops.HGR_NUM_HITS,), dtype=torch.int64, **pin) for _ in range(steps)]
+                self.dev_feats = [torch.empty((n_my, D), dtype=feat_dtype, device=self.device) for _ in range(steps)]
+                self.dev_labels = [torch.zeros((n_my,), dtype=torch.int32, device=self.device) for _ in range(steps)]
             if self.world > 1:
                 dist.barrier(group=group)          # every buffer is mapped everywhere before the first store
         else:
@@ -280,8 +326,15 @@ class ShardedEvalStream:
         self.hits.zero_()
 
     def _local(self, s: int):
-        x = ops.normalize_rows(self.dev_feats[s])
         bank = self.banks[s % len(self.banks)]
+        if self.host_io:
+            px, j = self.pxs[s % self.channels], s // self.channels
+            self.dev_feats[s].copy_(self.host_feats[s], non_blocking=True)
+            self.dev_labels[s].copy_(self.host_labels[s], non_blocking=True)
+            x = px.ingest(self.dev_feats[s], j % X_SLOTS)
+            px.scatter(x, bank, self.id_base, j % self.slots)
+            return None
+        x = ops.normalize_rows(self.dev_feats[s])
         if self.exchange == "p2p":
             self.pxs[s % self.channels].scatter(x, bank, self.id_base, (s // self.channels) % self.slots)
             return None
@@ -300,7 +353,9 @@ class ShardedEvalStream:
     def _merge(self, s: int, work):
         if self.exchange == "p2p":
             self.pxs[s % self.channels].merge((s // self.channels) % self.slots, self.dev_labels[s], self.hits,
-                                              out=(self.val[s], self.idx[s]))
+                                              out=(self.val[s], self.idx[s]), targets_local=self.host_io)
+            if self.host_io:
+                self.host_hits[s].copy_(self.hits, non_blocking=True)
             return
         if work is not None:
             work.wait()

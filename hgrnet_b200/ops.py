@@ -229,6 +229,19 @@ def peer_free(ptr: int) -> None:
     _cabi.check(_cabi.load().hgr_peer_free(ptr))
 
 
+def normalize_rows_bcast(x_block: torch.Tensor, row0: int, dst_ptrs) -> None:
+    """Normalise the rows of ``x_block`` and store row r at row ``row0 + r`` of every bf16 ``[*, D]`` array in
+    ``dst_ptrs`` (device pointers, local or peer)."""
+    import ctypes
+    x_block = _require(x_block, "x_block")
+    if x_block.dtype not in _DTYPE_CODE:
+        raise TypeError("x_block dtype %s not supported" % x_block.dtype)
+    n, D = x_block.shape
+    dt = (ctypes.c_void_p * len(dst_ptrs))(*dst_ptrs)
+    _cabi.check(_cabi.load().hgr_normalize_rows_bcast(_ptr(x_block), _DTYPE_CODE[x_block.dtype], n, D, row0,
+                                                      len(dst_ptrs), dt, _stream()))
+
+
 def peer_signal(flag_ptrs, seq: torch.Tensor) -> None:
     """Publish this rank's next sequence number (``seq`` is a 1-element int32 device counter) to ``flag_ptrs``."""
     import ctypes

@@ -154,6 +154,12 @@ int hgr_score_topk_scatter(const void* X, const void* bank, const int32_t* col_i
                            int64_t C, int64_t D, float scale, int K, void* workspace, size_t workspace_bytes,
                            int64_t block_rows, int n_blocks, float* const* val_blocks,
                            int32_t* const* idx_blocks, int impl, void* stream);
+ /* hgr_normalize_rows_bcast: feature ingest of the sharded head.  A rank copies only ITS block of image rows from the
+  * host; this kernel normalises them (clip_tree.py:330) and stores row r at row (row0 + r) of every destination
+  * dst[g] (HOST array of n_dst device pointers to bf16 [*, D] arrays, local or peer), so the A operand of
+  * hgr_score_topk is replicated over NVLink by the producer instead of n_dst times over PCIe. */
+int hgr_normalize_rows_bcast(const void* E, int e_dtype, int64_t n_rows, int64_t D, int64_t row0, int n_dst,
+                             void* const* dst, void* stream);
 int hgr_peer_signal(uint32_t* const* flags, int n, uint32_t* seq, void* stream);
 int hgr_peer_wait(const uint32_t* flags, int n, uint32_t* seq, void* stream);
 

@@ -52,6 +52,34 @@ def test_scatter_exchange_matches_single_gpu(B, C, D, G):
             ops.peer_free(b)
 
 
+@pytest.mark.parametrize("B,D,G,dtype", [(512, 1024, 8, torch.float32), (130, 256, 3, torch.float16), (5, 64, 8, torch.float32)])
+def test_feature_ingest_replicates_normalised_rows(B, D, G, dtype):
+    """Every logical rank normalises its own row block and broadcasts it; afterwards every replica equals the
+    single-GPU normalise of the whole batch, bit for bit."""
+    from hgrnet_b200 import ops
+    from hgrnet_b200.dist import PeerExchange, exchange_layout
+    dev = torch.device("cuda", 0)
+    feats = torch.randn(B, D, generator=torch.Generator().manual_seed(4)).to(dtype).to(dev)
+    ref = ops.normalize_rows(feats)
+    lay = exchange_layout(B, 20, G, 4, D)
+    bufs = [ops.peer_alloc(lay["total"])[0] for _ in range(G)]
+    try:
+        ranks = [PeerExchange(B, 20, dev, slots=4, D=D, _bases=bufs, _rank=r, _world=G) for r in range(G)]
+        for xslot in (0, 1, 0):
+            # producers first (a single stream: a consumer's wait must not precede the producers it waits for)
+            for px in ranks:
+                if px.hi > px.lo:
+                    ops.normalize_rows_bcast(feats[px.lo:px.hi], px.lo, px.x_ptrs(xslot))
+                ops.peer_signal(px.xflag_ptrs, px.seq[2:3])
+            for px in ranks:
+                ops.peer_wait(px.bases[px.rank] + 64, G, px.seq[3:4])
+                assert torch.equal(px.x_view(xslot), ref)
+    finally:
+        torch.cuda.synchronize()
+        for b in bufs:
+            ops.peer_free(b)
+
+
 def test_peer_wait_passes_only_after_all_signals():
     """The wait kernel of a consumer must not complete before every producer has signalled."""
     from hgrnet_b200 import ops
