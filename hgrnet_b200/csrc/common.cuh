@@ -114,6 +114,10 @@ int launch_score_topk_umma(const __nv_bfloat16* X, const __nv_bfloat16* bank, co
                            int32_t* topk_idx, int64_t* hits, int variant, bool skip_merge,
                            cudaStream_t stream, const OutScatter* scatter = nullptr);
 
+int launch_hier_metrics(const float* logits, int64_t ldl, int64_t B, const int32_t* cols, int64_t M,
+                        const int8_t* level, int n_levels, const int32_t* first_out, const int32_t* chain,
+                        const int32_t* chain_level, int L, int32_t* lvl_idx, int32_t* top1, int64_t* counts,
+                        cudaStream_t stream);
 int launch_normalize_bcast(const void* E, int e_dtype, int64_t n_rows, int64_t D, int64_t row0, int n_dst,
                            void* const* dst, cudaStream_t stream);
 

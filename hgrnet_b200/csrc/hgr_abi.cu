@@ -253,6 +253,20 @@ int hgr_logits_dense(const void* X, const void* bank, int64_t B, int64_t C, int6
   return set_error(HGR_ERR_BAD_ARG, "hgr_logits_dense: unknown impl %d", impl);
 }
 
+int hgr_hier_metrics(const float* logits, int64_t ldl, int64_t B, int64_t N, const int32_t* cols, int64_t M,
+                     const int8_t* level, int n_levels, const int32_t* first_out, const int32_t* chain,
+                     const int32_t* chain_level, int L, int32_t* lvl_idx, int32_t* top1, int64_t* counts, void* stream) {
+  HGR_CHECK_ARG(B >= 0 && N > 0 && M > 0 && M <= (int64_t(1) << 31) - 1, "hgr_hier_metrics: bad sizes B=%lld N=%lld M=%lld",
+                (long long)B, (long long)N, (long long)M);
+  HGR_CHECK_ARG(ldl >= N, "hgr_hier_metrics: ldl < N");
+  HGR_CHECK_ARG(L >= 1 && L <= 64, "hgr_hier_metrics: chain length %d outside [1, 64]", L);
+  if (B == 0) return HGR_OK;
+  HGR_CHECK_ARG(logits && level && first_out && chain && chain_level && counts, "hgr_hier_metrics: null pointer");
+  HGR_CHECK_ARG(cols != nullptr || M == N, "hgr_hier_metrics: cols == NULL needs M == N");
+  return launch_hier_metrics(logits, ldl, B, cols, M, level, n_levels, first_out, chain, chain_level, L, lvl_idx, top1,
+                             counts, static_cast<cudaStream_t>(stream));
+}
+
 size_t hgr_masked_ce_workspace_bytes(int64_t B, int64_t U, int64_t T) { return masked_ce_workspace_bytes(B, U, T) + 16; }
 
 int hgr_masked_ce(const float* logits, int64_t ldl, int64_t B, int64_t U, const int32_t* set_ptr, const int32_t* set_col,

@@ -1,0 +1,149 @@
+// TOR / POR hierarchical metrics of one single-label batch in ONE pass over the dense logits.
+//
+// Reference: main.py:143,152-191.  Per batch the reference takes the arg-max over `train_index` (TOR, :155-160)
+// and, for every node p of the label's ancestor chain, clones the [B, N] logits, fills every column that is not at
+// p's depth with -1, gathers `train_index` and takes another arg-max (:163-176) -- L + 1 passes over B x N plus a
+// Python B x L loop with device->host copies (:177-191).  Here one CTA per image row walks the train columns once,
+// keeps a running (value, position) arg-max PER DEPTH LEVEL (the depth of a column is one int8 look-up), and then
+// counts chain matches itself:
+//   counts[0] += #{k : top1 == chain[k]}                                   -> hits_all          (main.py:158-160)
+//   counts[1] += #{k : lvl[depth(chain[k])] == chain[k]}                   -> point             (main.py:182-189)
+//   counts[2] += #{k < L-1 : match[k] and match[k+1]}  (L == 1: match[0])  -> edge / single-node path (main.py:179-185)
+// HBM-bound: B * M * 4 bytes of logits read once (+ M * 5 bytes of column ids / levels from L2).
+//
+// Tie rule = first position (what an arg-max over the masked array returns on the CPU): among equal values the
+// smallest position j in `cols` wins; a masked column holds exactly -1.0f, so when no in-level value exceeds -1 the
+// first position holding -1 wins -- `first_out[l]` is the first position whose column is NOT at level l.
+#include "common.cuh"
+
+namespace hgr {
+namespace {
+
+constexpr int kHierThreads = 128;
+constexpr int kMaxLevels = 16;
+
+struct Best {
+  float v;
+  int32_t j;
+};
+__device__ __forceinline__ bool better(float v, int32_t j, float bv, int32_t bj) {
+  return v > bv || (v == bv && j < bj);
+}
+
+__global__ void __launch_bounds__(kHierThreads)
+hier_metrics_kernel(const float* __restrict__ logits, int64_t ldl, const int32_t* __restrict__ cols, int64_t M,
+                    const int8_t* __restrict__ level, int n_levels, const int32_t* __restrict__ first_out,
+                    const int32_t* __restrict__ chain, const int32_t* __restrict__ chain_level, int L,
+                    int32_t* __restrict__ lvl_idx, int32_t* __restrict__ top1, unsigned long long* counts) {
+  __shared__ float s_v[kMaxLevels][kHierThreads];
+  __shared__ int32_t s_j[kMaxLevels][kHierThreads];
+  __shared__ float s_wv[kMaxLevels][kHierThreads / 32];
+  __shared__ int32_t s_wj[kMaxLevels][kHierThreads / 32];
+  __shared__ int32_t s_node[kMaxLevels];      // winner node per level (after the -1 rule)
+  __shared__ float s_tv[kMaxLevels];          // in-level maxima (before the -1 rule): their best is the TOR top-1
+  __shared__ int32_t s_tj[kMaxLevels];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t row = blockIdx.x;
+  const float* lr = logits + row * ldl;
+  for (int l = 0; l < n_levels; ++l) {
+    s_v[l][tid] = -INFINITY;
+    s_j[l][tid] = 0x7FFFFFFF;
+  }
+  // one pass: positions tid, tid + 128, ... (ascending per thread, so `>` keeps the first of equal values)
+  for (int64_t j = tid; j < M; j += kHierThreads) {
+    const int32_t c = cols ? cols[j] : static_cast<int32_t>(j);
+    const int l = level[c];
+    const float v = lr[c];
+    if (l >= 0 && l < n_levels && v > s_v[l][tid]) {
+      s_v[l][tid] = v;
+      s_j[l][tid] = static_cast<int32_t>(j);
+    }
+  }
+  // per level: block arg-max by (value desc, position asc)
+  for (int l = 0; l < n_levels; ++l) {
+    float v = s_v[l][tid];
+    int32_t j = s_j[l][tid];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, v, o);
+      const int32_t oj = __shfl_xor_sync(0xffffffffu, j, o);
+      if (better(ov, oj, v, j)) {
+        v = ov;
+        j = oj;
+      }
+    }
+    if (lane == 0) {
+      s_wv[l][warp] = v;
+      s_wj[l][warp] = j;
+    }
+  }
+  __syncthreads();
+  if (tid <= n_levels) {
+    if (tid < n_levels) {
+      float v = s_wv[tid][0];
+      int32_t j = s_wj[tid][0];
+      for (int w = 1; w < kHierThreads / 32; ++w)
+        if (better(s_wv[tid][w], s_wj[tid][w], v, j)) {
+          v = s_wv[tid][w];
+          j = s_wj[tid][w];
+        }
+      s_tv[tid] = v;
+      s_tj[tid] = j;
+      // the masked array holds -1 at every out-of-level position (main.py:171)
+      const int32_t fo = first_out[tid];
+      if (fo >= 0 && fo < M && better(-1.0f, fo, v, j)) {
+        v = -1.0f;
+        j = fo;
+      }
+      if (j == 0x7FFFFFFF) j = 0;  // M == 0 cannot happen (checked on the host); defensive
+      const int32_t node = cols ? cols[j] : j;
+      s_node[tid] = node;
+      if (lvl_idx) lvl_idx[row * n_levels + tid] = node;
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    // overall top-1 over the train columns (main.py:155-156) = best of the per-level in-level maxima
+    float bv = -INFINITY;
+    int32_t bj = 0x7FFFFFFF;
+    for (int l = 0; l < n_levels; ++l)
+      if (s_tj[l] != 0x7FFFFFFF && better(s_tv[l], s_tj[l], bv, bj)) {
+        bv = s_tv[l];
+        bj = s_tj[l];
+      }
+    const int32_t t1 = bj == 0x7FFFFFFF ? -1 : (cols ? cols[bj] : bj);
+    if (top1) top1[row] = t1;
+    unsigned long long tor = 0, point = 0, edge = 0;
+    bool prev = false;
+    for (int k = 0; k < L; ++k) {
+      const int32_t p = chain[k];
+      tor += (t1 == p);
+      const int cl = chain_level[k];
+      const bool m = cl >= 0 && cl < n_levels && s_node[cl] == p;
+      point += m;
+      if (k > 0) edge += (prev && m);
+      prev = m;
+    }
+    if (L == 1) edge = prev ? 1 : 0;
+    if (tor) atomicAdd(counts + 0, tor);
+    if (point) atomicAdd(counts + 1, point);
+    if (edge) atomicAdd(counts + 2, edge);
+  }
+}
+
+}  // namespace
+
+int launch_hier_metrics(const float* logits, int64_t ldl, int64_t B, const int32_t* cols, int64_t M,
+                        const int8_t* level, int n_levels, const int32_t* first_out, const int32_t* chain,
+                        const int32_t* chain_level, int L, int32_t* lvl_idx, int32_t* top1, int64_t* counts,
+                        cudaStream_t stream) {
+  if (n_levels < 1 || n_levels > kMaxLevels)
+    return set_error(HGR_ERR_UNSUPPORTED, "hgr_hier_metrics: %d levels outside [1, %d]", n_levels, kMaxLevels);
+  hier_metrics_kernel<<<static_cast<unsigned>(B), kHierThreads, 0, stream>>>(
+      logits, ldl, cols, M, level, n_levels, first_out, chain, chain_level, L, lvl_idx, top1,
+      reinterpret_cast<unsigned long long*>(counts));
+  HGR_CHECK_LAUNCH();
+  return HGR_OK;
+}
+
+}  // namespace hgr

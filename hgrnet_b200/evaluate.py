@@ -34,44 +34,43 @@ def count_acc(hits_dict, num_tot):
 
 
 class HierMetrics:
-    """TOR / POR accumulators (main.py:123-127,152-191), vectorised over the batch."""
+    """TOR / POR accumulators (main.py:123-127,152-191).  One fused pass per batch (``hgr_hier_metrics``): per-level
+    arg-max over the train columns, chain matching and counting on the device; the per-batch divisions by the chain
+    length stay device-side float ops, nothing is copied to the host before the ratios are printed."""
 
     def __init__(self, model):
         self.model = model
-        self.hits_all = torch.zeros((), dtype=torch.float64, device=model.device)
-        self.path_all = torch.zeros((), dtype=torch.float64, device=model.device)
-        self.point_all = torch.zeros((), dtype=torch.float64, device=model.device)
+        dev = model.device
+        self.hits_all = torch.zeros((), dtype=torch.float64, device=dev)
+        self.path_all = torch.zeros((), dtype=torch.float64, device=dev)
+        self.point_all = torch.zeros((), dtype=torch.float64, device=dev)
         self.path_all_count = 0
-        N = len(model.nodes)
-        depth = torch.from_numpy(model.hierarchy.depth).to(model.device)
-        self._depth = depth
-        self._train_index = model.train_index
-        self._depth_train = depth[model.train_index]
-        self._N = N
+        depth = torch.from_numpy(model.hierarchy.depth).to(torch.int64)
+        self.n_levels = int(depth.max()) + 1 if depth.numel() else 1
+        self._level = depth.to(torch.int8).to(dev)
+        self._cols = model.train_index.to(torch.int32).contiguous()
+        # first position of train_index that is NOT at level l: where the reference's -1 fill (main.py:171) sits first
+        dt = depth[model.train_index.cpu()]
+        M = dt.numel()
+        first_out = []
+        for l in range(self.n_levels):
+            out = (dt != l).nonzero()
+            first_out.append(int(out[0]) if out.numel() else M)
+        self._first_out = torch.tensor(first_out, dtype=torch.int32, device=dev)
 
     def update(self, logits: torch.Tensor, target: int):
         m = self.model
         B = logits.shape[0]
         parents = list(m.c2p[target]) + [target]
         L = len(parents)
-        par = torch.tensor(parents, device=logits.device)
-        lt = logits[:, self._train_index]                                   # main.py:143
-        top1 = self._train_index[lt.argmax(1)]                              # main.py:155-156
-        self.hits_all += (top1[:, None] == par[None, :]).sum()              # main.py:158-160
-        # per chain level: arg-max over the nodes of that depth (everything else filled with -1), main.py:163-176
-        path = torch.empty((B, L), dtype=torch.long, device=logits.device)
-        for k, p in enumerate(parents):
-            level = len(m.c2p[p])
-            keep = self._depth_train == level                               # same_l = d2n[level] (p is in it)
-            lk = torch.where(keep[None, :], lt, torch.full_like(lt, -1.0))
-            path[:, k] = self._train_index[lk.argmax(1)]
-        match = path == par[None, :]                                        # main.py:179-189
-        point = match.sum()
-        if L - 1 == 0:
-            self.path_all += match[:, 0].sum()
-        else:
-            self.path_all += (match[:, :-1] & match[:, 1:]).sum().double() / (L - 1)
-        self.point_all += point.double() / L
+        chain = torch.tensor(parents, dtype=torch.int32).to(logits.device, non_blocking=True)
+        chain_level = torch.tensor([len(m.c2p[p]) for p in parents], dtype=torch.int32).to(logits.device, non_blocking=True)
+        counts = torch.zeros(3, dtype=torch.int64, device=logits.device)
+        ops.hier_metrics(logits, self._cols, self._level, self.n_levels, self._first_out, chain, chain_level, counts)
+        c = counts.double()
+        self.hits_all += c[0]                                               # main.py:158-160
+        self.path_all += c[2] if L == 1 else c[2] / (L - 1)                 # main.py:179-190
+        self.point_all += c[1] / L                                          # main.py:191
         self.path_all_count += B
 
     def ratios(self, num_sample):

@@ -270,6 +270,29 @@ def logits_dense(X: torch.Tensor, bank: torch.Tensor, scale: float = 1.0, impl: 
     return out
 
 
+def hier_metrics(logits: torch.Tensor, cols: Optional[torch.Tensor], level: torch.Tensor, n_levels: int,
+                 first_out: torch.Tensor, chain: torch.Tensor, chain_level: torch.Tensor, counts: torch.Tensor,
+                 lvl_idx: Optional[torch.Tensor] = None, top1: Optional[torch.Tensor] = None) -> None:
+    """TOR / POR counters of one single-label batch (main.py:143,152-191) in one pass over the dense logits;
+    ``counts`` (int64 [3]: TOR hits, points, edges) is incremented.  See ``hgr_hier_metrics`` in the header."""
+    lib = _cabi.load()
+    logits = _require(logits, "logits", torch.float32)
+    B, N = logits.shape
+    if cols is not None:
+        cols = _require(cols, "cols", torch.int32)
+    level = _require(level, "level", torch.int8)
+    first_out = _require(first_out, "first_out", torch.int32)
+    chain = _require(chain, "chain", torch.int32)
+    chain_level = _require(chain_level, "chain_level", torch.int32)
+    counts = _require(counts, "counts", torch.int64)
+    if level.numel() != N or first_out.numel() != n_levels or chain.numel() != chain_level.numel():
+        raise ValueError("hier_metrics: inconsistent sizes")
+    M = cols.numel() if cols is not None else N
+    _cabi.check(lib.hgr_hier_metrics(_ptr(logits), logits.stride(0), B, N, _ptr(cols), M, _ptr(level), n_levels,
+                                     _ptr(first_out), _ptr(chain), _ptr(chain_level), chain.numel(), _ptr(lvl_idx),
+                                     _ptr(top1), _ptr(counts), _stream()))
+
+
 def masked_ce(logits: torch.Tensor, set_ptr: torch.Tensor, set_col: torch.Tensor, label_pos: torch.Tensor,
               weight: torch.Tensor, need_grad: bool = True):
     """Fused masked CE over T class sets (model/clip_tree.py:241-277).  Returns ``(loss [T], dlogits [B,U] | None)``."""

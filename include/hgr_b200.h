@@ -174,6 +174,27 @@ int hgr_logits_dense(const void* X, const void* bank, int64_t B, int64_t C, int6
                      float scale, float* out, int64_t ldo, int impl, void* stream);
 
 /*
+ * TOR / POR hierarchical metrics of one single-label batch in one pass over dense logits (main.py:143,152-191;
+ * SURVEY.md 8-f1).  Replaces the L clone + index_fill + gather + topk passes over [B, N] and the Python B x L
+ * loop with device->host copies of the reference's test().
+ *
+ *  logits      [B, N] fp32 (hgr_logits_dense), row pitch ldl
+ *  cols        [M] int32 train_index (columns that take part), or NULL = all N columns
+ *  level       [N] int8 depth of every node (len(c2p[n])); n_levels <= 16
+ *  first_out   [n_levels] int32: first position j whose column is NOT at level l (a masked column holds -1.0,
+ *              so that position wins when no in-level logit exceeds -1; >= M when there is none)
+ *  chain       [L] int32 the label's ancestor chain + the label itself; chain_level [L] their depths
+ *  lvl_idx     [B, n_levels] int32 per-level arg-max node (optional), top1 [B] int32 arg-max over cols (optional)
+ *  counts      [3] int64, INCREMENTED: {TOR hits (sum over rows of #{k: top1 == chain[k]}),
+ *              points (#{k: lvl[chain_level[k]] == chain[k]}), edges (#{k: matches at k and k+1}; L == 1: match[0])}
+ * Ties: first position in `cols` (the CPU arg-max rule; torch's CUDA top-k leaves it unspecified).
+ */
+int hgr_hier_metrics(const float* logits, int64_t ldl, int64_t B, int64_t N, const int32_t* cols, int64_t M,
+                     const int8_t* level, int n_levels, const int32_t* first_out, const int32_t* chain,
+                     const int32_t* chain_level, int L, int32_t* lvl_idx, int32_t* top1, int64_t* counts,
+                     void* stream);
+
+/*
  * Fused masked cross-entropy of the OM training step over T sampled class sets
  * (model/clip_tree.py:241-277 with nn.CrossEntropyLoss, :49,:275).
  *

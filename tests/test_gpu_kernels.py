@@ -285,3 +285,40 @@ def test_masked_ce_matches_crossentropy(B, U, T):
     loss2, none = ops.masked_ce(logits.to(DEV), t(set_ptr), t(set_col), t(np.asarray(lps, np.int32)), t(weight),
                                 need_grad=False)
     assert none is None and torch.equal(loss2, loss)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# TOR / POR fused pass (hgr_hier_metrics) against the oracle's restatement of main.py:143,152-191
+@pytest.mark.parametrize("levels,B,train_every", [((4, 20, 200), 64, 1), ((3, 9, 40, 160), 33, 2), ((1, 5), 7, 1)])
+def test_hier_metrics_match_oracle(levels, B, train_every):
+    from hgrnet_b200 import ops
+    from hgrnet_b200.hierarchy import synthetic_hierarchy
+    from oracle import hgr_oracle as orc
+    h = synthetic_hierarchy(list(levels), seed=3)
+    N = len(h)
+    g = torch.Generator().manual_seed(11)
+    logits = torch.randn(B, N, generator=g).clamp_(-0.99, 0.99)
+    logits[:, 5] = logits[:, 3]                                       # exact ties between two columns
+    train_index = torch.arange(0, N, train_every)
+    depth = torch.from_numpy(h.depth).long()
+    n_levels = int(depth.max()) + 1
+    dt = depth[train_index]
+    first_out = torch.tensor([int((dt != l).nonzero()[0]) if (dt != l).any() else len(dt) for l in range(n_levels)],
+                             dtype=torch.int32, device=DEV)
+    for target in (N - 1, 0, N // 2):
+        parents = list(h.c2p[target]) + [target]
+        L = len(parents)
+        tor, path_add, point_add = orc.tor_por(logits, train_index, h.c2p, h.d2n, N, target)
+        counts = torch.zeros(3, dtype=torch.int64, device=DEV)
+        lvl = torch.empty((B, n_levels), dtype=torch.int32, device=DEV)
+        top1 = torch.empty((B,), dtype=torch.int32, device=DEV)
+        ops.hier_metrics(logits.to(DEV), train_index.int().to(DEV), depth.to(torch.int8).to(DEV), n_levels, first_out,
+                         torch.tensor(parents, dtype=torch.int32, device=DEV),
+                         torch.tensor([len(h.c2p[p]) for p in parents], dtype=torch.int32, device=DEV), counts,
+                         lvl_idx=lvl, top1=top1)
+        c = counts.tolist()
+        assert c[0] == int(tor)
+        assert abs((c[2] if L == 1 else c[2] / (L - 1)) - path_add) < 1e-9
+        assert abs(c[1] / L - point_add) < 1e-9
+        ref_top1 = train_index[logits[:, train_index].argmax(1)]
+        assert torch.equal(top1.cpu().long(), ref_top1)
