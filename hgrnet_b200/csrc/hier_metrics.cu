@@ -19,7 +19,8 @@
 namespace hgr {
 namespace {
 
-constexpr int kHierThreads = 128;
+constexpr int kHierThreads = 256;
+constexpr int kHierUnroll = 8;  // independent (column id -> level, logit) load chains in flight per thread
 constexpr int kMaxLevels = 16;
 
 struct Best {
@@ -50,13 +51,26 @@ hier_metrics_kernel(const float* __restrict__ logits, int64_t ldl, const int32_t
     s_j[l][tid] = 0x7FFFFFFF;
   }
   // one pass: positions tid, tid + 128, ... (ascending per thread, so `>` keeps the first of equal values)
-  for (int64_t j = tid; j < M; j += kHierThreads) {
-    const int32_t c = cols ? cols[j] : static_cast<int32_t>(j);
-    const int l = level[c];
-    const float v = lr[c];
-    if (l >= 0 && l < n_levels && v > s_v[l][tid]) {
-      s_v[l][tid] = v;
-      s_j[l][tid] = static_cast<int32_t>(j);
+  for (int64_t j0 = tid; j0 < M; j0 += kHierUnroll * kHierThreads) {
+    int32_t c[kHierUnroll];
+    int l[kHierUnroll];
+    float v[kHierUnroll];
+#pragma unroll
+    for (int u = 0; u < kHierUnroll; ++u) {
+      const int64_t j = j0 + u * kHierThreads;
+      c[u] = j < M ? (cols ? __ldg(cols + j) : static_cast<int32_t>(j)) : -1;
+    }
+#pragma unroll
+    for (int u = 0; u < kHierUnroll; ++u) {
+      l[u] = c[u] >= 0 ? __ldg(level + c[u]) : -1;
+      v[u] = c[u] >= 0 ? __ldg(lr + c[u]) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < kHierUnroll; ++u) {
+      if (l[u] >= 0 && l[u] < n_levels && v[u] > s_v[l[u]][tid]) {
+        s_v[l[u]][tid] = v[u];
+        s_j[l[u]][tid] = static_cast<int32_t>(j0 + u * kHierThreads);
+      }
     }
   }
   // per level: block arg-max by (value desc, position asc)

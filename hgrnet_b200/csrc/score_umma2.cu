@@ -33,6 +33,7 @@ __host__ __device__ constexpr int defer_depth(int wpq) { return wpq == 1 ? kDefe
 // ~2 us of main loop at cfg 2, and leaving room for co-resident small kernels bought nothing).
 constexpr int kDeferStages = kDeferDepth > 64 ? 4 : 5;
 constexpr int kOtherStages = 6;
+constexpr int kDenseTileFloats = 32 * 33;                  // dense epilogue: one padded 32x32 transpose tile per warp
 constexpr int kPairBBytes = (kSubN / 2) * kBlockK * 2;     // 16 KB: half of the bank sub-tile
 constexpr int kPairStageBytes = kABytes + kPairBBytes;     // 32 KB
 
@@ -51,7 +52,8 @@ score_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
   constexpr int kEpiThreads = 128 * WPQ;
   constexpr int kQueueDepth = defer_depth(WPQ);    // deferred-insert queue entries per thread (+1 dud slot)
   constexpr int kQueueBytes = EPI == kEpiTopkQueue ? kChunk * kEpiThreads * 4
-                            : EPI == kEpiTopkDefer ? (kQueueDepth + 1) * kEpiThreads * 8 : 0;
+                            : EPI == kEpiTopkDefer ? (kQueueDepth + 1) * kEpiThreads * 8
+                            : EPI == kEpiDense ? (kEpiThreads / 32) * kDenseTileFloats * 4 : 0;
   constexpr int kPairStages = EPI == kEpiTopkDefer ? kDeferStages : kOtherStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -216,12 +218,20 @@ score_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
           ck.lap(ck.ld);
           const int nv = t.nvalid - c0;
           if (EPI == kEpiDense) {
-            if (row < p.B) {
-              float* o = p.dense_out + row * p.ldo + t.col0 + c0;
+            // thread = row holds 32 consecutive columns; transpose the warp's 32x32 block through a padded smem
+            // tile so that every store instruction writes 128 contiguous bytes of ONE row
+            float* tile = queue_base + (warp - kEpiWarp0) * kDenseTileFloats;
 #pragma unroll
-              for (int j = 0; j < kChunk; ++j)
-                if (j < nv) o[j] = __uint_as_float(r[j]) * p.scale;
+            for (int j = 0; j < kChunk; ++j) tile[lane * 33 + j] = __uint_as_float(r[j]) * p.scale;
+            __syncwarp();
+            const int64_t row_base = row - lane;
+            float* o = p.dense_out + row_base * p.ldo + t.col0 + c0 + lane;
+            const int nrows = p.B - row_base < 32 ? static_cast<int>(p.B - row_base) : 32;
+            if (lane < nv) {
+#pragma unroll 8
+              for (int rr = 0; rr < nrows; ++rr) o[static_cast<int64_t>(rr) * p.ldo] = tile[rr * 33 + lane];
             }
+            __syncwarp();
           } else if (EPI == kEpiTopkQueue) {
             scan_chunk_queue<KL>(list, r, nv, t.col0 + c0, qaddr, qswz, floor_thr, ck);
           } else if (EPI == kEpiTopkDefer) {
@@ -314,7 +324,8 @@ template <int EPI, int KL, int WPQ>
 int launch_one(const CUtensorMap& mx, const CUtensorMap& mb, const Params& p, cudaStream_t stream) {
   constexpr int threads = 64 + 128 * WPQ;
   constexpr size_t queue = EPI == kEpiTopkQueue ? static_cast<size_t>(kChunk) * 128 * WPQ * 4
-                         : EPI == kEpiTopkDefer ? static_cast<size_t>(defer_depth(WPQ) + 1) * 128 * WPQ * 8 : 0;
+                         : EPI == kEpiTopkDefer ? static_cast<size_t>(defer_depth(WPQ) + 1) * 128 * WPQ * 8
+                         : EPI == kEpiDense ? static_cast<size_t>(4 * WPQ) * kDenseTileFloats * 4 : 0;
   const size_t smem = 1024 + static_cast<size_t>(EPI == kEpiTopkDefer ? kDeferStages : kOtherStages) * kPairStageBytes + queue + sizeof(PairCtl);
   auto kern = score_umma_pair_kernel<EPI, KL, WPQ>;
   HGR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));

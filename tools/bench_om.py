@@ -25,6 +25,9 @@ from hgrnet_b200.hierarchy import WORDNET_LIKE_21841, synthetic_hierarchy
 from hgrnet_b200.levels import level_weights
 from hgrnet_b200.synthetic import TableEncoder, node_id_tokens, synthetic_embeddings
 
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from sweep import timeit as graph_us   # per-call microseconds with the interpreter off the path (CUDA graph replay)
+
 DEV = "cuda:0"
 HBM = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))["hbm_gbs"] \
     if os.path.exists(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")) else 6650.0
@@ -120,7 +123,7 @@ def main():
     set_col = torch.tensor(np.concatenate(sets).astype(np.int32), device=DEV)
     lp = torch.tensor(rng.randint(0, 257, 17).astype(np.int32), device=DEV)
     w = torch.rand(17, device=DEV)
-    us_ce = events(lambda: ops.masked_ce(logits, set_ptr, set_col, lp, w), 200)
+    us_ce = graph_us(lambda i: ops.masked_ce(logits, set_ptr, set_col, lp, w))
     bytes_ce = 8.0 * B * U
     out["masked_ce_kernel"] = {"B": B, "U": U, "T": 17, "us": us_ce, "algorithmic_bytes": bytes_ce,
                                "achieved_GBs": bytes_ce / (us_ce * 1e-6) / 1e9, "hbm_peak_GBs": HBM,
@@ -129,15 +132,15 @@ def main():
 
     # ---- kernel (1) at bank size
     E = synthetic_embeddings(N, D, 2, normalize=False).to(DEV)
-    us_id = events(lambda: ops.aggregate_normalize(E), 100)
+    us_id = graph_us(lambda i: ops.aggregate_normalize(E))
     b_id = N * D * 4 + N * D * 2
     Eb = E.bfloat16()
-    us_id16 = events(lambda: ops.aggregate_normalize(Eb), 100)
+    us_id16 = graph_us(lambda i: ops.aggregate_normalize(Eb))
     b_id16 = N * D * 2 * 2
     rp, col, wt = hier.chain_csr(0.25, lambda n: level_weights("increasing", n).numpy())
     t = lambda a: torch.from_numpy(a).to(DEV)
     rp_d, col_d, w_d = t(rp), t(col), t(wt)
-    us_ch = events(lambda: ops.aggregate_normalize(Eb, rp_d, col_d, w_d), 100)
+    us_ch = graph_us(lambda i: ops.aggregate_normalize(Eb, rp_d, col_d, w_d))
     nnz = int(rp[-1])
     b_ch = 2 * N * D * 2 + 4 * (nnz + N + 1) + 4 * nnz       # compulsory: every source row once + output + CSR
     out["aggregate_normalize_bank"] = {
@@ -146,6 +149,36 @@ def main():
         "identity_bf16_in": {"us": us_id16, "bytes": b_id16, "GBs": b_id16 / us_id16 / 1e3, "frac": b_id16 / us_id16 / 1e3 / HBM},
         "chain_csr_bf16_in": {"us": us_ch, "nnz": nnz, "compulsory_bytes": b_ch, "GBs": b_ch / us_ch / 1e3,
                               "frac": b_ch / us_ch / 1e3 / HBM, "gathered_GBs": (nnz * D * 2 + N * D * 2) / us_ch / 1e3}}
+    # ---- row f1: TOR / POR pass at cfg-2 shape (B=512 rows of dense logits over 21,841 nodes, chain of 12)
+    from hgrnet_b200.evaluate import HierMetrics
+    Bt = 512
+    xt = ops.normalize_rows(synthetic_embeddings(Bt, D, 7, normalize=False).to(DEV))
+    model.update_classifier()
+    dense = ops.logits_dense(xt, model.zsl_weights)
+    hm = HierMetrics(model)
+    us_dense = graph_us(lambda i: ops.logits_dense(xt, model.zsl_weights, out=dense))
+    us_fused = events(lambda: hm.update(dense, target), 50)
+    parents = list(model.c2p[target]) + [target]
+    depth_t = torch.from_numpy(hier.depth).to(DEV)
+
+    def reference_passes():                                   # main.py:153-176 with stock torch ops on the GPU
+        lt = dense[:, model.train_index]
+        _ = model.train_index[lt.topk(1, 1, True, True)[1]]
+        for p in parents:
+            rest = (depth_t != len(model.c2p[p])).nonzero().squeeze(1)
+            lk = dense.detach().clone().index_fill(1, rest, -1)[:, model.train_index]
+            _ = model.train_index[lk.topk(1, 1, True, True)[1]].squeeze()
+    us_ref = events(reference_passes, 5)
+    kb = Bt * N * 4 + N * 5
+    ch_, cl_ = torch.zeros(12, dtype=torch.int32, device=DEV), torch.arange(12, dtype=torch.int32, device=DEV)
+    cnt_ = torch.zeros(3, dtype=torch.int64, device=DEV)
+    us_kernel = graph_us(lambda i: ops.hier_metrics(dense, hm._cols, hm._level, hm.n_levels, hm._first_out, ch_, cl_, cnt_))
+    out["hier_metrics_f1"] = {"B": Bt, "N": N, "L": len(parents), "us_kernel_plus_host_glue": us_fused,
+                              "us_kernel_call": us_kernel, "kernel_bytes": kb, "kernel_GBs": kb / us_kernel / 1e3,
+                              "frac_hbm": kb / us_kernel / 1e3 / HBM, "us_dense_logits": us_dense,
+                              "us_reference_torch_passes_gpu": us_ref,
+                              "speedup_vs_torch_passes": us_ref / (us_fused + us_dense),
+                              "note": "reference = L+1 clone/index_fill/gather/topk passes over [B,N] (without its Python BxL loop)"}
     print(json.dumps(out, indent=1))
 
 
