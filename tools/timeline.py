@@ -16,9 +16,13 @@ def emb(n, d, seed):
 
 names = ["entry", "setup", "first_full", "last_mma_issued", "acc0", "acc1", "acc2", "acc3", "epi0", "epi1", "epi2", "epi3",
          "epi_done", "exit", "release0", "release1", "-", "-", "-", "-", "-", "mma_grant0", "mma_grant1", "mma_grant2"]
-for (B, C, D, impl, tag) in ((512, 21841, 1024, ops.HGR_IMPL_TCGEN05 | _cabi.HGR_IMPL_FLAG_NO_MERGE, "prod"),
-                             (512, 21841, 1024, ops.HGR_IMPL_TCGEN05_NULL, "null"),
-                             (512, 2731, 1024, ops.HGR_IMPL_TCGEN05_NULL, "null-small")):
+NM = ops.HGR_IMPL_TCGEN05 | _cabi.HGR_IMPL_FLAG_NO_MERGE
+CASES = ((512, 21841, 1024, NM, "prod"), (512, 21841, 1024, ops.HGR_IMPL_TCGEN05_NULL, "null"),
+         (512, 2731, 1024, ops.HGR_IMPL_TCGEN05_NULL, "null-small"))
+if len(sys.argv) >= 3:   # python tools/timeline.py B C  -> production and null epilogue at that shape
+    b_, c_ = int(sys.argv[1]), int(sys.argv[2])
+    CASES = ((b_, c_, 1024, NM, "prod"), (b_, c_, 1024, ops.HGR_IMPL_TCGEN05_NULL, "null"))
+for (B, C, D, impl, tag) in CASES:
     banks = [emb(C, D, 2).cuda() for _ in range(5)]
     x = emb(B, D, 1).cuda()
     for i in range(6):
