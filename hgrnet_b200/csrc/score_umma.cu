@@ -318,24 +318,35 @@ int common_setup(const __nv_bfloat16* X, const __nv_bfloat16* bank, int64_t B, i
 }
 
 // ---- list-width policy -------------------------------------------------------------------
-// With `lists` lists per row and bank rows in random order, the true top-K members of a row fall
-// into a given list with probability 1/lists each, so a list of KL < K entries overflows with
-// probability <= C(K, KL) / lists^KL.  Speculate only while the expected number of re-scanned
-// rows per call stays below 1e-3 (a re-scan costs ~1 ms of one warp).
-double overflow_bound(int K, int KL, int lists) {
+// With bank rows in random order, each of a row's true top-K members falls into a given list with probability
+// `share` = the fraction of the row's columns that list streams (the largest one: a worker's chunk of the schedule,
+// halved when two epilogue warps alternate its chunks).  A list of KL < K entries cannot be certified when it
+// receives KL or more of them: probability <= C(K, KL) * share^KL.  A repair re-scans that list's column range on
+// the CUDA cores: share * C * D MACs by one warp at ~20 GMAC/s, against 2 * B * C * D FLOPs at ~1.6 PFLOP/s for the
+// whole call.  Speculate only while (a) fewer than 5e-3 repairs are expected per call (a rare latency hiccup) and
+// (b) their expected time stays below 1 % of the call's ideal time.
+double overflow_bound(int K, int KL, double share) {
   double c = 1.0;
   for (int i = 0; i < KL; ++i) c = c * (K - i) / (i + 1);
-  return c * std::pow(1.0 / lists, KL);
+  return c * std::pow(share, KL);
 }
 
-int pick_list_len(int K, int64_t B, int lists_per_row, bool allow_speculation) {
+double max_list_share(const Sched& s, int wpq) {
+  const double chunk = static_cast<double>((s.T + s.G - 1) / s.G);   // units per worker
+  const double share = chunk / static_cast<double>(s.U);
+  return (share > 1.0 ? 1.0 : share) / wpq;
+}
+
+int pick_list_len(int K, int64_t B, int lists_per_row, double share, bool allow_speculation) {
   const int exact = K <= 8 ? 8 : (K <= 12 ? 12 : (K <= 20 ? 20 : 32));
   if (!allow_speculation) return exact;
   const int cand[4] = {8, 10, 12, 16};
   for (int i = 0; i < 4; ++i) {
     const int kl = cand[i];
     if (kl >= K) break;
-    if (static_cast<double>(B) * lists_per_row * overflow_bound(K, kl, lists_per_row) < 1e-3) return kl;
+    const double repairs = static_cast<double>(B) * lists_per_row * overflow_bound(K, kl, share);
+    const double rel_cost = repairs * share * (1.6e15 / (2.0 * 20e9)) / static_cast<double>(B);
+    if (repairs < 5e-3 && rel_cost < 0.01) return kl;
   }
   return exact;
 }
@@ -376,11 +387,11 @@ int launch_score_topk_umma(const __nv_bfloat16* X, const __nv_bfloat16* bank, co
                      umma_score_workspace_bytes(B, C, K));
   // the pair kernel picks its epilogue arrangement from the list length, which depends on lists/row = P * wpq
   int wpq = variant == 1 ? 1 : kWpq;
-  int KL = pick_list_len(K, B, p.sched.P * wpq, variant == 0 || variant == 4);
+  int KL = pick_list_len(K, B, p.sched.P * wpq, max_list_share(p.sched, wpq), variant == 0 || variant == 4);
   if (pair) {
-    const int kl1 = pick_list_len(K, B, p.sched.P, variant == 0);       // one list per (row, pair)
+    const int kl1 = pick_list_len(K, B, p.sched.P, max_list_share(p.sched, 1), variant == 0);   // one list per (row, pair)
     wpq = pair_wpq(kl1);
-    KL = wpq == 1 ? kl1 : pick_list_len(K, B, p.sched.P * 2, variant == 0);
+    KL = wpq == 1 ? kl1 : pick_list_len(K, B, p.sched.P * 2, max_list_share(p.sched, 2), variant == 0);
   }
   const int lists = p.sched.P * wpq;
   p.KL = KL;

@@ -33,19 +33,86 @@ __device__ __forceinline__ float f32_from_order_key(uint32_t k) {
   return __uint_as_float((k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k);
 }
 
+constexpr int kDoubtWords = 10;  // bit per list, up to 320 lists per row
+
+// Exact repair of a row whose speculative lists could not all be certified.  Only the column ranges of the
+// DOUBTFUL lists are re-scanned on the CUDA cores (1 / lists-per-row of the bank each); the entries of the certified
+// lists are final as they are (whatever such a list dropped is below the old K-th value, which can only rise) and are
+// inserted as candidates.  Lists are visited in ascending column order and SortedList keeps the first of equal
+// values, so the result has the documented (value desc, bank row asc) order.  The list is replicated in every lane.
+// (Arguments by value: handing the kernel's whole MergeArgs to a non-inlined function would copy it to the stack of
+// every thread at kernel entry.)
+struct RepairArgs {
+  const float* part_val;
+  const int32_t* part_idx;
+  int64_t pstride, C;
+  const void* X;
+  const void* bank;
+  Sched sched;
+  int KL, wpq, D8;
+};
+__device__ __noinline__ void repair_row(const RepairArgs a, int64_t row, int lane, int cnt, const uint32_t* dmask,
+                                        SortedList<HGR_TOPK_MAX>& full) {
+  full.init();
+  const int KL = a.KL;
+  const int64_t pstride = a.pstride;
+  const int32_t mt = static_cast<int32_t>(row / a.sched.rows);
+  const int32_t w0 = a.sched.first_cta(mt);
+  const int workers = cnt / a.wpq;
+  for (int wi = 0; wi < workers; ++wi) {
+    bool doubtful = false;
+    for (int m = 0; m < a.wpq; ++m) {
+      const int p = wi * a.wpq + m;
+      doubtful |= (dmask[p >> 5] >> (p & 31)) & 1u;
+    }
+    if (doubtful) {
+      // the worker's chunk of flattened units, clipped to this row tile -> bank rows [c0, c1)
+      const int64_t t0 = static_cast<int64_t>(mt) * a.sched.U;
+      int64_t u0 = a.sched.unit_begin(w0 + wi) - t0, u1 = a.sched.unit_begin(w0 + wi + 1) - t0;
+      u0 = u0 < 0 ? 0 : u0;
+      u1 = u1 > a.sched.U ? a.sched.U : u1;
+      int64_t c0 = u0 * kUnit, c1 = u1 * kUnit;
+      c1 = c1 > a.C ? a.C : c1;
+      if (c0 < c1)
+        scan_row_range<HGR_TOPK_MAX>(reinterpret_cast<const uint4*>(a.X) + row * a.D8,
+                                     reinterpret_cast<const uint4*>(a.bank), c0, c1, a.D8, lane, full);
+    } else {
+      for (int m = 0; m < a.wpq; ++m) {
+        const int p = wi * a.wpq + m;
+        for (int k = 0; k < KL; ++k) {
+          const int64_t g = p * pstride + row * KL + k;
+          const int32_t it = a.part_idx[g];
+          const float v = a.part_val[g];
+          if (it >= 0 && v > full.thr()) full.insert(v, it);
+        }
+      }
+    }
+  }
+}
+
 // Tail shared by both merge kernels.  Lane r holds rank r of the merged list (my_v, my_i = bank row or -1).
-// `doubt`: some lane saw a full speculative list that ends at or above the merged K-th value -> the row is
-// re-scanned exactly on the CUDA cores.  Then: bank row -> node id, scale, store (dense or row-block scatter),
-// Hit@k.
+// `dmask` (per-warp shared memory, one bit per list): full speculative lists that end at or above the merged K-th
+// value -> the row is repaired exactly (repair_row).  Then: bank row -> node id, scale, store (dense or row-block
+// scatter), Hit@k.
 __device__ __forceinline__ void finish_row(const MergeArgs& a, int64_t row, int lane, float my_v, int32_t my_i,
-                                           bool doubt, int* s_hits) {
+                                           bool doubt, const uint32_t* dmask, int cnt, int* s_hits) {
   const int K = a.K;
   if (a.KL < K && __any_sync(0xffffffffu, doubt)) {
     if (lane == 0 && a.rescan_count) atomicAdd(a.rescan_count, 1u);
+    __syncwarp();
     SortedList<HGR_TOPK_MAX> full;
-    full.init();
-    scan_row_range<HGR_TOPK_MAX>(reinterpret_cast<const uint4*>(a.X) + row * a.D8,
-                                 reinterpret_cast<const uint4*>(a.bank), 0, a.C, a.D8, lane, full);
+    RepairArgs ra;
+    ra.part_val = a.part_val;
+    ra.part_idx = a.part_idx;
+    ra.pstride = a.part_stride > 0 ? a.part_stride : a.B * a.KL;
+    ra.C = a.C;
+    ra.X = a.X;
+    ra.bank = a.bank;
+    ra.sched = a.sched;
+    ra.KL = a.KL;
+    ra.wpq = a.wpq;
+    ra.D8 = a.D8;
+    repair_row(ra, row, lane, cnt, dmask, full);
     my_v = -INFINITY;
     my_i = -1;
 #pragma unroll
@@ -90,7 +157,9 @@ __global__ void __launch_bounds__(kMergeWarps * 32)
 topk_merge_kernel(const MergeArgs a) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ int s_hits[HGR_NUM_HITS];
+  __shared__ uint32_t s_dmask[kMergeWarps][kDoubtWords];
   if (threadIdx.x < HGR_NUM_HITS) s_hits[threadIdx.x] = 0;
+  if (threadIdx.x < kMergeWarps * kDoubtWords) (&s_dmask[0][0])[threadIdx.x] = 0;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int KL = a.KL, K = a.K;
@@ -189,10 +258,13 @@ topk_merge_kernel(const MergeArgs a) {
 #pragma unroll
       for (int q = 0; q < kMaxListsPerLane; ++q) {
         const int p = lane + 32 * q;
-        if (p < cnt && li[p * KL + KL - 1] >= 0 && lv[p * KL + KL - 1] >= kth) doubt = true;
+        if (p < cnt && li[p * KL + KL - 1] >= 0 && lv[p * KL + KL - 1] >= kth) {
+          doubt = true;
+          atomicOr(&s_dmask[warp][p >> 5], 1u << (p & 31));
+        }
       }
     }
-    finish_row(a, row, lane, my_v, my_i, doubt, s_hits);
+    finish_row(a, row, lane, my_v, my_i, doubt, s_dmask[warp], cnt, s_hits);
   }
   __syncthreads();
   if (a.hits && threadIdx.x < HGR_NUM_HITS && s_hits[threadIdx.x] != 0)
@@ -212,7 +284,9 @@ __global__ void __launch_bounds__(kMergeWarps * 32)
 topk_select_kernel(const MergeArgs a) {
   __shared__ int s_hits[HGR_NUM_HITS];
   __shared__ unsigned long long s_win[kMergeWarps][32];
+  __shared__ uint32_t s_dmask[kMergeWarps][kDoubtWords];
   if (threadIdx.x < HGR_NUM_HITS) s_hits[threadIdx.x] = 0;
+  if (threadIdx.x < kMergeWarps * kDoubtWords) (&s_dmask[0][0])[threadIdx.x] = 0;
   __syncthreads();
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -281,7 +355,11 @@ topk_select_kernel(const MergeArgs a) {
       for (int s = 0; s < NPL; ++s) {
         sel[s] = key[s] > T;
         above += sel[s];
-        if (tail[s] && key[s] >= T) doubt = true;
+        if (tail[s] && key[s] >= T) {
+          doubt = true;
+          const int p = (lane + 32 * s) / KL;
+          atomicOr(&s_dmask[warp][p >> 5], 1u << (p & 31));
+        }
       }
       above = __reduce_add_sync(0xffffffffu, above);
       for (int need = ksel - above; need > 0; --need) {  // ties at the cut: ascending item
@@ -322,7 +400,7 @@ topk_select_kernel(const MergeArgs a) {
         my_i = static_cast<int32_t>(~static_cast<uint32_t>(w));
       }
     }
-    finish_row(a, row, lane, my_v, my_i, doubt, s_hits);
+    finish_row(a, row, lane, my_v, my_i, doubt, s_dmask[warp], cnt, s_hits);
   }
   __syncthreads();
   if (a.hits && threadIdx.x < HGR_NUM_HITS && s_hits[threadIdx.x] != 0)
@@ -398,8 +476,8 @@ int launch_topk_merge(const MergeArgs& args, cudaStream_t stream) {
     return set_error(HGR_ERR_UNSUPPORTED, "topk merge: %lld lists per row exceed 320", (long long)args.P);
   if (args.K > HGR_TOPK_MAX || args.KL < 1)
     return set_error(HGR_ERR_UNSUPPORTED, "topk merge: K = %d / KL = %d unsupported", args.K, args.KL);
-  if (args.KL < args.K && (args.X == nullptr || args.bank == nullptr))
-    return set_error(HGR_ERR_BAD_ARG, "topk merge: speculative lists need X / bank for the exact re-scan");
+  if (args.KL < args.K && (args.X == nullptr || args.bank == nullptr || !args.use_sched || args.wpq < 1))
+    return set_error(HGR_ERR_BAD_ARG, "topk merge: speculative lists need X / bank / the schedule for the exact repair");
   const int blocks = static_cast<int>((args.B + kMergeWarps - 1) / kMergeWarps);
   const int64_t cand = args.P * args.KL;  // candidates per row (upper bound)
   static const bool force_pway = getenv("HGR_MERGE_PWAY") != nullptr;

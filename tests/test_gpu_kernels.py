@@ -188,11 +188,13 @@ def test_score_topk_implementations_agree_at_cfg2_size():
     assert h1.tolist() == hits_from_idx(i1, targets)
 
 
-def test_speculative_lists_are_certified_or_rescanned_exactly():
-    """At cfg 2 size a row is split over 74 lists, so the production kernel keeps SPECULATIVE 8-entry lists.
-    (a) random bank order: every row certifies, no re-scan; (b) an adversarial bank whose best classes sit in
-    adjacent rows overflows single lists: the merge must detect it and re-scan those rows exactly."""
-    B, C, D, K = 512, 21841, 1024, 20
+@pytest.mark.parametrize("B,C", [(512, 21841), (4096, 5461)])
+def test_speculative_lists_are_certified_or_rescanned_exactly(B, C):
+    """At cfg 2 size a row is split over 37 lists, so the production kernel keeps SPECULATIVE 8-entry lists (16-entry
+    lists for the 5-6 lists per row of a 4096-image batch).  (a) random bank order: every row certifies, nothing is
+    repaired; (b) an adversarial bank whose best classes sit in adjacent rows overflows single lists: the merge must
+    detect it and repair those rows exactly (re-scan of the doubtful lists' column ranges)."""
+    D, K = 1024, 20
     x, w = _emb(B, D, 51), _emb(C, D, 52)
     xn = ops.normalize_rows(x.to(DEV))
     v0, i0 = ops.score_topk(xn, w.to(DEV).bfloat16(), K=K, impl=IMPLS["tcgen05"])
@@ -204,15 +206,16 @@ def test_speculative_lists_are_certified_or_rescanned_exactly():
     mean_dir = x.mean(0)
     mean_dir = mean_dir / mean_dir.norm()
     noise = _emb(40, D, 53)
-    w2[5000:5040] = ((mean_dir[None, :] * 3 + noise) / (mean_dir[None, :] * 3 + noise).norm(dim=-1, keepdim=True)
-                     ).to(torch.bfloat16).float()
+    r0 = C // 4 + 37
+    w2[r0:r0 + 40] = ((mean_dir[None, :] * 3 + noise) / (mean_dir[None, :] * 3 + noise).norm(dim=-1, keepdim=True)
+                      ).to(torch.bfloat16).float()
     v2, i2 = ops.score_topk(xn, w2.to(DEV).bfloat16(), K=K, impl=IMPLS["tcgen05"])
     rescans = ops.last_rescan_count(DEV)
     assert rescans > 0, "the adversarial bank should overflow at least one speculative list"
     logits = xn.float().cpu() @ w2.T
     compare_topk(v2, i2, logits, torch.arange(C), K)
     v3, i3 = ops.score_topk(xn, w2.to(DEV).bfloat16(), K=K, impl=IMPLS["tcgen05_exact"])
-    assert (i2 != i3).any(1).sum() <= 2                         # re-scanned rows use CUDA-core sums: near-ties may swap
+    assert (i2 != i3).any(1).sum() <= max(2, B // 256)          # repaired rows use CUDA-core sums: near-ties may swap
 
 
 def test_score_topk_empty_and_bad_args():
