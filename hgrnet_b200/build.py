@@ -54,7 +54,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     def compile_one(src):
         obj = os.path.join(LIBDIR, src.replace(".cu", ".o"))
-        cmd = [nvcc, *ARCH, *NVCC_FLAGS, "-I", INCLUDE, "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc, *ARCH, *NVCC_FLAGS, *os.environ.get("HGR_NVCC_EXTRA", "").split(), "-I", INCLUDE, "-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         logs[src] = r.stdout + r.stderr
         if r.returncode != 0:

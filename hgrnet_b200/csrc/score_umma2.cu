@@ -33,6 +33,19 @@ __host__ __device__ constexpr int defer_depth(int wpq) { return wpq == 1 ? kDefe
 // ~2 us of main loop at cfg 2, and leaving room for co-resident small kernels bought nothing).
 constexpr int kDeferStages = kDeferDepth > 64 ? 4 : 5;
 constexpr int kOtherStages = 6;
+// Run-time stage count (Params::stages).  Large batches use ONE stage less than fits: their main loop does not
+// notice (measured at B = 4096: 82.9 / 56.1 / 40.1 us either way), and the 32 KB left free let a neighbouring
+// stream's small kernels (normalise, merge, flags) share the SM with a resident GEMM CTA instead of waiting for it
+// (class-sharded pipeline: -5 % per step).  At cfg 2 (B = 512) the fifth stage is worth 0.7 us, so it stays.
+inline int pair_stages(int epi, int64_t B) {
+  static const int forced = [] {
+    const char* e = getenv("HGR_STAGES");
+    return e ? atoi(e) : 0;
+  }();
+  const int most = epi == kEpiTopkDefer ? kDeferStages : kOtherStages;
+  if (forced >= 2 && forced <= most) return forced;
+  return (epi == kEpiTopkDefer && B >= 2048) ? most - 1 : most;
+}
 constexpr int kDenseTileFloats = 32 * 33;                  // dense epilogue: one padded 32x32 transpose tile per warp
 constexpr int kPairBBytes = (kSubN / 2) * kBlockK * 2;     // 16 KB: half of the bank sub-tile
 constexpr int kPairStageBytes = kABytes + kPairBBytes;     // 32 KB
@@ -54,7 +67,7 @@ score_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
   constexpr int kQueueBytes = EPI == kEpiTopkQueue ? kChunk * kEpiThreads * 4
                             : EPI == kEpiTopkDefer ? (kQueueDepth + 1) * kEpiThreads * 8
                             : EPI == kEpiDense ? (kEpiThreads / 32) * kDenseTileFloats * 4 : 0;
-  constexpr int kPairStages = EPI == kEpiTopkDefer ? kDeferStages : kOtherStages;
+  const int kPairStages = p.stages;   // <= kPairStagesMax, chosen by the launcher (pair_stages)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* stage_base = smem;
@@ -332,10 +345,16 @@ int launch_one(const CUtensorMap& mx, const CUtensorMap& mb, const Params& p, cu
   constexpr size_t queue = EPI == kEpiTopkQueue ? static_cast<size_t>(kChunk) * 128 * WPQ * 4
                          : EPI == kEpiTopkDefer ? static_cast<size_t>(defer_depth(WPQ) + 1) * 128 * WPQ * 8
                          : EPI == kEpiDense ? static_cast<size_t>(4 * WPQ) * kDenseTileFloats * 4 : 0;
-  const size_t smem = 1024 + static_cast<size_t>(EPI == kEpiTopkDefer ? kDeferStages : kOtherStages) * kPairStageBytes + queue + sizeof(PairCtl);
+  Params pp = p;
+  pp.stages = pair_stages(EPI, p.B);
+  const size_t smem = 1024 + static_cast<size_t>(pp.stages) * kPairStageBytes + queue + sizeof(PairCtl);
   auto kern = score_umma_pair_kernel<EPI, KL, WPQ>;
-  HGR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  kern<<<2 * p.sched.G, threads, smem, stream>>>(mx, mb, p);
+  // the opt-in limit is a per-function attribute: always ask for the deepest ring so that concurrent callers with
+  // different stage counts cannot lower it under each other
+  const size_t smem_max = 1024 + static_cast<size_t>(EPI == kEpiTopkDefer ? kDeferStages : kOtherStages) * kPairStageBytes +
+                          queue + sizeof(PairCtl);
+  HGR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_max)));
+  kern<<<2 * p.sched.G, threads, smem, stream>>>(mx, mb, pp);
   HGR_CHECK_LAUNCH();
   return HGR_OK;
 }

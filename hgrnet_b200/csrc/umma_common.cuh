@@ -89,6 +89,7 @@ struct Params {
   unsigned int* stats; // [0] = rows re-scanned by the merge kernel of this call (reset here)
   unsigned long long* timeline;  // optional [CTA][24] %globaltimer stamps (HGR_TIMELINE=1), else nullptr
   int rem_first;       // sub-tile order inside a segment: remainder first (1) or last (0)
+  int stages;          // operand ring depth of the CTA-pair kernel (set by its launcher)
 };
 
 constexpr int kTimelineSlots = 24;
