@@ -429,7 +429,7 @@ __global__ void peer_signal_kernel(const PeerFlags flags, int n, uint32_t* seq) 
   }
 }
 
-__global__ void peer_wait_kernel(const uint32_t* flags, int n, uint32_t* seq) {
+__global__ void peer_wait_kernel(const uint32_t* flags, int n, uint32_t* seq, unsigned long long timeout_ns) {
   __shared__ uint32_t s_v;
   if (threadIdx.x == 0) s_v = ++(*seq);
   __syncthreads();
@@ -443,7 +443,7 @@ __global__ void peer_wait_kernel(const uint32_t* flags, int n, uint32_t* seq) {
       if (static_cast<int32_t>(got - want) >= 0) break;
       unsigned long long t1;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-      if (t1 - t0 > 4000000000ull) {  // 4 s: a peer died or the schedules diverged -- fail loudly, never hang the GPU
+      if (t1 - t0 > timeout_ns) {  // a peer died or the schedules diverged -- fail loudly, never hang the GPU
         printf("hgr peer_wait: producer %d stuck at %u, waiting for %u\n", static_cast<int>(threadIdx.x), got, want);
         __trap();
       }
@@ -465,7 +465,14 @@ int launch_peer_signal(uint32_t* const* flags, int n, uint32_t* seq, cudaStream_
 
 int launch_peer_wait(const uint32_t* flags, int n, uint32_t* seq, cudaStream_t stream) {
   if (n < 1 || n > kMaxScatterBlocks) return set_error(HGR_ERR_BAD_ARG, "peer wait: %d ranks outside [1, %d]", n, kMaxScatterBlocks);
-  peer_wait_kernel<<<1, 32, 0, stream>>>(flags, n, seq);
+  // how long a consumer waits for the slowest producer before it traps: 10 s unless HGR_PEER_TIMEOUT_MS says otherwise
+  // (a rank whose host stalls longer than this between two graph launches would take the job down)
+  static const unsigned long long timeout_ns = [] {
+    const char* e = getenv("HGR_PEER_TIMEOUT_MS");
+    const long long ms = e ? atoll(e) : 10000;
+    return static_cast<unsigned long long>(ms > 0 ? ms : 10000) * 1000000ull;
+  }();
+  peer_wait_kernel<<<1, 32, 0, stream>>>(flags, n, seq, timeout_ns);
   HGR_CHECK_LAUNCH();
   return HGR_OK;
 }

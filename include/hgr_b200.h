@@ -141,7 +141,8 @@ int hgr_topk_merge(const float* part_val, const int32_t* part_idx, int64_t P, in
  * hgr_peer_signal                  after the scatter: publish this rank's next sequence number (device counter
  *                                  *seq, incremented by the kernel) to flags[g] (one word on every rank g).
  * hgr_peer_wait                    before the merge: increment the consumer's own device counter *seq and spin
- *                                  until all n local flag words have reached it.  Traps (never hangs) after 4 s.
+ *                                  until all n local flag words have reached it.  Traps (never hangs) after 10 s
+ *                                  (HGR_PEER_TIMEOUT_MS overrides).
  * Both counters advance once per launch, so a signal/wait pair can live in a replayed CUDA graph.
  */
 #define HGR_IPC_HANDLE_BYTES 64

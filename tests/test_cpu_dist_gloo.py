@@ -77,3 +77,25 @@ def test_shard_bounds_cover_the_bank_once():
         assert all(b[i][1] == b[i + 1][0] for i in range(G - 1))
         assert all(lo <= hi for lo, hi in b)
     assert shard_bounds(21841, 8)[0] == (0, 2731) and shard_bounds(21841, 8)[7] == (19117, 21841)
+
+
+def test_exchange_layout_and_row_blocks():
+    """Host arithmetic of the peer-memory exchange: regions do not overlap, feature slots are 256-byte aligned, row
+    blocks cover the batch exactly once (ragged last block, ranks without rows)."""
+    from hgrnet_b200.dist import X_SLOTS, exchange_layout
+    for B, K, world, slots, D in [(4096, 20, 8, 4, 1024), (130, 20, 3, 4, 256), (5, 20, 8, 4, 64), (512, 5, 1, 2, 0)]:
+        lay = exchange_layout(B, K, world, slots, D)
+        rows = lay["block_rows"]
+        assert rows * world >= B and (rows - 1) * world < B       # smallest block size that covers the batch
+        assert lay["part_bytes"] == rows * K * 4 and lay["slot_bytes"] == 2 * world * lay["part_bytes"]
+        assert lay["header"] >= 64 + 4 * 16                      # two flag sets of up to 16 ranks
+        assert lay["x_off"] % 256 == 0 and lay["x_off"] >= lay["header"] + slots * lay["slot_bytes"]
+        assert lay["total"] == lay["x_off"] + (X_SLOTS * lay["x_bytes"] if D else 0)
+        if D:
+            assert lay["x_bytes"] % 256 == 0 and lay["x_bytes"] >= B * D * 2
+        covered = []
+        for r in range(world):
+            lo = min(B, r * rows)
+            hi = min(B, lo + rows)
+            covered.extend(range(lo, hi))
+        assert covered == list(range(B))
