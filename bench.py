@@ -301,6 +301,12 @@ def run_ours(args):
             ses.dev_feats[s_].copy_(feats_dev[s_ % n_feat])
             ses.dev_labels[s_].copy_(labels_dev[s_ % n_feat])
         multi_graph = ses.graph is not None
+        # our kernels per batch on this path (one eager issue of the 8-batch pipeline, every rank alike)
+        l0 = _cabi.launch_count()
+        with torch.cuda.stream(ses.stream):
+            ses._issue()
+        torch.cuda.synchronize()
+        kernels_per_step = (_cabi.launch_count() - l0) // G_STEPS
 
         def step_resident(i):                    # one replay = G_STEPS batches; issue it on every G_STEPS-th step
             if i % G_STEPS == 0:
