@@ -106,3 +106,35 @@ def test_peer_wait_passes_only_after_all_signals():
         torch.cuda.synchronize()
         for b in bufs:
             ops.peer_free(b)
+
+
+@pytest.mark.parametrize("host_io", [False, True])
+def test_sharded_eval_stream_single_rank(host_io):
+    """The graph-captured class-sharded evaluator on ONE rank (its own exchange buffer, 4 channels): same lists and
+    hit counters as plain score_topk; host-fed mode reads features / labels from pinned memory and copies the
+    counters back after every batch."""
+    from hgrnet_b200 import ops
+    from hgrnet_b200.dist import ShardedEvalStream
+    dev = torch.device("cuda", 0)
+    B, C, D, K = 300, 5000, 512, 20
+    w = _emb(C, D, 2).to(dev)
+    feats = [torch.randn(B, D, generator=torch.Generator().manual_seed(10 + s)) for s in range(8)]
+    labels = [torch.randint(0, C, (B,), generator=torch.Generator().manual_seed(30 + s)).int() for s in range(8)]
+    ses = ShardedEvalStream(w, 0, batch=B, K=K, steps=8, host_io=host_io)
+    for s in range(8):
+        if host_io:
+            ses.host_feats[s].copy_(feats[s])
+            ses.host_labels[s].copy_(labels[s])
+        else:
+            ses.dev_feats[s].copy_(feats[s])
+            ses.dev_labels[s].copy_(labels[s])
+    ses.run()
+    ses.run()
+    torch.cuda.synchronize()
+    ref_hits = ops.new_hits(dev)
+    for s in range(8):
+        rv, ri = ops.score_topk(ops.normalize_rows(feats[s].to(dev)), w, targets=labels[s].to(dev), K=K, hits=ref_hits)
+        assert torch.equal(ses.idx[s], ri) and torch.equal(ses.val[s], rv)
+    assert ses.all_reduce_hits().tolist() == [2 * h for h in ref_hits.tolist()]
+    if host_io:
+        assert torch.equal(torch.stack(ses.host_hits).max(dim=0).values, ses.hits.cpu())
