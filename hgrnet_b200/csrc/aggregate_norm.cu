@@ -110,22 +110,41 @@ aggregate_normalize_kernel(const TIn* __restrict__ E, int D8, const int32_t* __r
 #pragma unroll
       for (int e = 0; e < 8; ++e) acc[v][e] = 0.f;
 
-    for (int32_t j = beg; j < end; ++j) {
-      const int32_t c = rowptr ? col[j] : j;
-      const float wj = (rowptr && w) ? w[j] : 1.f;
-      const TIn* srcp = E + static_cast<int64_t>(c) * D;
-      float f[MAXV][8];
+    // The row's column ids / weights are fetched by the whole warp in one coalesced load (32 entries at a time)
+    // and broadcast by shuffle -- no per-entry dependent scalar load -- and TWO source rows are in flight per step:
+    // with ~2 entries per row (ancestor chains) a row costs one gather round trip instead of a chain of them.
+    // (Also tried: prefetching the next row's pointers / ids one row ahead -- no gain, the gather itself dominates.)
+    const int32_t n = end - beg;
+    int32_t myc = src;
+    float myw = 1.f;
+    for (int32_t j0 = 0; j0 < n; j0 += 2) {
+      if ((j0 & 31) == 0 && rowptr) {
+        const int32_t j = beg + j0 + lane;
+        myc = j < end ? __ldg(col + j) : 0;
+        myw = (j < end && w) ? __ldg(w + j) : 1.f;
+      }
+      const bool two = j0 + 1 < n;
+      const int32_t c0 = __shfl_sync(0xffffffffu, myc, j0 & 31);
+      const int32_t c1 = __shfl_sync(0xffffffffu, myc, (j0 + 1) & 31);
+      const float w0 = __shfl_sync(0xffffffffu, myw, j0 & 31);
+      const float w1 = two ? __shfl_sync(0xffffffffu, myw, (j0 + 1) & 31) : 0.f;
+      const TIn* s0 = E + static_cast<int64_t>(c0) * D;
+      const TIn* s1 = E + static_cast<int64_t>(two ? c1 : c0) * D;
+      float f0[MAXV][8], f1[MAXV][8];
 #pragma unroll
-      for (int v = 0; v < MAXV; ++v) {  // issue all loads of this source row first
+      for (int v = 0; v < MAXV; ++v) {  // issue all loads of both source rows first
         const int idx = lane + 32 * v;
-        if (idx < D8) Vec8<TIn>::load(srcp + idx * 8, f[v]);
+        if (idx < D8) {
+          Vec8<TIn>::load(s0 + idx * 8, f0[v]);
+          Vec8<TIn>::load(s1 + idx * 8, f1[v]);
+        }
       }
 #pragma unroll
       for (int v = 0; v < MAXV; ++v) {
         const int idx = lane + 32 * v;
         if (idx < D8) {
 #pragma unroll
-          for (int e = 0; e < 8; ++e) acc[v][e] = fmaf(wj, f[v][e], acc[v][e]);
+          for (int e = 0; e < 8; ++e) acc[v][e] = fmaf(w1, f1[v][e], fmaf(w0, f0[v][e], acc[v][e]));
         }
       }
     }
@@ -333,9 +352,16 @@ int dispatch(const void* E, int64_t D, const int32_t* rowptr, const int32_t* col
     HGR_CHECK_LAUNCH();
     return HGR_OK;
   }
-#define HGR_AGG_LAUNCH(MAXV)                                                                           \
-  aggregate_normalize_kernel<TIn, TOut, MAXV><<<blocks, threads, 0, stream>>>(e, D8, rowptr, col, w,  \
-                                                                               row_map, n_out, o, out_norm)
+  // one wave: as many CTAs as are resident at once (register-limited), each warp strides over the rows
+#define HGR_AGG_LAUNCH(MAXV)                                                                                      \
+  do {                                                                                                            \
+    int per_sm = 1;                                                                                               \
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, aggregate_normalize_kernel<TIn, TOut, MAXV>, threads, 0); \
+    const int64_t wave = static_cast<int64_t>(num_sms()) * (per_sm < 1 ? 1 : per_sm);                              \
+    const int nblk = static_cast<int>(want < wave ? (want < 1 ? 1 : want) : wave);                                \
+    aggregate_normalize_kernel<TIn, TOut, MAXV><<<nblk, threads, 0, stream>>>(e, D8, rowptr, col, w, row_map,     \
+                                                                              n_out, o, out_norm);                \
+  } while (0)
   if (D8 <= 32) HGR_AGG_LAUNCH(1);
   else if (D8 <= 64) HGR_AGG_LAUNCH(2);
   else if (D8 <= 96) HGR_AGG_LAUNCH(3);
