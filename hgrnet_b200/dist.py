@@ -294,12 +294,18 @@ class ShardedEvalStream:
                 # feature ingest: this rank copies only ITS rows (and their labels) from pinned host memory; the
                 # normalised rows reach the other ranks over NVLink (PeerExchange.ingest); Hit@k counters go back
                 # to the host after every batch
-                pin = dict(pin_memory=True)
-                self.host_feats = [torch.zeros((n_my, D), dtype=feat_dtype, **pin) for _ in range(steps)]
-                self.host_labels = [torch.zeros((n_my,), dtype=torch.int32, **pin) for _ in range(steps)]
-                self.host_hits = [torch.zeros((ops.HGR_NUM_HITS,), dtype=torch.int64, **pin) for _ in range(steps)]
-                self.dev_feats = [torch.empty((n_my, D), dtype=feat_dtype, device=self.device) for _ in range(steps)]
-                self.dev_labels = [torch.zeros((n_my,), dtype=torch.int32, device=self.device) for _ in range(steps)]
+                # (features + labels of a batch share one staging buffer per side: a single DMA per batch)
+                fbytes = n_my * D * torch.empty((), dtype=feat_dtype).element_size()
+
+                def views(pack):
+                    return pack[:fbytes].view(feat_dtype).view(n_my, D), pack[fbytes:].view(torch.int32)
+
+                self.host_pack = [torch.zeros(fbytes + n_my * 4, dtype=torch.uint8, pin_memory=True) for _ in range(steps)]
+                self.dev_pack = [torch.zeros(fbytes + n_my * 4, dtype=torch.uint8, device=self.device) for _ in range(steps)]
+                self.host_feats, self.host_labels = map(list, zip(*[views(p) for p in self.host_pack]))
+                self.dev_feats, self.dev_labels = map(list, zip(*[views(p) for p in self.dev_pack]))
+                self.host_hits = [torch.zeros((ops.HGR_NUM_HITS,), dtype=torch.int64, pin_memory=True)
+                                  for _ in range(steps)]
             if self.world > 1:
                 dist.barrier(group=group)          # every buffer is mapped everywhere before the first store
         else:
@@ -329,8 +335,7 @@ class ShardedEvalStream:
         bank = self.banks[s % len(self.banks)]
         if self.host_io:
             px, j = self.pxs[s % self.channels], s // self.channels
-            self.dev_feats[s].copy_(self.host_feats[s], non_blocking=True)
-            self.dev_labels[s].copy_(self.host_labels[s], non_blocking=True)
+            self.dev_pack[s].copy_(self.host_pack[s], non_blocking=True)
             x = px.ingest(self.dev_feats[s], j % X_SLOTS)
             px.scatter(x, bank, self.id_base, j % self.slots)
             return None

@@ -41,12 +41,20 @@ class EvalStream:
         self.col_id, self.id_base = col_id, id_base
         self.slots = slots
         self.host_io = host_io
+        # features and labels of a slot share ONE staging buffer on each side, so a batch is a single DMA (a second,
+        # 2 KB copy costs a descriptor's fixed latency on the same copy engine that carries the 2 MB of features)
+        fbytes = batch * D * torch.empty((), dtype=feat_dtype).element_size()
+        nbytes = fbytes + batch * 4
+
+        def views(pack):
+            return pack[:fbytes].view(feat_dtype).view(batch, D), pack[fbytes:].view(torch.int32)
+
+        self.dev_pack = [torch.zeros(nbytes, dtype=torch.uint8, device=self.device) for _ in range(slots)]
+        self.dev_feats, self.dev_labels = map(list, zip(*[views(p) for p in self.dev_pack]))
         if host_io:
-            self.host_feats = [torch.empty((batch, D), dtype=feat_dtype).pin_memory() for _ in range(slots)]
-            self.host_labels = [torch.zeros((batch,), dtype=torch.int32).pin_memory() for _ in range(slots)]
+            self.host_pack = [torch.zeros(nbytes, dtype=torch.uint8).pin_memory() for _ in range(slots)]
+            self.host_feats, self.host_labels = map(list, zip(*[views(p) for p in self.host_pack]))
             self.host_hits = torch.zeros(ops.HGR_NUM_HITS, dtype=torch.int64).pin_memory()
-        self.dev_feats = [torch.empty((batch, D), dtype=feat_dtype, device=self.device) for _ in range(slots)]
-        self.dev_labels = [torch.zeros((batch,), dtype=torch.int32, device=self.device) for _ in range(slots)]
         self.hits = ops.new_hits(self.device)
         self.val = [None] * slots
         self.idx = [None] * slots
@@ -60,8 +68,7 @@ class EvalStream:
 
     def _body(self, s: int):
         if self.host_io:
-            self.dev_feats[s].copy_(self.host_feats[s], non_blocking=True)
-            self.dev_labels[s].copy_(self.host_labels[s], non_blocking=True)
+            self.dev_pack[s].copy_(self.host_pack[s], non_blocking=True)
         x = ops.normalize_rows(self.dev_feats[s])                                    # clip_tree.py:330
         self.val[s], self.idx[s] = ops.score_topk(x, self.banks[s % len(self.banks)], col_id=self.col_id,
                                                   id_base=self.id_base, targets=self.dev_labels[s], K=self.K,
