@@ -106,6 +106,14 @@ def _cpu_steps(wl, steps, warmup, seed=0):
     import torch
     from oracle import hgr_oracle as orc
     from hgrnet_b200.synthetic import synthetic_embeddings
+    # all the host threads the box offers: torchrun exports OMP_NUM_THREADS=1 to every rank, which would turn the
+    # CPU arm into a single-core run
+    try:
+        ncpu = len(os.sched_getaffinity(0))
+    except AttributeError:
+        ncpu = os.cpu_count() or 1
+    if torch.get_num_threads() < ncpu:
+        torch.set_num_threads(ncpu)
     B, C, D = wl["B"], wl["C"], wl["D"]
     bank = orc.normalize_rows(synthetic_embeddings(C, D, seed + 1))
     test_index = torch.arange(C)
