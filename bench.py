@@ -456,7 +456,7 @@ def run_ours(args):
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s",
                          "frac": achieved / tf_peak,
                          # DRAM bytes of one launch from the committed `ncu --set full` capture of this workload
-                         # (profiles/r01_ncu_full_summary.md); compulsory bytes = bank + features + lists
+                         # (profiles/r01c_ncu_summary.md); compulsory bytes = bank + features + lists
                          "traffic": NCU_DRAM_BYTES.get((B, Cs, D)),
                          "traffic_unit": "bytes/launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)",
                          "compulsory_bytes": Cs * D * 2 + B * D * 2,
@@ -477,7 +477,7 @@ def run_ours(args):
 
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel, keyed by (B, C_local, D);
 # from the ncu --set full captures summarised under profiles/ (a profiler cannot run inside the timed region)
-NCU_DRAM_BYTES = {(512, 21841, 1024): 45825792 + 50688}
+NCU_DRAM_BYTES = {(512, 21841, 1024): 45838336 + 82432}
 
 
 def main():
