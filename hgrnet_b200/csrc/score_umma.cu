@@ -295,8 +295,48 @@ int usable_sms() {
   return n < 2 ? 2 : n;
 }
 
+// Rough cost of the slowest worker of a schedule, in operand columns streamed through shared memory: every
+// sub-tile re-streams the A operand (one row tile = 256 "columns" worth of bytes) next to its own bank rows, and
+// every segment (row tile x worker intersection) starts a fresh list (floor pass, warm-up inserts, list write-out).
+static double sched_cost(const Sched& s) {
+  constexpr double kSegmentOverhead = 400.0;   // ~3-4 us of floor pass + warm-up inserts + list write-out
+  double worst = 0.0;
+  for (int32_t w = 0; w < s.G; ++w) {
+    int64_t u = s.unit_begin(w);
+    const int64_t u_end = s.unit_begin(w + 1);
+    double cost = 0.0;
+    while (u < u_end) {
+      const int64_t tile_end = (u / s.U + 1) * s.U;
+      const int64_t e = u_end < tile_end ? u_end : tile_end;
+      const int64_t cols = (e - u) * kUnit;
+      cost += static_cast<double>((cols + kSubN - 1) / kSubN) * 256.0 + static_cast<double>(cols) + kSegmentOverhead;
+      u = e;
+    }
+    worst = cost > worst ? cost : worst;
+  }
+  return worst;
+}
+
+// Workers: all CTA pairs, unless a slightly smaller count that is a multiple of the row-tile count wins -- then no
+// chunk straddles a row tile (one list per worker, no ragged sub-tiles at both ends; measured at B = 4096:
+// 64 aligned pairs beat 74 for every bank size, e.g. 33.6 vs 39.7 us at C = 2,731).
 Sched pick_sched(int64_t B, int64_t C, bool pair) {
-  return pair ? make_sched(B, C, usable_sms() / 2, 2 * kTileM) : make_sched(B, C, usable_sms(), kTileM);
+  if (!pair) return make_sched(B, C, usable_sms(), kTileM);
+  const int most = usable_sms() / 2;
+  Sched best = make_sched(B, C, most, 2 * kTileM);
+  static const bool no_align = getenv("HGR_NO_ALIGN") != nullptr;
+  if (!no_align && best.MT > 1 && best.MT <= most && best.G == most) {
+    const int aligned = most / best.MT * best.MT;
+    if (aligned != most && aligned * 10 >= most * 8) {
+      const Sched alt = make_sched(B, C, aligned, 2 * kTileM);
+      // only for short streams (<= 3072 columns per worker): there the per-segment costs decide; on long streams the
+      // fewer, larger lists of the aligned split sit closer to the speculation limit (an expected repair of a
+      // 5,000-column range costs more than the alignment saves -- measured at cfg 5)
+      const int64_t cols_per_worker = (alt.T + alt.G - 1) / alt.G * kUnit;
+      if (cols_per_worker <= 3072 && sched_cost(alt) < sched_cost(best)) best = alt;
+    }
+  }
+  return best;
 }
 
 int common_setup(const __nv_bfloat16* X, const __nv_bfloat16* bank, int64_t B, int64_t C, int64_t D, bool pair,
@@ -323,8 +363,10 @@ int common_setup(const __nv_bfloat16* X, const __nv_bfloat16* bank, int64_t B, i
 // halved when two epilogue warps alternate its chunks).  A list of KL < K entries cannot be certified when it
 // receives KL or more of them: probability <= C(K, KL) * share^KL.  A repair re-scans that list's column range on
 // the CUDA cores: share * C * D MACs by one warp at ~20 GMAC/s, against 2 * B * C * D FLOPs at ~1.6 PFLOP/s for the
-// whole call.  Speculate only while (a) fewer than 5e-3 repairs are expected per call (a rare latency hiccup) and
-// (b) their expected time stays below 1 % of the call's ideal time.
+// whole call (the repair streams one bank row per lane, simt_row.cuh).  Speculate only while (a) fewer than 3e-2
+// repairs are expected per call (a rare latency hiccup) and (b) their expected time stays below 6 % of the call's
+// ideal time (four aligned lists per row of a 4096-image batch sit just inside: 2e-2 repairs of ~45 us per call at
+// the N = 8 shard, against 6 us gained per call by 16-entry lists).
 double overflow_bound(int K, int KL, double share) {
   double c = 1.0;
   for (int i = 0; i < KL; ++i) c = c * (K - i) / (i + 1);
@@ -346,7 +388,9 @@ int pick_list_len(int K, int64_t B, int lists_per_row, double share, bool allow_
     if (kl >= K) break;
     const double repairs = static_cast<double>(B) * lists_per_row * overflow_bound(K, kl, share);
     const double rel_cost = repairs * share * (1.6e15 / (2.0 * 20e9)) / static_cast<double>(B);
-    if (repairs < 5e-3 && rel_cost < 0.01) return kl;
+    static const double max_repairs = getenv("HGR_SPEC_REPAIRS") ? atof(getenv("HGR_SPEC_REPAIRS")) : 3e-2;
+    static const double max_cost = getenv("HGR_SPEC_COST") ? atof(getenv("HGR_SPEC_COST")) : 0.06;
+    if (repairs < max_repairs && rel_cost < max_cost) return kl;
   }
   return exact;
 }

@@ -74,8 +74,8 @@ __device__ __noinline__ void repair_row(const RepairArgs a, int64_t row, int lan
       int64_t c0 = u0 * kUnit, c1 = u1 * kUnit;
       c1 = c1 > a.C ? a.C : c1;
       if (c0 < c1)
-        scan_row_range<HGR_TOPK_MAX>(reinterpret_cast<const uint4*>(a.X) + row * a.D8,
-                                     reinterpret_cast<const uint4*>(a.bank), c0, c1, a.D8, lane, full);
+        scan_row_range_lanes<HGR_TOPK_MAX>(reinterpret_cast<const uint4*>(a.X) + row * a.D8,
+                                           reinterpret_cast<const uint4*>(a.bank), c0, c1, a.D8, lane, full);
     } else {
       for (int m = 0; m < a.wpq; ++m) {
         const int p = wi * a.wpq + m;
