@@ -361,12 +361,9 @@ int common_setup(const __nv_bfloat16* X, const __nv_bfloat16* bank, int64_t B, i
 // With bank rows in random order, each of a row's true top-K members falls into a given list with probability
 // `share` = the fraction of the row's columns that list streams (the largest one: a worker's chunk of the schedule,
 // halved when two epilogue warps alternate its chunks).  A list of KL < K entries cannot be certified when it
-// receives KL or more of them: probability <= C(K, KL) * share^KL.  A repair re-scans that list's column range on
-// the CUDA cores: share * C * D MACs by one warp at ~20 GMAC/s, against 2 * B * C * D FLOPs at ~1.6 PFLOP/s for the
-// whole call (the repair streams one bank row per lane, simt_row.cuh).  Speculate only while (a) fewer than 3e-2
-// repairs are expected per call (a rare latency hiccup) and (b) their expected time stays below 6 % of the call's
-// ideal time (four aligned lists per row of a 4096-image batch sit just inside: 2e-2 repairs of ~45 us per call at
-// the N = 8 shard, against 6 us gained per call by 16-entry lists).
+// receives KL or more of them: probability <= C(K, KL) * share^KL.  A repair re-scans that list's column range with
+// ONE warp of the merge kernel: measured ~0.6 us per bank row of 1024 elements (a 590-column range of cfg 2:
+// 0.36 ms; a 4,700-column range of cfg 5: 2.8 ms), and the whole call waits for it.
 double overflow_bound(int K, int KL, double share) {
   double c = 1.0;
   for (int i = 0; i < KL; ++i) c = c * (K - i) / (i + 1);
@@ -379,7 +376,12 @@ double max_list_share(const Sched& s, int wpq) {
   return (share > 1.0 ? 1.0 : share) / wpq;
 }
 
-int pick_list_len(int K, int64_t B, int lists_per_row, double share, bool allow_speculation) {
+// Speculate only while the EXPECTED repair time per call stays below 1.5 % of the call's estimated duration (main
+// loop at 60 % of the bf16 peak).  cfg 2 (37 lists of 590 columns per row, KL = 8): 7e-4 repairs x 0.36 ms = 0.25 us
+// of 24 us -- accepted, and worth it (exact 20-entry lists cost 55 us there).  B = 4096 (4-6 lists per row): 16-entry
+// lists would save ~6 us per call but cost 1-8 us in expected repairs -- rejected, exact lists run in the same
+// deferred-insert mode.
+int pick_list_len(int K, int64_t B, int64_t C, int64_t D, int lists_per_row, double share, bool allow_speculation) {
   const int exact = K <= 8 ? 8 : (K <= 12 ? 12 : (K <= 20 ? 20 : 32));
   if (!allow_speculation) return exact;
   const int cand[4] = {8, 10, 12, 16};
@@ -387,10 +389,10 @@ int pick_list_len(int K, int64_t B, int lists_per_row, double share, bool allow_
     const int kl = cand[i];
     if (kl >= K) break;
     const double repairs = static_cast<double>(B) * lists_per_row * overflow_bound(K, kl, share);
-    const double rel_cost = repairs * share * (1.6e15 / (2.0 * 20e9)) / static_cast<double>(B);
-    static const double max_repairs = getenv("HGR_SPEC_REPAIRS") ? atof(getenv("HGR_SPEC_REPAIRS")) : 3e-2;
-    static const double max_cost = getenv("HGR_SPEC_COST") ? atof(getenv("HGR_SPEC_COST")) : 0.06;
-    if (repairs < max_repairs && rel_cost < max_cost) return kl;
+    const double t_repair = share * static_cast<double>(C) * (static_cast<double>(D) / 1024.0) * 0.6e-6;
+    const double t_call = 2.0 * static_cast<double>(B) * static_cast<double>(C) * static_cast<double>(D) / (0.6 * 1.6e15);
+    static const double max_cost = getenv("HGR_SPEC_COST") ? atof(getenv("HGR_SPEC_COST")) : 0.015;
+    if (repairs * t_repair < max_cost * t_call) return kl;
   }
   return exact;
 }
@@ -431,11 +433,11 @@ int launch_score_topk_umma(const __nv_bfloat16* X, const __nv_bfloat16* bank, co
                      umma_score_workspace_bytes(B, C, K));
   // the pair kernel picks its epilogue arrangement from the list length, which depends on lists/row = P * wpq
   int wpq = variant == 1 ? 1 : kWpq;
-  int KL = pick_list_len(K, B, p.sched.P * wpq, max_list_share(p.sched, wpq), variant == 0 || variant == 4);
+  int KL = pick_list_len(K, B, C, D, p.sched.P * wpq, max_list_share(p.sched, wpq), variant == 0 || variant == 4);
   if (pair) {
-    const int kl1 = pick_list_len(K, B, p.sched.P, max_list_share(p.sched, 1), variant == 0);   // one list per (row, pair)
+    const int kl1 = pick_list_len(K, B, C, D, p.sched.P, max_list_share(p.sched, 1), variant == 0);   // one list per (row, pair)
     wpq = pair_wpq(kl1);
-    KL = wpq == 1 ? kl1 : pick_list_len(K, B, p.sched.P * 2, max_list_share(p.sched, 2), variant == 0);
+    KL = wpq == 1 ? kl1 : pick_list_len(K, B, C, D, p.sched.P * 2, max_list_share(p.sched, 2), variant == 0);
   }
   const int lists = p.sched.P * wpq;
   p.KL = KL;

@@ -188,10 +188,10 @@ def test_score_topk_implementations_agree_at_cfg2_size():
     assert h1.tolist() == hits_from_idx(i1, targets)
 
 
-@pytest.mark.parametrize("B,C", [(512, 21841), (4096, 5461)])
+@pytest.mark.parametrize("B,C", [(512, 21841), (1024, 10450)])
 def test_speculative_lists_are_certified_or_rescanned_exactly(B, C):
-    """At cfg 2 size a row is split over 37 lists, so the production kernel keeps SPECULATIVE 8-entry lists (16-entry
-    lists for the 5-6 lists per row of a 4096-image batch).  (a) random bank order: every row certifies, nothing is
+    """At cfg 2 size a row is split over 37 lists (18 lists of a row-tile-aligned schedule in the second case), so
+    the production kernel keeps SPECULATIVE 8-entry lists.  (a) random bank order: every row certifies, nothing is
     repaired; (b) an adversarial bank whose best classes sit in adjacent rows overflows single lists: the merge must
     detect it and repair those rows exactly (re-scan of the doubtful lists' column ranges)."""
     D, K = 1024, 20
