@@ -108,6 +108,7 @@ int launch_logits_simt(const __nv_bfloat16* X, const __nv_bfloat16* bank, int64_
 
 size_t umma_score_workspace_bytes(int64_t B, int64_t C, int K);
 bool umma_supported(int64_t B, int64_t C, int64_t D, int K);
+void umma_plan(int64_t B, int64_t C, int64_t D, int K, int32_t* plan);
 int launch_score_topk_umma(const __nv_bfloat16* X, const __nv_bfloat16* bank, const int32_t* col_id,
                            int32_t id_base, const int32_t* targets, int64_t B, int64_t C, int64_t D,
                            float scale, int K, void* ws, size_t ws_bytes, float* topk_val,

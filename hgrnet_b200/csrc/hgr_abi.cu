@@ -122,6 +122,14 @@ static int score_topk_impl(const void* X, const void* bank, const int32_t* col_i
   return set_error(HGR_ERR_BAD_ARG, "hgr_score_topk: unknown impl %d", impl);
 }
 
+int hgr_score_topk_plan(int64_t B, int64_t C, int64_t D, int K, int32_t* plan) {
+  HGR_CHECK_ARG(plan != nullptr, "hgr_score_topk_plan: null plan");
+  HGR_CHECK_ARG(K >= 1 && K <= HGR_TOPK_MAX, "hgr_score_topk_plan: K = %d outside [1, %d]", K, HGR_TOPK_MAX);
+  if (!umma_supported(B, C, D, K)) return set_error(HGR_ERR_UNSUPPORTED, "hgr_score_topk_plan: shape not supported by the tcgen05 kernel");
+  umma_plan(B, C, D, K, plan);
+  return HGR_OK;
+}
+
 int hgr_score_topk(const void* X, const void* bank, const int32_t* col_id, int32_t id_base, const int32_t* targets,
                    int64_t B, int64_t C, int64_t D, float scale, int K, void* workspace, size_t workspace_bytes,
                    float* topk_val, int32_t* topk_idx, int64_t* hits, int impl, void* stream) {

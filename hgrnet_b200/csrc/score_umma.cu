@@ -413,6 +413,22 @@ size_t umma_score_workspace_bytes(int64_t B, int64_t C, int K) {
   return static_cast<size_t>(p1 > p2 ? p1 : p2) * B * kl * (sizeof(float) + sizeof(int32_t)) + kWsHeaderBytes;
 }
 
+// The decisions launch_score_topk_umma takes for the production variant, without launching anything.
+void umma_plan(int64_t B, int64_t C, int64_t D, int K, int32_t* plan) {
+  const Sched s = pick_sched(B, C, true);
+  const int kl1 = pick_list_len(K, B, C, D, s.P, max_list_share(s, 1), true);
+  const int wpq = pair_wpq(kl1);
+  const int KL = wpq == 1 ? kl1 : pick_list_len(K, B, C, D, s.P * 2, max_list_share(s, 2), true);
+  plan[0] = s.G;
+  plan[1] = s.MT;
+  plan[2] = s.U;
+  plan[3] = s.P * wpq;
+  plan[4] = KL;
+  plan[5] = wpq;
+  plan[6] = pair_ring_depth(B);
+  plan[7] = static_cast<int32_t>((s.T + s.G - 1) / s.G * kUnit);
+}
+
 int launch_score_topk_umma(const __nv_bfloat16* X, const __nv_bfloat16* bank, const int32_t* col_id,
                            int32_t id_base, const int32_t* targets, int64_t B, int64_t C, int64_t D, float scale,
                            int K, void* ws, size_t ws_bytes, float* topk_val, int32_t* topk_idx, int64_t* hits,

@@ -406,6 +406,8 @@ int launch_pair_wpq(int epi, int KL, const CUtensorMap& mx, const CUtensorMap& m
   return set_error(HGR_ERR_UNSUPPORTED, "hgr_score_topk(tcgen05 pair): list length %d", KL);
 }
 
+int pair_ring_depth(int64_t B) { return pair_stages(kEpiTopkDefer, B); }
+
 int launch_pair_kernel(int epi, int KL, int wpq, const CUtensorMap& mx, const CUtensorMap& mb, const Params& p,
                        cudaStream_t stream) {
   return wpq == 2 ? launch_pair_wpq<2>(epi, KL, mx, mb, p, stream) : launch_pair_wpq<1>(epi, KL, mx, mb, p, stream);

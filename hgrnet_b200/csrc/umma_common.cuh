@@ -328,6 +328,7 @@ __device__ __forceinline__ void cand_drain(SortedList<KL>& list, CandQueue<NTHR,
 // SEL issue every other cycle per sub-partition), not by latency, so ONE warp per quarter keeping ONE list per
 // row is the cheapest arrangement: a second warp would halve each stream and pay the list warm-up twice.
 int pair_wpq(int KL);
+int pair_ring_depth(int64_t B);   // operand stages of the production (deferred-insert) kernel for a batch size
 int launch_pair_kernel(int epi, int KL, int wpq, const CUtensorMap& mx, const CUtensorMap& mb, const Params& p,
                        cudaStream_t stream);
 

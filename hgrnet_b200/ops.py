@@ -137,6 +137,16 @@ def score_topk(X: torch.Tensor, bank: torch.Tensor, *, col_id: Optional[torch.Te
     return val, idx
 
 
+def score_topk_plan(B: int, C: int, D: int, K: int = 20) -> dict:
+    """What ``score_topk`` would do for this shape on the tcgen05 path (no launch, works without a GPU)."""
+    import ctypes
+    plan = (ctypes.c_int32 * 8)()
+    _cabi.check(_cabi.load().hgr_score_topk_plan(B, C, D, K, plan))
+    keys = ("workers", "row_tiles", "units_per_row_tile", "lists_per_row", "list_len", "warps_per_quarter",
+            "ring_depth", "cols_per_worker")
+    return dict(zip(keys, list(plan)))
+
+
 def topk_merge(part_val: torch.Tensor, part_idx: torch.Tensor, *, targets: Optional[torch.Tensor] = None,
                hits: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
     """Merge ``[P, B, K]`` partial lists (node ids) into the final ``[B, K]`` top-K + hits.

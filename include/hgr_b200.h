@@ -106,6 +106,11 @@ int hgr_aggregate_normalize(const void* E, int e_dtype, int64_t n_src, int64_t D
  * If C < K the missing entries are (-inf, -1).
  */
 size_t hgr_score_topk_workspace_bytes(int64_t B, int64_t C, int64_t D, int K);
+/* The decisions hgr_score_topk takes for a shape on the tcgen05 path, without launching anything (host only; on a
+ * box without a GPU the SM count of a B200 is assumed): plan[0..7] = {workers (CTA pairs), row tiles, 16-row units
+ * per row tile, partial lists per row, entries per list (< K: speculative), epilogue warps per TMEM quarter, operand
+ * ring depth, bank rows streamed per worker}. */
+int hgr_score_topk_plan(int64_t B, int64_t C, int64_t D, int K, int32_t* plan /* [8] */);
 int hgr_score_topk(const void* X, const void* bank, const int32_t* col_id, int32_t id_base,
                    const int32_t* targets, int64_t B, int64_t C, int64_t D, float scale, int K,
                    void* workspace, size_t workspace_bytes, float* topk_val, int32_t* topk_idx,

@@ -230,3 +230,24 @@ def test_ops_refuse_cpu_tensors():
         ops.score_topk(x, x, K=20)
     with pytest.raises(ValueError, match="no CPU path"):
         ops.logits_dense(x, x)
+
+
+def test_score_topk_plan_policy():
+    """Host-side decisions of the fused kernel (no GPU needed: a B200's 148 SMs are assumed): schedule, list length,
+    ring depth.  Pins the measured choices documented in DESIGN.md section 4."""
+    from hgrnet_b200 import ops
+    p = ops.score_topk_plan(512, 21841, 1024)                       # cfg 2: many short lists -> speculative 8-entry lists
+    assert (p["workers"], p["row_tiles"], p["lists_per_row"], p["list_len"], p["ring_depth"]) == (74, 2, 37, 8, 5)
+    p = ops.score_topk_plan(4096, 21841, 1024)                      # cfg 5: few long lists -> exact, all 74 pairs
+    assert (p["workers"], p["list_len"], p["ring_depth"]) == (74, 20, 4) and p["cols_per_worker"] > 3072
+    for C in (2731, 5461, 10921):                                   # class shards at N = 8 / 4 / 2: row-tile aligned workers
+        p = ops.score_topk_plan(4096, C, 1024)
+        assert p["workers"] == 64 and p["workers"] % p["row_tiles"] == 0 and p["lists_per_row"] == 4
+        assert p["list_len"] == 20
+    for (B, C, D) in [(64, 1000, 1024), (1024, 10450, 512), (512, 2731, 1024), (1, 17, 64), (300, 5000, 512)]:
+        p = ops.score_topk_plan(B, C, D)
+        assert 1 <= p["workers"] <= 74 and p["warps_per_quarter"] == 1
+        assert p["list_len"] in (8, 10, 12, 16, 20)
+        assert p["workers"] * p["cols_per_worker"] >= p["row_tiles"] * C          # the chunks cover every (row tile, column)
+    with pytest.raises(Exception):
+        ops.score_topk_plan(8, 8, 12)                                             # D % 8 != 0
