@@ -19,9 +19,8 @@
 namespace hgr {
 namespace {
 
-constexpr int kHierThreads = 256;
 constexpr int kHierUnroll = 8;  // independent (column id -> level, logit) load chains in flight per thread
-constexpr int kMaxLevels = 16;
+constexpr int kMaxLevels = 32;   // <= 16 levels: 256 threads per row; 17..32 levels: 128 threads (same 32 KB of slots)
 
 struct Best {
   float v;
@@ -31,18 +30,19 @@ __device__ __forceinline__ bool better(float v, int32_t j, float bv, int32_t bj)
   return v > bv || (v == bv && j < bj);
 }
 
+template <int kLevels, int kHierThreads>
 __global__ void __launch_bounds__(kHierThreads)
 hier_metrics_kernel(const float* __restrict__ logits, int64_t ldl, const int32_t* __restrict__ cols, int64_t M,
                     const int8_t* __restrict__ level, int n_levels, const int32_t* __restrict__ first_out,
                     const int32_t* __restrict__ chain, const int32_t* __restrict__ chain_level, int L,
                     int32_t* __restrict__ lvl_idx, int32_t* __restrict__ top1, unsigned long long* counts) {
-  __shared__ float s_v[kMaxLevels][kHierThreads];
-  __shared__ int32_t s_j[kMaxLevels][kHierThreads];
-  __shared__ float s_wv[kMaxLevels][kHierThreads / 32];
-  __shared__ int32_t s_wj[kMaxLevels][kHierThreads / 32];
-  __shared__ int32_t s_node[kMaxLevels];      // winner node per level (after the -1 rule)
-  __shared__ float s_tv[kMaxLevels];          // in-level maxima (before the -1 rule): their best is the TOR top-1
-  __shared__ int32_t s_tj[kMaxLevels];
+  __shared__ float s_v[kLevels][kHierThreads];
+  __shared__ int32_t s_j[kLevels][kHierThreads];
+  __shared__ float s_wv[kLevels][kHierThreads / 32];
+  __shared__ int32_t s_wj[kLevels][kHierThreads / 32];
+  __shared__ int32_t s_node[kLevels];      // winner node per level (after the -1 rule)
+  __shared__ float s_tv[kLevels];          // in-level maxima (before the -1 rule): their best is the TOR top-1
+  __shared__ int32_t s_tj[kLevels];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t row = blockIdx.x;
   const float* lr = logits + row * ldl;
@@ -153,9 +153,13 @@ int launch_hier_metrics(const float* logits, int64_t ldl, int64_t B, const int32
                         cudaStream_t stream) {
   if (n_levels < 1 || n_levels > kMaxLevels)
     return set_error(HGR_ERR_UNSUPPORTED, "hgr_hier_metrics: %d levels outside [1, %d]", n_levels, kMaxLevels);
-  hier_metrics_kernel<<<static_cast<unsigned>(B), kHierThreads, 0, stream>>>(
-      logits, ldl, cols, M, level, n_levels, first_out, chain, chain_level, L, lvl_idx, top1,
-      reinterpret_cast<unsigned long long*>(counts));
+  unsigned long long* cnt = reinterpret_cast<unsigned long long*>(counts);
+  if (n_levels <= 16)
+    hier_metrics_kernel<16, 256><<<static_cast<unsigned>(B), 256, 0, stream>>>(
+        logits, ldl, cols, M, level, n_levels, first_out, chain, chain_level, L, lvl_idx, top1, cnt);
+  else
+    hier_metrics_kernel<32, 128><<<static_cast<unsigned>(B), 128, 0, stream>>>(
+        logits, ldl, cols, M, level, n_levels, first_out, chain, chain_level, L, lvl_idx, top1, cnt);
   HGR_CHECK_LAUNCH();
   return HGR_OK;
 }

@@ -186,7 +186,7 @@ int hgr_logits_dense(const void* X, const void* bank, int64_t B, int64_t C, int6
  *
  *  logits      [B, N] fp32 (hgr_logits_dense), row pitch ldl
  *  cols        [M] int32 train_index (columns that take part), or NULL = all N columns
- *  level       [N] int8 depth of every node (len(c2p[n])); n_levels <= 16
+ *  level       [N] int8 depth of every node (len(c2p[n])); n_levels <= 32
  *  first_out   [n_levels] int32: first position j whose column is NOT at level l (a masked column holds -1.0,
  *              so that position wins when no in-level logit exceeds -1; >= M when there is none)
  *  chain       [L] int32 the label's ancestor chain + the label itself; chain_level [L] their depths

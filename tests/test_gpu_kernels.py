@@ -292,7 +292,8 @@ def test_masked_ce_matches_crossentropy(B, U, T):
 
 # ---------------------------------------------------------------------------------------------------------------
 # TOR / POR fused pass (hgr_hier_metrics) against the oracle's restatement of main.py:143,152-191
-@pytest.mark.parametrize("levels,B,train_every", [((4, 20, 200), 64, 1), ((3, 9, 40, 160), 33, 2), ((1, 5), 7, 1)])
+@pytest.mark.parametrize("levels,B,train_every", [((4, 20, 200), 64, 1), ((3, 9, 40, 160), 33, 2), ((1, 5), 7, 1),
+                                                  (tuple(1 + i // 2 for i in range(20)), 9, 1)])   # 20 levels: the 32-level variant
 def test_hier_metrics_match_oracle(levels, B, train_every):
     from hgrnet_b200 import ops
     from hgrnet_b200.hierarchy import synthetic_hierarchy
