@@ -15,14 +15,20 @@ import random as _random
 from typing import List, Optional, Sequence, Tuple
 
 
+_LIST_CACHE_ENTRIES = 512
+
+
 def contra_topk(d2n, target: int, depth: int, parents: Sequence[int], k: int, num_compare: int,
                 rng=_random, cache: Optional[dict] = None) -> Tuple[List[int], int]:
     """model/clip_tree.py:116-141.  Returns ``(compare_idx, label_position)``.
 
-    ``cache`` (optional dict owned by the caller) memoises the candidate SET of a depth window: it only depends
-    on ``(low, depth)``, and a set built from the same insertion sequence has the same iteration order, so the
-    list handed to ``random.sample`` -- and therefore the draw -- is exactly what rebuilding it every call
-    (as the reference does, :125-131) would give.  At 21,841 nodes this is ~95 % of the step's host time.
+    ``cache`` (optional dict owned by the caller) memoises (a) the candidate SET of a depth window: it only depends
+    on ``(low, depth)``, and a set built from the same insertion sequence has the same iteration order; (b) the
+    candidate LIST after the anchor chain has been removed, keyed by ``(low, depth, chain)`` -- a class comes back
+    for several batches per epoch and for every epoch, and the set difference over thousands of nodes is what is
+    left of the step's host time (bounded to ``_LIST_CACHE_ENTRIES`` lists, oldest evicted first).  Either way the
+    list handed to ``random.sample`` -- and therefore the draw -- is exactly what rebuilding it every call (as the
+    reference does, :125-131) would give: the same objects built by the same operations.
     """
     low = min(d2n.keys())
     if depth - k > low:
@@ -38,9 +44,20 @@ def contra_topk(d2n, target: int, depth: int, parents: Sequence[int], k: int, nu
         candi_set = set(candi)
         if cache is not None:
             cache[key] = candi_set
-    compare_idx = list(candi_set - set(parents))
-    if len(compare_idx) > num_compare:
-        compare_idx = rng.sample(compare_idx, num_compare)
+    lkey = ("list", low, depth, tuple(parents))
+    base = cache.get(lkey) if cache is not None else None
+    if base is None:
+        base = list(candi_set - set(parents))
+        if cache is not None:
+            order = cache.setdefault("_list_keys", [])
+            if len(order) >= _LIST_CACHE_ENTRIES:
+                cache.pop(order.pop(0), None)
+            order.append(lkey)
+            cache[lkey] = base
+    if len(base) > num_compare:
+        compare_idx = rng.sample(base, num_compare)   # a new list; the cached one is never modified
+    else:
+        compare_idx = list(base)
     if target not in compare_idx:
         compare_idx.append(target)
     return compare_idx, compare_idx.index(target)

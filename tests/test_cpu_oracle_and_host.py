@@ -251,3 +251,33 @@ def test_score_topk_plan_policy():
         assert p["workers"] * p["cols_per_worker"] >= p["row_tiles"] * C          # the chunks cover every (row tile, column)
     with pytest.raises(Exception):
         ops.score_topk_plan(8, 8, 12)                                             # D % 8 != 0
+
+
+def test_contra_topk_cache_preserves_draws():
+    """The memoised candidate sets / lists of sampling.contra_topk must hand `random.sample` exactly the list the
+    reference rebuilds on every call (clip_tree.py:125-134): same draws with and without the cache, also after
+    evictions."""
+    import random
+    from hgrnet_b200 import sampling
+    from hgrnet_b200.hierarchy import synthetic_hierarchy
+    h = synthetic_hierarchy([5, 40, 300, 1200, 900, 300], seed=2)
+    n = len(h)
+    targets = [n - 1, n - 50, 400, n - 1, 60, n - 50, 3, n - 1]
+
+    def run(cache):
+        random.seed(11)
+        out = []
+        for t in targets:
+            for (_, _, p_out, depth, parents_in, _, _) in sampling.om_schedule(h.c2p, t, 0.5, 0.5):
+                out.append(sampling.contra_topk(h.d2n, p_out, depth, parents_in, 2, 64, cache=cache))
+        return out
+
+    ref = run(None)
+    assert run({}) == ref
+    old = sampling._LIST_CACHE_ENTRIES
+    sampling._LIST_CACHE_ENTRIES = 3            # force evictions
+    try:
+        cache = {}
+        assert run(cache) == ref and len(cache["_list_keys"]) <= 3
+    finally:
+        sampling._LIST_CACHE_ENTRIES = old
