@@ -21,60 +21,10 @@ constexpr int kChunk = 32;                          // accumulator columns per t
 
 enum EpiMode { kEpiDense = 0, kEpiTopkReload = 1, kEpiTopkQueue = 2, kEpiNull = 3, kEpiTopkDefer = 4 };
 
-struct SubTile {
-  int mt;      // row tile
-  int col0;    // first bank row
-  int n;       // MMA N (multiple of 16)
-  int nvalid;  // bank rows < C inside the sub-tile
-  bool first;  // first sub-tile of a (row tile, CTA) segment
-  bool last;   // last sub-tile of the segment
-  int seq;     // index of the sub-tile inside its segment
-};
-
-struct TileWalker {
-  int64_t u, u_end;
-  int U;
-  int64_t C;
-  bool first;
-  int seq;
-  int rem_first;
-  __device__ TileWalker(const Sched& s, int cta, int64_t C_, int rem_first_ = 1)
-      : u(s.unit_begin(cta)), u_end(s.unit_begin(cta + 1)), U(s.U), C(C_), first(true), seq(0),
-        rem_first(rem_first_) {}
-  // Sub-tiles of a segment in ascending column order; the REMAINDER (segment length mod 256 columns) comes
-  // first: a narrow sub-tile costs almost a full one on the tensor pipe (the A operand is re-streamed for
-  // every sub-tile), so it is best spent while the epilogue has nothing to drain yet, and its short epilogue
-  // frees the first accumulator buffer long before the third sub-tile needs it.
-  __device__ bool next(SubTile& t) {
-    if (u >= u_end) return false;
-    const int mt = static_cast<int>(u / U);
-    int uu = static_cast<int>(u - static_cast<int64_t>(mt) * U);
-    constexpr int kFull = kSubN / kUnit;
-    int64_t seg = U - uu;                          // units left in this segment
-    if (u_end - u < seg) seg = u_end - u;
-    int nu;
-    if (first) {
-      const int rem = static_cast<int>(seg % kFull);
-      nu = (rem != 0 && rem_first) ? rem : (seg < kFull ? static_cast<int>(seg) : kFull);
-      seq = 0;
-    } else {
-      nu = seg < kFull ? static_cast<int>(seg) : kFull;
-      ++seq;
-    }
-    t.seq = seq;
-    t.mt = mt;
-    t.col0 = uu * kUnit;
-    t.n = nu * kUnit;
-    const int64_t left = C - t.col0;
-    t.nvalid = left < t.n ? static_cast<int>(left) : t.n;
-    t.first = first;
-    u += nu;
-    uu += nu;
-    t.last = (u >= u_end) || (uu == U);
-    first = t.last;
-    return true;
-  }
-};
+// SubTile / TileWalker (the walk of one worker over its chunk of the schedule) live in sched.cuh: plain integer
+// arithmetic, shared with the host-side unit test of the schedule (tests/test_cpu_sched.py).
+using ::hgr::SubTile;
+using ::hgr::TileWalker;
 
 struct Params {
   Sched sched;
