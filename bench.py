@@ -304,7 +304,14 @@ def run_ours(args):
     else:
         from hgrnet_b200.dist import ShardedEvalStream
         G_STEPS = 8
-        ses = ShardedEvalStream(banks[0], lo, batch=B, K=K, steps=G_STEPS, banks=banks, exchange=args.exchange)
+        from hgrnet_b200.dist import PeerMemoryUnavailable
+        try:
+            ses = ShardedEvalStream(banks[0], lo, batch=B, K=K, steps=G_STEPS, banks=banks, exchange=args.exchange)
+        except PeerMemoryUnavailable as e:      # raised on every rank alike: fall back together
+            if rank == 0:
+                print("bench: %s -- falling back to the NCCL exchange" % (e,), file=sys.stderr)
+            args.exchange = "nccl"
+            ses = ShardedEvalStream(banks[0], lo, batch=B, K=K, steps=G_STEPS, banks=banks, exchange="nccl")
         for s_ in range(G_STEPS):
             ses.dev_feats[s_].copy_(feats_dev[s_ % n_feat])
             ses.dev_labels[s_].copy_(labels_dev[s_ % n_feat])

@@ -123,6 +123,10 @@ def exchange_layout(B: int, K: int, world: int, slots: int, D: int = 0):
             "x_off": x_off, "x_bytes": x_bytes, "total": x_off + (X_SLOTS * x_bytes if D else 0)}
 
 
+class PeerMemoryUnavailable(RuntimeError):
+    """Raised by ``PeerExchange`` on EVERY rank when any rank could not set the exchange up."""
+
+
 class PeerExchange:
     """Peer-memory exchange of the class-sharded head (no collective call on the data path).
 
@@ -155,25 +159,53 @@ class PeerExchange:
             self.bases = list(_bases)
             self._own = None
         else:
-            with torch.cuda.device(self.device):
-                own, handle = ops.peer_alloc(self.lay["total"])
-                self._own = own
-                if self.world > 1:
-                    handles = [None] * self.world
-                    dist.all_gather_object(handles, handle, group=group)
-                    self.bases = []
-                    for g in range(self.world):
-                        if g == self.rank:
-                            self.bases.append(own)
-                        else:
-                            self.bases.append(ops.peer_open(handles[g]))
-                            self._opened.append(self.bases[-1])
-                else:
-                    self.bases = [own]
+            self._own = None
+            self._map_peers(group)
         self.local = torch.as_tensor(_RawCuda(self.bases[self.rank], self.lay["total"]), device=self.device)
         self.seq = torch.zeros(4, dtype=torch.int32, device=self.device)   # lists: [sent, waited]; features: same
         self.flag_ptrs = [b + 4 * self.rank for b in self.bases]
         self.xflag_ptrs = [b + 64 + 4 * self.rank for b in self.bases]
+
+    def _map_peers(self, group) -> None:
+        """Allocate this rank's buffer, swap the IPC handles, map every peer.  A failure on ANY rank (no CUDA IPC in
+        the container, no peer access between two GPUs, out of memory) is agreed on collectively: every rank frees
+        what it holds and raises ``PeerMemoryUnavailable``, so that callers can fall back together (the NCCL
+        exchange) instead of deadlocking in the next collective."""
+        err = None
+        own, handle = None, None
+        with torch.cuda.device(self.device):
+            try:
+                own, handle = ops.peer_alloc(self.lay["total"])
+                self._own = own
+            except Exception as e:  # noqa: BLE001 -- reported through the agreement below
+                err = e
+            if self.world == 1:
+                if err is not None:
+                    raise PeerMemoryUnavailable("peer_alloc failed: %r" % (err,))
+                self.bases = [own]
+                return
+            handles = [None] * self.world
+            dist.all_gather_object(handles, handle, group=group)
+            bases = []
+            if err is None and all(h is not None for h in handles):
+                try:
+                    for g in range(self.world):
+                        if g == self.rank:
+                            bases.append(own)
+                        else:
+                            bases.append(ops.peer_open(handles[g]))
+                            self._opened.append(bases[-1])
+                except Exception as e:  # noqa: BLE001
+                    err = e
+            elif err is None:
+                err = RuntimeError("a peer could not allocate its exchange buffer")
+            oks = [None] * self.world
+            dist.all_gather_object(oks, err is None, group=group)
+            if not all(oks):
+                self.close()
+                raise PeerMemoryUnavailable("peer-memory exchange unavailable on rank(s) %s%s" % (
+                    [g for g, ok in enumerate(oks) if not ok], "" if err is None else ": %r" % (err,)))
+            self.bases = bases
 
     # -- addresses -------------------------------------------------------------------------------------------
     def _slot_base(self, base: int, slot: int) -> int:

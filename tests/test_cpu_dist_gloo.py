@@ -99,3 +99,64 @@ def test_exchange_layout_and_row_blocks():
             hi = min(B, lo + rows)
             covered.extend(range(lo, hi))
         assert covered == list(range(B))
+
+
+def _peer_setup_worker(rank, world, port, failing_rank, stage, out):
+    """PeerExchange set-up with faked allocation / mapping calls: the rank `failing_rank` fails at `stage`."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import contextlib
+
+        from hgrnet_b200 import dist as hd
+        from hgrnet_b200 import ops
+        freed = []
+
+        def fake_alloc(nbytes):
+            if stage == "alloc" and rank == failing_rank:
+                raise RuntimeError("out of memory (fake)")
+            return 0x1000 * (rank + 1), bytes([rank]) * 64
+
+        def fake_open(handle):
+            if stage == "open" and rank == failing_rank:
+                raise RuntimeError("cudaIpcOpenMemHandle: peer access unsupported (fake)")
+            return 0x100000 + handle[0]
+
+        ops.peer_alloc, ops.peer_open = fake_alloc, fake_open
+        ops.peer_close = lambda p: freed.append(("close", p))
+        ops.peer_free = lambda p: freed.append(("free", p))
+        torch.cuda.device = lambda d: contextlib.nullcontext()         # no CUDA on this box
+        px = hd.PeerExchange.__new__(hd.PeerExchange)
+        px.device, px.world, px.rank, px._opened, px._own = "cpu", world, rank, [], None
+        px.lay = hd.exchange_layout(64, 20, world, 4)
+        try:
+            px._map_peers(None)
+            out.put((rank, "mapped", px.bases))
+        except hd.PeerMemoryUnavailable as e:
+            out.put((rank, "unavailable", str(e), freed))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("stage", ["alloc", "open", "none"])
+def test_peer_exchange_setup_failure_is_agreed_on_by_all_ranks(stage):
+    """If ANY rank cannot allocate or map the exchange buffers, EVERY rank must raise PeerMemoryUnavailable (and free
+    what it holds) -- otherwise the healthy ranks would sit in the next collective forever."""
+    ctx = mp.get_context("spawn")
+    out = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_peer_setup_worker, args=(r, 2, port, 1, stage, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    res = sorted(out.get() for _ in range(2))
+    if stage == "none":
+        assert [r[1] for r in res] == ["mapped", "mapped"]
+        assert res[0][2] == [0x1000, 0x100001] and res[1][2] == [0x100000, 0x2000]
+    else:
+        assert [r[1] for r in res] == ["unavailable", "unavailable"], res
+        if stage == "open":
+            assert ("free", 0x1000) in res[0][3] and ("close", 0x100001) in res[0][3]    # the healthy rank cleaned up
