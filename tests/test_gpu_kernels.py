@@ -293,7 +293,9 @@ def test_masked_ce_matches_crossentropy(B, U, T):
 # ---------------------------------------------------------------------------------------------------------------
 # TOR / POR fused pass (hgr_hier_metrics) against the oracle's restatement of main.py:143,152-191
 @pytest.mark.parametrize("levels,B,train_every", [((4, 20, 200), 64, 1), ((3, 9, 40, 160), 33, 2), ((1, 5), 7, 1),
-                                                  (tuple(1 + i // 2 for i in range(20)), 9, 1)])   # 20 levels: the 32-level variant
+                                                  (tuple(1 + i // 2 for i in range(20)), 9, 1),    # 20 levels: the 32-level variant
+                                                  ((6, 60, 600, 2400, 1500, 400), 12, 1),          # several passes of the column loop
+                                                  ((6, 60, 600, 2400, 1500, 400), 5, 3)])
 def test_hier_metrics_match_oracle(levels, B, train_every):
     from hgrnet_b200 import ops
     from hgrnet_b200.hierarchy import synthetic_hierarchy
