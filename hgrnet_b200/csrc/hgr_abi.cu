@@ -108,12 +108,13 @@ static int score_topk_impl(const void* X, const void* bank, const int32_t* col_i
   const bool skip_merge = (impl & HGR_IMPL_FLAG_NO_MERGE) != 0;
   impl &= ~HGR_IMPL_FLAG_NO_MERGE;
   const int which = pick_impl(impl, B, C, D, K);
-  if (which >= HGR_IMPL_TCGEN05 && which <= HGR_IMPL_TCGEN05_1CTA_NULL) {
+  if ((which >= HGR_IMPL_TCGEN05 && which <= HGR_IMPL_TCGEN05_1CTA_NULL) || which == HGR_IMPL_TCGEN05_STREAM ||
+      which == HGR_IMPL_TCGEN05_STREAM_NULL) {
     if (!umma_supported(B, C, D, K)) return set_error(HGR_ERR_UNSUPPORTED, "hgr_score_topk: shape not supported by the tcgen05 kernel");
     const int variant = which - HGR_IMPL_TCGEN05;  // see launch_score_topk_umma
     return launch_score_topk_umma(static_cast<const __nv_bfloat16*>(X), static_cast<const __nv_bfloat16*>(bank), col_id,
                                   id_base, targets, B, C, D, scale, K, workspace, workspace_bytes, topk_val, topk_idx,
-                                  hits, variant, skip_merge || variant == 3 || variant == 5, s, scatter);
+                                  hits, variant, skip_merge || variant == 3 || variant == 5 || variant == 9, s, scatter);
   }
   if (which == HGR_IMPL_SIMT)
     return launch_score_topk_simt(static_cast<const __nv_bfloat16*>(X), static_cast<const __nv_bfloat16*>(bank), col_id,

@@ -66,14 +66,83 @@ static __device__ __noinline__ void mbar_timeout_trap(uint32_t parity) {
          parity);
   __trap();
 }
-// The waiting thread is suspended by the hardware (no issue slots burnt) until the phase completes or the hint
-// expires; the clock is consulted only every 1024 wake-ups.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  const uint32_t addr = smem_u32(bar);
-  if (mbar_try_wait_suspend(addr, parity, 1000u)) return;
+// Plain try_wait: the hardware suspends the thread until the phase completes or an implementation-defined time
+// limit passes, and WAKES IT ON COMPLETION (~60 cycles after the arrive).  The suspend-time-hint form compiles to
+// TRYWAIT + NANOSLEEP.SYNCS <hint> + PHASECHK: a wait that misses the first try then sleeps for the whole hint
+// (measured: a 1 us hint quantised every ring hand-off to ~1 us -- the main loop ran at half speed with 8 KB
+// stages), so it is only used for the long back-off of the time-out path.
+__device__ __forceinline__ bool mbar_try_wait_addr(uint32_t bar_addr, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(ok)
+      : "r"(bar_addr), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Blocking wait as ONE asm statement (the retry loop lives inside it): the compiler sees no data-dependent branch,
+// so everything the issue loops compute around it stays provably warp-uniform and lives in uniform registers
+// (a visible `while (!try_wait)` makes the loop-carried stage / phase / descriptor cursors "divergent": every
+// use then costs an R2UR).  Unbounded -- used only by the producer / MMA warps; the epilogue warps of the same CTA
+// wait with the bounded mbar_wait and trap the launch if the pipeline ever stops.
+__device__ __forceinline__ void mbar_wait_spin(uint32_t bar_addr, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred P;\n"
+      "HGR_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P, [%0], %1;\n\t"
+      "@P bra HGR_DONE;\n\t"
+      "bra HGR_WAIT;\n"
+      "HGR_DONE:\n\t}"
+      ::"r"(bar_addr), "r"(parity)
+      : "memory");
+}
+// Out-of-line blocking wait for the issue loops, whose instruction count is their throughput (a single warp retires
+// one instruction every ~6-8 cycles there): the hot path is `if (!ready) mbar_wait_cold(...)` with `ready` probed
+// one stage ahead by mbar_test.
+static __device__ __noinline__ void mbar_wait_cold(uint32_t bar_addr, uint32_t parity) {
   uint32_t spins = 0;
   long long t0 = 0;
-  while (!mbar_try_wait_suspend(addr, parity, 100000u)) {
+  while (!mbar_try_wait_addr(bar_addr, parity)) {
+    if ((++spins & 1023u) == 0) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000LL) mbar_timeout_trap(parity);
+    }
+  }
+}
+__device__ __forceinline__ bool mbar_test_addr(uint32_t bar_addr, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(ok)
+      : "r"(bar_addr), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Non-blocking probe of a phase (mbarrier.test_wait): issued ahead of time, its latency overlaps what follows.
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded: a protocol bug must surface as a launch failure, never as a hung GPU (the clock is consulted only every
+// 1024 failed tries).
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  if (mbar_try_wait_addr(addr, parity)) return;
+  uint32_t spins = 0;
+  long long t0 = 0;
+  while (!mbar_try_wait_addr(addr, parity)) {
     if ((++spins & 1023u) == 0) {
       const long long now = clock64();
       if (t0 == 0) t0 = now;
@@ -94,6 +163,9 @@ __device__ __forceinline__ void st_shared_v2(uint32_t addr, uint32_t a, uint32_t
 __device__ __forceinline__ void ld_shared_v2(uint32_t addr, uint32_t& a, uint32_t& b) {
   asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(a), "=r"(b) : "r"(addr) : "memory");
 }
+__device__ __forceinline__ void ld_shared_v4(uint32_t addr, uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d) {
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(addr) : "memory");
+}
 __device__ __forceinline__ float ld_shared_f32(uint32_t addr) {
   float v;
   asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
@@ -113,6 +185,17 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0),
       "r"(c1), "l"(cache_policy)
       : "memory");
+}
+// L2 prefetch of one box (no shared-memory destination, no completion): pulls HBM lines ahead of the real load
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int32_t c0, int32_t c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ uint64_t policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
 }
 __device__ __forceinline__ uint64_t policy_evict_last() {
   uint64_t p;
@@ -184,6 +267,21 @@ __device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, uint32_t (&r)[16]) {
       : "r"(taddr)
       : "memory");
 }
+// Warp-collective: lane l writes 32 consecutive 32-bit columns of TMEM lane (lane_base + l).
+__device__ __forceinline__ void tmem_st_x32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]),
+        "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]),
+        "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() {
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
 __device__ __forceinline__ uint32_t tmem_ld_x1(uint32_t taddr) {
   uint32_t r;
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
@@ -240,11 +338,103 @@ __device__ __forceinline__ void umma_bf16_cg2(uint32_t tmem_d, uint64_t adesc, u
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Same with the A operand read from TENSOR MEMORY: each CTA's 128 rows live in its own TMEM lanes, two bf16 of
+// consecutive k per 32-bit column (K = 16 of one instruction = 8 columns starting at `tmem_a`).
+__device__ __forceinline__ void umma_bf16_cg2_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                                 uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // arrive (once the issuing thread's prior MMAs retire) on the barrier at this offset in every CTA of `cta_mask`
 __device__ __forceinline__ void umma_commit_cg2_mc(uint64_t* bar, uint16_t cta_mask) {
   asm volatile(
       "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
       ::"r"(smem_u32(bar)), "h"(cta_mask)
+      : "memory");
+}
+
+// ---- warp-uniform issue path -----------------------------------------------------------------------------
+// tcgen05.mma / TMA operands live in UNIFORM registers.  Issued under `if (lane == 0)` the compiler cannot prove
+// the operands warp-uniform and wraps every instruction in an ELECT / R2UR.BROADCAST waterfall loop (~25
+// instructions, ~170 cycles per MMA: the tensor pipe was ISSUE-bound, measured).  The issuing warp therefore stays
+// CONVERGENT (all lanes run the loop and wait on the barriers), computes descriptors from uniform values only, and
+// single-thread instructions sit under `if (elect_one())`.
+// Low 32 bits of a SWIZZLE_128B K-major descriptor (start address >> 4, LBO = 1); the high word is constant.
+constexpr uint32_t kDescHiSw128 = (1024u >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint32_t desc_lo_sw128(uint32_t smem_addr) {
+  return ((smem_addr & 0x3FFFFu) >> 4) | (1u << 16);
+}
+__device__ __forceinline__ void umma_bf16_cg2_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc,
+                                                 uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "mov.b64 da, {%1, %5};\n\tmov.b64 db, {%2, %5};\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kDescHiSw128)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_cg2_ts_lo(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_lo, uint32_t idesc,
+                                                    uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], db, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kDescHiSw128)
+      : "memory");
+}
+// smem -> TMEM copy of 128 rows x 256 bits (16 bf16 of K per row: the A operand of ONE K = 16 MMA) described by the
+// same K-major SWIZZLE_128B descriptor the SS MMA would read; row r lands in TMEM lane r, 8 columns from `taddr`.
+// cta_group::2: executed by both CTAs of the pair on their own shared / tensor memory, ordered with the MMAs of the
+// issuing thread (tcgen05.cp and tcgen05.mma form one in-order pipe).
+__device__ __forceinline__ void tmem_cp_128x256b_cg2_lo(uint32_t taddr, uint32_t desc_lo) {
+  asm volatile(
+      "{\n\t.reg .b64 d;\n\tmov.b64 d, {%1, %2};\n\t"
+      "tcgen05.cp.cta_group::2.128x256b [%0], d;\n\t}"
+      ::"r"(taddr), "r"(desc_lo), "r"(kDescHiSw128)
+      : "memory");
+}
+// The four K = 16 MMAs of one 64-wide K block in ONE statement (descriptor low words advance by 2 = 32 bytes, the
+// TMEM A address by 8 columns per step); `acc_first` = 0 only for the very first MMA of an accumulator.
+__device__ __forceinline__ void umma_kblock_cg2_ss(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc,
+                                                   uint32_t acc_first) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t.reg .b32 a, b;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\tsetp.eq.u32 q, %0, %0;\n\t"
+      "mov.b64 da, {%1, %5};\n\tmov.b64 db, {%2, %5};\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, p;\n\t"
+      "add.u32 a, %1, 2;\n\tadd.u32 b, %2, 2;\n\tmov.b64 da, {a, %5};\n\tmov.b64 db, {b, %5};\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, q;\n\t"
+      "add.u32 a, %1, 4;\n\tadd.u32 b, %2, 4;\n\tmov.b64 da, {a, %5};\n\tmov.b64 db, {b, %5};\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, q;\n\t"
+      "add.u32 a, %1, 6;\n\tadd.u32 b, %2, 6;\n\tmov.b64 da, {a, %5};\n\tmov.b64 db, {b, %5};\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, q;\n\t}"
+      ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(acc_first), "r"(kDescHiSw128)
+      : "memory");
+}
+__device__ __forceinline__ void umma_kblock_cg2_ts(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_lo, uint32_t idesc,
+                                                   uint32_t acc_first) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t.reg .b64 db;\n\t.reg .b32 a, b;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\tsetp.eq.u32 q, %0, %0;\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], db, %3, p;\n\t"
+      "add.u32 a, %1, 8;\n\tadd.u32 b, %2, 2;\n\tmov.b64 db, {b, %5};\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [a], db, %3, q;\n\t"
+      "add.u32 a, %1, 16;\n\tadd.u32 b, %2, 4;\n\tmov.b64 db, {b, %5};\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [a], db, %3, q;\n\t"
+      "add.u32 a, %1, 24;\n\tadd.u32 b, %2, 6;\n\tmov.b64 db, {b, %5};\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [a], db, %3, q;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "r"(b_lo), "r"(idesc), "r"(acc_first), "r"(kDescHiSw128)
+      : "memory");
+}
+// commit with the barrier given as a shared-space address
+__device__ __forceinline__ void umma_commit_cg2_mc_addr(uint32_t bar_addr, uint16_t cta_mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(bar_addr), "h"(cta_mask)
       : "memory");
 }
 

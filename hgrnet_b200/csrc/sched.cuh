@@ -76,9 +76,10 @@ struct TileWalker {
   bool first;
   int seq;
   int rem_first;
-  __host__ __device__ TileWalker(const Sched& s, int cta, int64_t C_, int rem_first_ = 1)
+  int full_units;   // units of a full sub-tile (sub-tile width / 16)
+  __host__ __device__ TileWalker(const Sched& s, int cta, int64_t C_, int rem_first_ = 1, int sub_n = kSubN)
       : u(s.unit_begin(cta)), u_end(s.unit_begin(cta + 1)), U(s.U), C(C_), first(true), seq(0),
-        rem_first(rem_first_) {}
+        rem_first(rem_first_), full_units(sub_n / kUnit) {}
   // Sub-tiles of a segment in ascending column order; the REMAINDER (segment length mod 256 columns) comes
   // first: a narrow sub-tile costs almost a full one on the tensor pipe (the A operand is re-streamed for
   // every sub-tile), so it is best spent while the epilogue has nothing to drain yet, and its short epilogue
@@ -87,7 +88,7 @@ struct TileWalker {
     if (u >= u_end) return false;
     const int mt = static_cast<int>(u / U);
     int uu = static_cast<int>(u - static_cast<int64_t>(mt) * U);
-    constexpr int kFull = kSubN / kUnit;
+    const int kFull = full_units;
     int64_t seg = U - uu;                          // units left in this segment
     if (u_end - u < seg) seg = u_end - u;
     int nu;

@@ -339,6 +339,41 @@ Sched pick_sched(int64_t B, int64_t C, bool pair) {
   return best;
 }
 
+// Schedule of the resident-A kernel: a segment switch inside a worker costs a pipeline bubble (the next row tile's
+// A operand can only be loaded once the last MMA of the previous segment has retired) and a fresh list, so a worker
+// count that is a multiple of the row-tile count (no chunk straddles a row tile) wins whenever the idle pairs cost
+// less than that.  Costs in bank columns of the slowest worker.
+static double resident_cost(const Sched& s) {
+  constexpr double kSegment = 200.0;   // A reload bubble + list warm-up of one more segment
+  double worst = 0.0;
+  for (int32_t w = 0; w < s.G; ++w) {
+    int64_t u = s.unit_begin(w);
+    const int64_t u_end = s.unit_begin(w + 1);
+    double cost = 0.0;
+    while (u < u_end) {
+      const int64_t tile_end = (u / s.U + 1) * s.U;
+      const int64_t e = u_end < tile_end ? u_end : tile_end;
+      cost += static_cast<double>((e - u) * kUnit) + kSegment;
+      u = e;
+    }
+    worst = cost > worst ? cost : worst;
+  }
+  return worst;
+}
+
+Sched pick_sched_resident(int64_t B, int64_t C) {
+  const int most = usable_sms() / 2;
+  Sched best = make_sched(B, C, most, 2 * kTileM);
+  if (best.MT > 1 && best.MT <= most && best.G == most) {
+    const int aligned = most / best.MT * best.MT;
+    if (aligned != most) {
+      const Sched alt = make_sched(B, C, aligned, 2 * kTileM);
+      if (resident_cost(alt) < resident_cost(best)) best = alt;
+    }
+  }
+  return best;
+}
+
 int common_setup(const __nv_bfloat16* X, const __nv_bfloat16* bank, int64_t B, int64_t C, int64_t D, bool pair,
                  CUtensorMap* mx, CUtensorMap* mb, Params* p) {
   int rc = make_map(mx, X, B, D, kTileM);
@@ -408,13 +443,27 @@ bool umma_supported(int64_t B, int64_t C, int64_t D, int K) {
 
 size_t umma_score_workspace_bytes(int64_t B, int64_t C, int K) {
   // worst case over the kernel variants (single CTA / CTA pair) and the list-width policy (exact lists)
-  const int p1 = pick_sched(B, C, false).P * kWpq, p2 = pick_sched(B, C, true).P * 2;
+  const int p1 = pick_sched(B, C, false).P * kWpq, p2 = pick_sched(B, C, true).P * 2, p3 = pick_sched_resident(B, C).P;
   const int kl = K <= 8 ? 8 : (K <= 12 ? 12 : (K <= 20 ? 20 : 32));
-  return static_cast<size_t>(p1 > p2 ? p1 : p2) * B * kl * (sizeof(float) + sizeof(int32_t)) + kWsHeaderBytes;
+  const int pm = p1 > p2 ? (p1 > p3 ? p1 : p3) : (p2 > p3 ? p2 : p3);
+  return static_cast<size_t>(pm) * B * kl * (sizeof(float) + sizeof(int32_t)) + kWsHeaderBytes;
 }
 
 // The decisions launch_score_topk_umma takes for the production variant, without launching anything.
 void umma_plan(int64_t B, int64_t C, int64_t D, int K, int32_t* plan) {
+  if (resident_supported(D)) {
+    const Sched s = pick_sched_resident(B, C);
+    const ResGeom g = resident_geom(D, kEpiTopkDefer);
+    plan[0] = s.G;
+    plan[1] = s.MT;
+    plan[2] = s.U;
+    plan[3] = s.P;
+    plan[4] = pick_list_len(K, B, C, D, s.P, max_list_share(s, 1), true);
+    plan[5] = 1;
+    plan[6] = g.stages;
+    plan[7] = static_cast<int32_t>((s.T + s.G - 1) / s.G * kUnit);
+    return;
+  }
   const Sched s = pick_sched(B, C, true);
   const int kl1 = pick_list_len(K, B, C, D, s.P, max_list_share(s, 1), true);
   const int wpq = pair_wpq(kl1);
@@ -433,20 +482,81 @@ int launch_score_topk_umma(const __nv_bfloat16* X, const __nv_bfloat16* bank, co
                            int32_t id_base, const int32_t* targets, int64_t B, int64_t C, int64_t D, float scale,
                            int K, void* ws, size_t ws_bytes, float* topk_val, int32_t* topk_idx, int64_t* hits,
                            int variant, bool skip_merge, cudaStream_t stream, const OutScatter* scatter) {
+  // variants: 0 = production: resident-A CTA-pair kernel, speculative lists when provably safe
+  //           2 = production kernel with exact lists; 3 = production main loop, null epilogue (ceiling; NOT a top-k)
   // variants: 0 = production: CTA-pair kernel, queue epilogue, speculative lists when provably safe
   //           1 = single-CTA kernel, reload epilogue, 1 warp/quarter, exact lists (cross-check)
   //           2 = production kernel with exact lists (no speculation)
   //           3 = production main loop with a null epilogue (ceiling; NOT a top-k) -- diagnostics only
   //           4 = single-CTA kernel, queue epilogue, speculative lists (the pre-pair production kernel)
   //           5 = single-CTA main loop with a null epilogue -- diagnostics only
+  //           8 = streaming CTA-pair kernel (A re-streamed per sub-tile; the round-1 production kernel), 9 = its null epilogue
+  if (ws == nullptr || ws_bytes < umma_score_workspace_bytes(B, C, K))
+    return set_error(HGR_ERR_WORKSPACE, "hgr_score_topk(tcgen05): workspace %zu < %zu bytes", ws_bytes,
+                     umma_score_workspace_bytes(B, C, K));
+  if ((variant == 0 || variant == 2 || variant == 3) && resident_supported(D) && num_sms() >= 2) {
+    const int epi = variant == 3 ? kEpiNull : kEpiTopkDefer;
+    const ResGeom g = resident_geom(D, epi);
+    CUtensorMap mx, mb;
+    Params p{};
+    int rc = make_map(&mx, X, B, D, kTileM);
+    if (rc != HGR_OK) return rc;
+    rc = make_map(&mb, bank, C, D, g.sub_n / 2);
+    if (rc != HGR_OK) return rc;
+    p.sched = pick_sched_resident(B, C);
+    p.B = B;
+    p.C = C;
+    p.num_k_blocks = g.nkb;
+    p.kb_tmem = g.kb_tmem;
+    p.a_slots = g.a_slots;
+    p.sub_n = g.sub_n;
+    p.b_stage_bytes = g.b_stage_bytes;
+    p.stage_kb = g.stage_kb;
+    p.stages = g.stages;
+    static const int no_prefetch = getenv("HGR_NO_PREFETCH") != nullptr;
+    p.prefetch = no_prefetch ? 0 : 1;
+    const int KL = pick_list_len(K, B, C, D, p.sched.P, max_list_share(p.sched, 1), variant == 0);
+    p.KL = KL;
+    p.scale = scale;
+    p.stats = static_cast<unsigned int*>(ws);
+    static const bool want_tl = getenv("HGR_TIMELINE") != nullptr;
+    p.timeline = want_tl ? reinterpret_cast<unsigned long long*>(static_cast<uint8_t*>(ws) + 64) : nullptr;
+    p.part_val = reinterpret_cast<float*>(static_cast<uint8_t*>(ws) + kWsHeaderBytes);
+    p.part_idx = reinterpret_cast<int32_t*>(p.part_val + static_cast<size_t>(p.sched.P) * B * KL);
+    rc = launch_resident_kernel(epi, KL, mx, mb, p, g, stream);
+    if (rc != HGR_OK || skip_merge || variant == 3) return rc;
+    MergeArgs m{};
+    m.part_val = p.part_val;
+    m.part_idx = p.part_idx;
+    m.P = p.sched.P;
+    m.B = B;
+    m.KL = KL;
+    m.K = K;
+    m.use_sched = 1;
+    m.wpq = 1;
+    m.sched = p.sched;
+    m.col_id = col_id;
+    m.id_base = id_base;
+    m.scale = scale;
+    m.targets = targets;
+    m.topk_val = topk_val;
+    m.topk_idx = topk_idx;
+    m.hits = hits;
+    m.X = X;
+    m.bank = bank;
+    m.C = C;
+    m.D8 = static_cast<int>(D / 8);
+    m.rescan_count = p.stats;
+    if (scatter) m.scatter = *scatter;
+    return launch_topk_merge(m, stream);
+  }
+  if (variant == 8) variant = 0;
+  if (variant == 9) variant = 3;
   const bool pair = (variant == 0 || variant == 2 || variant == 3) && num_sms() >= 2;
   CUtensorMap mx, mb;
   Params p{};
   int rc = common_setup(X, bank, B, C, D, pair, &mx, &mb, &p);
   if (rc != HGR_OK) return rc;
-  if (ws == nullptr || ws_bytes < umma_score_workspace_bytes(B, C, K))
-    return set_error(HGR_ERR_WORKSPACE, "hgr_score_topk(tcgen05): workspace %zu < %zu bytes", ws_bytes,
-                     umma_score_workspace_bytes(B, C, K));
   // the pair kernel picks its epilogue arrangement from the list length, which depends on lists/row = P * wpq
   int wpq = variant == 1 ? 1 : kWpq;
   int KL = pick_list_len(K, B, C, D, p.sched.P * wpq, max_list_share(p.sched, wpq), variant == 0 || variant == 4);
@@ -514,6 +624,30 @@ int launch_score_topk_umma(const __nv_bfloat16* X, const __nv_bfloat16* bank, co
 
 int launch_logits_umma(const __nv_bfloat16* X, const __nv_bfloat16* bank, int64_t B, int64_t C, int64_t D,
                        float scale, float* out, int64_t ldo, cudaStream_t stream) {
+  if (resident_supported(D) && num_sms() >= 2 && getenv("HGR_DENSE_STREAM") == nullptr) {
+    const ResGeom g = resident_geom(D, kEpiDense);
+    CUtensorMap mx, mb;
+    Params p{};
+    int rc = make_map(&mx, X, B, D, kTileM);
+    if (rc != HGR_OK) return rc;
+    rc = make_map(&mb, bank, C, D, g.sub_n / 2);
+    if (rc != HGR_OK) return rc;
+    p.sched = pick_sched_resident(B, C);
+    p.B = B;
+    p.C = C;
+    p.num_k_blocks = g.nkb;
+    p.kb_tmem = g.kb_tmem;
+    p.a_slots = g.a_slots;
+    p.sub_n = g.sub_n;
+    p.b_stage_bytes = g.b_stage_bytes;
+    p.stage_kb = g.stage_kb;
+    p.stages = g.stages;
+    p.prefetch = 1;
+    p.scale = scale;
+    p.dense_out = out;
+    p.ldo = ldo;
+    return launch_resident_kernel(kEpiDense, 8, mx, mb, p, g, stream);
+  }
   const bool pair = num_sms() >= 2 && getenv("HGR_DENSE_1CTA") == nullptr;
   CUtensorMap mx, mb;
   Params p{};

@@ -106,8 +106,8 @@ score_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
   if (threadIdx.x == 0) stamp(p, 1);  // set-up done (barriers, TMEM, cluster sync)
 
   if (warp == 0) {
-    // ===================== TMA producer (both CTAs) =====================
-    if (lane == 0) {
+    // ===================== TMA producer (both CTAs; convergent warp, elected issue -- see ptx.cuh) =====================
+    {
       const uint64_t pol = ptx::policy_evict_last();
       TileWalker walk(p.sched, pair, p.C, p.rem_first);
       SubTile t;
@@ -123,11 +123,14 @@ score_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
           uint8_t* sa = stage_base + stage * kPairStageBytes;
           uint8_t* sb = sa + kABytes;
           const uint32_t full_leader = ptx::mapa_shared(ptx::smem_u32(&ctl->full[stage]), 0);
-          if (rank == 0) ptx::mbar_arrive_expect_tx(&ctl->full[stage], 2 * (kABytes + nbox * kBBoxBytes));
-          ptx::tma_load_2d_cg2(sa, &map_x, full_leader, kb * kBlockK, row0, pol);
-          for (int b = 0; b < nbox; ++b)
-            ptx::tma_load_2d_cg2(sb + b * kBBoxBytes, &map_bank, full_leader, kb * kBlockK, bcol0 + b * kBBoxRows,
-                                 pol);
+          if (ptx::elect_one()) {
+            if (rank == 0) ptx::mbar_arrive_expect_tx(&ctl->full[stage], 2 * (kABytes + nbox * kBBoxBytes));
+            ptx::tma_load_2d_cg2(sa, &map_x, full_leader, kb * kBlockK, row0, pol);
+            for (int b = 0; b < nbox; ++b)
+              ptx::tma_load_2d_cg2(sb + b * kBBoxBytes, &map_bank, full_leader, kb * kBlockK, bcol0 + b * kBBoxRows,
+                                   pol);
+          }
+          __syncwarp();
           if (++stage == kPairStages) {
             stage = 0;
             phase ^= 1u;
@@ -136,42 +139,45 @@ score_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (leader CTA only) =====================
-    if (rank == 0 && lane == 0) {
+    // ===================== MMA issuer (leader CTA only; convergent warp, elected issue) =====================
+    if (rank == 0) {
       TileWalker walk(p.sched, pair, p.C, p.rem_first);
       SubTile t;
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
+      const uint32_t empty0 = ptx::smem_u32(&ctl->empty[0]);
       while (walk.next(t)) {
         const int buf = it & 1;
         ptx::mbar_wait(&ctl->tmem_empty[buf], ((it >> 1) & 1) ^ 1u);
         ptx::tc_fence_after();
-        if (it < 3) stamp(p, 21 + it);  // accumulator buffer granted for sub-tile `it`
+        if (it < 3 && lane == 0) stamp(p, 21 + it);  // accumulator buffer granted for sub-tile `it`
         const uint32_t d_tmem = tmem_base + buf * kSubN;
         const uint32_t idesc = ptx::umma_idesc_bf16(2 * kTileM, t.n);
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
           ptx::mbar_wait(&ctl->full[stage], phase);
           ptx::tc_fence_after();
-          if (it == 0 && kb == 0) stamp(p, 2);  // first operands landed
+          if (it == 0 && kb == 0 && lane == 0) stamp(p, 2);  // first operands landed
           const uint32_t a_addr = ptx::smem_u32(stage_base + stage * kPairStageBytes);
-          const uint32_t b_addr = a_addr + kABytes;
+          const uint32_t a_lo = ptx::desc_lo_sw128(a_addr), b_lo = ptx::desc_lo_sw128(a_addr + kABytes);
+          if (ptx::elect_one()) {
 #pragma unroll
-          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-            const uint64_t adesc = ptx::umma_smem_desc_sw128(a_addr + k * kUmmaK * 2);
-            const uint64_t bdesc = ptx::umma_smem_desc_sw128(b_addr + k * kUmmaK * 2);
-            ptx::umma_bf16_cg2(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < kBlockK / kUmmaK; ++k)
+              ptx::umma_bf16_cg2_lo(d_tmem, a_lo + k * (kUmmaK * 2 / 16), b_lo + k * (kUmmaK * 2 / 16), idesc,
+                                    (kb | k) != 0 ? 1u : 0u);
+            ptx::umma_commit_cg2_mc_addr(empty0 + stage * 8, 0x3);  // frees this stage in both CTAs
           }
-          ptx::umma_commit_cg2_mc(&ctl->empty[stage], 0x3);  // frees this stage in both CTAs
+          __syncwarp();
           if (++stage == kPairStages) {
             stage = 0;
             phase ^= 1u;
           }
         }
-        ptx::umma_commit_cg2_mc(&ctl->tmem_full[buf], 0x3);  // accumulators of both CTAs complete
+        if (ptx::elect_one()) ptx::umma_commit_cg2_mc(&ctl->tmem_full[buf], 0x3);  // accumulators of both CTAs complete
+        __syncwarp();
         ++it;
       }
-      stamp(p, 3);  // last MMA issued
+      if (lane == 0) stamp(p, 3);  // last MMA issued
     }
   } else {
     // ===================== epilogue (both CTAs, own 128 rows each) =====================

@@ -40,9 +40,26 @@ struct Params {
   unsigned long long* timeline;  // optional [CTA][24] %globaltimer stamps (HGR_TIMELINE=1), else nullptr
   int rem_first;       // sub-tile order inside a segment: remainder first (1) or last (0)
   int stages;          // operand ring depth of the CTA-pair kernel (set by its launcher)
+  // resident-A kernel (score_resident.cu)
+  int kb_tmem;         // K blocks of A held in tensor memory (the first kb_tmem of the K loop)
+  int a_slots;         // K blocks of A held in shared memory
+  int sub_n;           // bank rows per sub-tile = columns of one accumulator buffer
+  int b_stage_bytes;   // bytes of one K block of a CTA's bank half sub-tile (sub_n / 2 rows x 64 bf16)
+  int stage_kb;        // K blocks per bank ring stage
+  int prefetch;        // L2 prefetch of the next sub-tile's bank boxes
 };
 
-constexpr int kTimelineSlots = 24;
+// Geometry of the resident-A kernel for an embedding width (host side).
+struct ResGeom {
+  int nkb, kb_tmem, a_slots, sub_n, b_stage_bytes, stage_kb, stages;
+  size_t smem;
+};
+bool resident_supported(int64_t D);
+ResGeom resident_geom(int64_t D, int epi);
+int launch_resident_kernel(int epi, int KL, const CUtensorMap& mx, const CUtensorMap& mb, const Params& p,
+                           const ResGeom& g, cudaStream_t stream);
+
+constexpr int kTimelineSlots = 32;
 constexpr int kWsHeaderBytes = 64 + 256 * kTimelineSlots * 8;  // statistics + timeline stamps in front of the partial lists
 
 __device__ __forceinline__ void stamp(const Params& p, int slot) {

@@ -53,6 +53,8 @@ extern "C" {
 #define HGR_IMPL_TCGEN05_NULL 5   /* diagnostics: production main loop, trivial epilogue; outputs untouched */
 #define HGR_IMPL_TCGEN05_1CTA 6   /* single-CTA (cta_group::1) kernel with the production epilogue */
 #define HGR_IMPL_TCGEN05_1CTA_NULL 7 /* diagnostics: single-CTA main loop, trivial epilogue */
+#define HGR_IMPL_TCGEN05_STREAM 10      /* round-1 CTA-pair kernel (A re-streamed per sub-tile), for comparison */
+#define HGR_IMPL_TCGEN05_STREAM_NULL 11 /* its main loop with a trivial epilogue */
 /* OR-ed into `impl`: run only the GEMM + fused top-k kernel and leave the per-CTA partial lists in
  * the workspace (outputs untouched).  Lets bench.py time the dominant kernel alone for the roofline. */
 #define HGR_IMPL_FLAG_NO_MERGE 0x100

@@ -35,7 +35,8 @@ def cosine_lr(optimizer, base_lr, warmup_length, steps):
 
 
 def train(opts, epoch, model, train_loader, num_batches, optimizer, optimizer2, scheduler, device):
-    """main.py:72-101 (without the per-step fp16<->fp32 whole-model casts: parameters stay fp32 here)."""
+    """main.py:72-101.  ``optimizer`` is a ``hgrnet_b200.optim.MasterStepper``: the reference's fp32-cast / step / fp16-cast
+    sequence (main.py:90-94) on persistent fp32 masters instead of two whole-model re-allocations per step."""
     if not opts.open_eval:
         model.train()
     for i, data in enumerate(train_loader):
@@ -108,7 +109,8 @@ def main(argv=None):
                 f.writelines(k + " : " + str(v) + "\n")
         print("Training.")
         params = [p for name, p in model.named_parameters() if p.requires_grad and name != "layer_weight"]
-        optimizer = torch.optim.AdamW(params, lr=opts.lr, weight_decay=opts.wd)
+        from hgrnet_b200.optim import MasterStepper
+        optimizer = MasterStepper(params, lambda ps: torch.optim.AdamW(ps, lr=opts.lr, weight_decay=opts.wd))
         optimizer2 = torch.optim.SGD([model.layer_weight], lr=opts.w_lr) if opts.weights == "adaptive" else None
         scheduler = cosine_lr(optimizer, opts.lr, opts.warmup_length, opts.epochs * num_batches)
         for epoch in range(opts.from_epoch + 1, opts.epochs):

@@ -281,3 +281,34 @@ def test_contra_topk_cache_preserves_draws():
         assert run(cache) == ref and len(cache["_list_keys"]) <= 3
     finally:
         sampling._LIST_CACHE_ENTRIES = old
+
+
+def test_master_stepper_equals_the_reference_cast_step_cast_sequence():
+    """main.py:90-94 / utils.py:98-123: fp16 working weights must be stepped in fp32 and rounded back.  The stepper
+    has to reproduce that sequence bit for bit (and stay finite, which AdamW on fp16 tensors does not)."""
+    import copy
+    import torch.nn as nn
+    from hgrnet_b200.optim import MasterStepper
+    torch.manual_seed(0)
+    ours = nn.Sequential(nn.Linear(8, 8), nn.LayerNorm(8))
+    ours[0].half()                                            # conv / linear weights are fp16 (clip/model.py:371-392)
+    ref = copy.deepcopy(ours)
+    stepper = MasterStepper(list(ours.parameters()), lambda ps: torch.optim.AdamW(ps, lr=1e-2, weight_decay=0.1))
+    opt_ref = torch.optim.AdamW(list(ref.parameters()), lr=1e-2, weight_decay=0.1)
+    for step in range(4):
+        g = torch.Generator().manual_seed(step)
+        for po, pr in zip(ours.parameters(), ref.parameters()):
+            grad = torch.randn(po.shape, generator=g) * 1e-3
+            po.grad = grad.to(po.dtype)
+            pr.grad = grad.to(pr.dtype)
+        stepper.step()
+        for p in ref.parameters():                            # convert_models_to_fp32 (utils.py:98-101)
+            p.data = p.data.float()
+            p.grad.data = p.grad.data.float()
+        opt_ref.step()
+        ref[0].weight.data = ref[0].weight.data.half()        # convert_weights (utils.py:103-123)
+        ref[0].bias.data = ref[0].bias.data.half()
+        for po, pr in zip(ours.parameters(), ref.parameters()):
+            assert po.dtype == pr.dtype and torch.isfinite(po.float()).all()
+            assert torch.equal(po.data, pr.data), step
+    assert ours[0].weight.dtype == torch.float16 and ours[1].weight.dtype == torch.float32

@@ -34,11 +34,18 @@ def timeit(fn, n=200, warm=10, variants=20):
                 fn(i)
     torch.cuda.current_stream().wait_stream(side)
     torch.cuda.synchronize()
-    reps = max(1, n // variants)
-    for _ in range(2):
+    # clocks: the GPU idles at 120 MHz between measurements and needs tens of ms of load to reach its boost clock,
+    # so warm up for >= 0.25 s and time >= 0.2 s of back-to-back replays
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    g.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    one = max(e0.elapsed_time(e1), 1e-3)           # ms per replay (cold clocks: an over-estimate)
+    for _ in range(int(250.0 / one) + 1):
         g.replay()
     torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = max(n // variants, int(200.0 / one) + 1)
     e0.record()
     for _ in range(reps):
         g.replay()
@@ -51,7 +58,7 @@ def main():
     NM = _cabi.HGR_IMPL_FLAG_NO_MERGE
     variants = [("prod+merge", ops.HGR_IMPL_TCGEN05), ("prod", ops.HGR_IMPL_TCGEN05 | NM),
                 ("exact", ops.HGR_IMPL_TCGEN05_EXACT | NM), ("null", ops.HGR_IMPL_TCGEN05_NULL),
-                ("1cta", ops.HGR_IMPL_TCGEN05_1CTA | NM), ("1cta_null", ops.HGR_IMPL_TCGEN05_1CTA_NULL)]
+                ("stream", _cabi.HGR_IMPL_TCGEN05_STREAM | NM), ("stream_null", _cabi.HGR_IMPL_TCGEN05_STREAM_NULL)]
     out = []
     for (B, C, D) in ((512, 21841, 1024), (4096, 21841, 1024), (1024, 10450, 512), (4096, 2731, 1024), (512, 2731, 1024)):
         nb = max(2, int(1.6 * 126e6 / (C * D * 2)) + 1)

@@ -15,13 +15,15 @@ def emb(n, d, seed):
 
 
 names = ["entry", "setup", "first_full", "last_mma_issued", "acc0", "acc1", "acc2", "acc3", "epi0", "epi1", "epi2", "epi3",
-         "epi_done", "exit", "release0", "release1", "-", "-", "-", "-", "-", "mma_grant0", "mma_grant1", "mma_grant2"]
+         "epi_done", "exit", "-", "-", "-", "-", "-", "-", "-", "-", "-", "a_copies_done", "mma_a_first", "mma_a_last",
+         "a_copy_first", "a_loads_issued", "-", "-", "-", "-"]
 NM = ops.HGR_IMPL_TCGEN05 | _cabi.HGR_IMPL_FLAG_NO_MERGE
 CASES = ((512, 21841, 1024, NM, "prod"), (512, 21841, 1024, ops.HGR_IMPL_TCGEN05_NULL, "null"),
          (512, 2731, 1024, ops.HGR_IMPL_TCGEN05_NULL, "null-small"))
 if len(sys.argv) >= 3:   # python tools/timeline.py B C  -> production and null epilogue at that shape
     b_, c_ = int(sys.argv[1]), int(sys.argv[2])
-    CASES = ((b_, c_, 1024, NM, "prod"), (b_, c_, 1024, ops.HGR_IMPL_TCGEN05_NULL, "null"))
+    d_ = int(sys.argv[3]) if len(sys.argv) > 3 else 1024
+    CASES = ((b_, c_, d_, NM, "prod"), (b_, c_, d_, ops.HGR_IMPL_TCGEN05_NULL, "null"))
 for (B, C, D, impl, tag) in CASES:
     banks = [emb(C, D, 2).cuda() for _ in range(5)]
     x = emb(B, D, 1).cuda()
@@ -29,7 +31,8 @@ for (B, C, D, impl, tag) in CASES:
         ops.score_topk(x, banks[i % 5], K=20, impl=impl)
     torch.cuda.synchronize()
     ws = ops._workspaces[("cuda", 0, torch.cuda.current_stream().cuda_stream)]
-    tl = ws[64:64 + 256 * 24 * 8].view(torch.int64).reshape(256, 24)[:148].cpu()
+    tl = ws[64:64 + 256 * 32 * 8].view(torch.int64).reshape(256, 32)[:148].cpu()
+    tl = tl[tl[:, 13] > 0]                                   # CTAs of this launch
     t0 = tl[:, 0].min()
     rel = (tl - t0).float() / 1e3
     print("== %s B=%d C=%d: all times in us relative to the first CTA entry" % (tag, B, C))
@@ -41,5 +44,9 @@ for (B, C, D, impl, tag) in CASES:
     cyc = tl[:, 16:21].float()
     for j, n in enumerate(["wait acc", "warm-up pass", "tmem ld", "scan", "drain"]):
         print("  cycles %-14s median %8.0f  (%.2f us at 1.9 GHz)" % (n, cyc[:, j].median(), cyc[:, j].median() / 1900))
+    even = tl[0::2]                       # leader CTAs: MMA-warp cycle accounting (resident kernel)
+    if (even[:, 22] > 0).any():
+        for j, n in ((14, "wait bank stage"), (15, "wait accumulator buffer"), (21, "wait A operand"), (22, "MMA warp total")):
+            print("  MMA warp cycles %-24s median %8.0f" % (n, even[:, j].float().median()))
     d = rel[:, 13] - rel[:, 0]
     print("  CTA lifetime     min %7.2f  median %7.2f  max %7.2f" % (d.min(), d.median(), d.max()))
