@@ -17,7 +17,7 @@ HGR_OK = 0
 HGR_F32, HGR_BF16, HGR_F16 = 0, 1, 2
 HGR_IMPL_AUTO, HGR_IMPL_SIMT, HGR_IMPL_TCGEN05, HGR_IMPL_TCGEN05_RELOAD = 0, 1, 2, 3
 HGR_IMPL_TCGEN05_EXACT, HGR_IMPL_TCGEN05_NULL, HGR_IMPL_TCGEN05_1CTA, HGR_IMPL_TCGEN05_1CTA_NULL = 4, 5, 6, 7
-HGR_IMPL_TCGEN05_STREAM, HGR_IMPL_TCGEN05_STREAM_NULL = 10, 11
+HGR_IMPL_TCGEN05_STREAM, HGR_IMPL_TCGEN05_STREAM_NULL, HGR_IMPL_TCGEN05_SKETCH = 10, 11, 12
 HGR_IMPL_FLAG_NO_MERGE = 0x100
 HGR_NUM_HITS = 5
 HGR_TOPK_MAX = 32

@@ -94,6 +94,11 @@ struct MergeArgs {
   int D8;
   unsigned int* rescan_count;  // optional statistics: number of rows re-scanned
   OutScatter scatter;          // n_blocks > 0: replaces topk_val / topk_idx
+  // candidate lists of the floor-sketch epilogue (sketch_epi.cuh): list p of a row holds sk_cnt[p * B + row] <= sk_cap
+  // unsorted (value bits, bank row) entries at sk_part[(p * B + row) * sk_cap]; replaces part_val / part_idx / KL
+  const uint2* sk_part = nullptr;
+  const int32_t* sk_cnt = nullptr;
+  int sk_cap = 0;
 };
 int launch_topk_merge(const MergeArgs& args, cudaStream_t stream);
 

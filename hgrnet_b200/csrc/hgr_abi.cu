@@ -109,7 +109,7 @@ static int score_topk_impl(const void* X, const void* bank, const int32_t* col_i
   impl &= ~HGR_IMPL_FLAG_NO_MERGE;
   const int which = pick_impl(impl, B, C, D, K);
   if ((which >= HGR_IMPL_TCGEN05 && which <= HGR_IMPL_TCGEN05_1CTA_NULL) || which == HGR_IMPL_TCGEN05_STREAM ||
-      which == HGR_IMPL_TCGEN05_STREAM_NULL) {
+      which == HGR_IMPL_TCGEN05_STREAM_NULL || which == HGR_IMPL_TCGEN05_SKETCH) {
     if (!umma_supported(B, C, D, K)) return set_error(HGR_ERR_UNSUPPORTED, "hgr_score_topk: shape not supported by the tcgen05 kernel");
     const int variant = which - HGR_IMPL_TCGEN05;  // see launch_score_topk_umma
     return launch_score_topk_umma(static_cast<const __nv_bfloat16*>(X), static_cast<const __nv_bfloat16*>(bank), col_id,

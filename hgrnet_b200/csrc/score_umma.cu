@@ -30,6 +30,7 @@
 
 #include <cmath>
 
+#include "sketch_epi.cuh"
 #include "umma_common.cuh"
 
 namespace hgr {
@@ -436,6 +437,11 @@ constexpr int kWpq = 2;  // epilogue warps per TMEM lane quarter of the producti
 
 }  // namespace
 
+// floor-sketch epilogue: [B][20] floor words, [P][B] list lengths, [P][B][kSkCap] (value, bank row) entries
+static size_t sketch_workspace_bytes(int64_t B, int P) {
+  return static_cast<size_t>(B) * kSkSlots * 8 + static_cast<size_t>(P) * B * 4 + static_cast<size_t>(P) * B * kSkCap * 8 + 64;
+}
+
 bool umma_supported(int64_t B, int64_t C, int64_t D, int K) {
   return B >= 1 && C >= 1 && D >= 8 && D % 8 == 0 && K >= 1 && K <= HGR_TOPK_MAX &&
          C < (int64_t(1) << 31) - 512 && B < (int64_t(1) << 31) - 512;
@@ -446,7 +452,10 @@ size_t umma_score_workspace_bytes(int64_t B, int64_t C, int K) {
   const int p1 = pick_sched(B, C, false).P * kWpq, p2 = pick_sched(B, C, true).P * 2, p3 = pick_sched_resident(B, C).P;
   const int kl = K <= 8 ? 8 : (K <= 12 ? 12 : (K <= 20 ? 20 : 32));
   const int pm = p1 > p2 ? (p1 > p3 ? p1 : p3) : (p2 > p3 ? p2 : p3);
-  return static_cast<size_t>(pm) * B * kl * (sizeof(float) + sizeof(int32_t)) + kWsHeaderBytes;
+  const size_t lists = static_cast<size_t>(pm) * B * kl * (sizeof(float) + sizeof(int32_t));
+  const int p4 = make_sched(B, C, usable_sms() / 2, 2 * kTileM).P;
+  const size_t sketch = sketch_workspace_bytes(B, p4 > p2 / 2 ? p4 : p2 / 2);
+  return (lists > sketch ? lists : sketch) + kWsHeaderBytes;
 }
 
 // The decisions launch_score_topk_umma takes for the production variant, without launching anything.
@@ -547,6 +556,49 @@ int launch_score_topk_umma(const __nv_bfloat16* X, const __nv_bfloat16* bank, co
     m.C = C;
     m.D8 = static_cast<int>(D / 8);
     m.rescan_count = p.stats;
+    if (scatter) m.scatter = *scatter;
+    return launch_topk_merge(m, stream);
+  }
+  if (variant == 10) {
+    // streaming CTA-pair main loop + floor-sketch epilogue (sketch_epi.cuh): exact lists of <= kSkCap unsorted entries
+    if (K > kSkKeep) return set_error(HGR_ERR_UNSUPPORTED, "hgr_score_topk(tcgen05 sketch): K = %d > %d", K, kSkKeep);
+    CUtensorMap mx, mb;
+    Params p{};
+    int rc = common_setup(X, bank, B, C, D, true, &mx, &mb, &p);
+    if (rc != HGR_OK) return rc;
+    static const bool no_align = getenv("HGR_SK_ALIGN") == nullptr;
+    if (no_align) p.sched = make_sched(B, C, usable_sms() / 2, 2 * kTileM);   // lists are cheap: every pair works
+    p.scale = scale;
+    p.stats = static_cast<unsigned int*>(ws);
+    static const bool want_tl = getenv("HGR_TIMELINE") != nullptr;
+    p.timeline = want_tl ? reinterpret_cast<unsigned long long*>(static_cast<uint8_t*>(ws) + 64) : nullptr;
+    uint8_t* w = static_cast<uint8_t*>(ws) + kWsHeaderBytes;
+    p.sk_floors = reinterpret_cast<unsigned long long*>(w);
+    w += static_cast<size_t>(B) * kSkSlots * 8;
+    p.sk_part = reinterpret_cast<uint2*>(w);
+    w += static_cast<size_t>(p.sched.P) * B * kSkCap * 8;
+    p.sk_cnt = reinterpret_cast<int32_t*>(w);
+    rc = launch_pair_kernel(kEpiSketch, 8, 1, mx, mb, p, stream);
+    if (rc != HGR_OK || skip_merge) return rc;
+    MergeArgs m{};
+    m.sk_part = p.sk_part;
+    m.sk_cnt = p.sk_cnt;
+    m.sk_cap = kSkCap;
+    m.P = p.sched.P;
+    m.B = B;
+    m.KL = K;
+    m.K = K;
+    m.use_sched = 1;
+    m.wpq = 1;
+    m.sched = p.sched;
+    m.col_id = col_id;
+    m.id_base = id_base;
+    m.scale = scale;
+    m.targets = targets;
+    m.topk_val = topk_val;
+    m.topk_idx = topk_idx;
+    m.hits = hits;
+    m.C = C;
     if (scatter) m.scatter = *scatter;
     return launch_topk_merge(m, stream);
   }

@@ -16,6 +16,7 @@
 // `tmem_empty`.  Epilogue and work split are shared with the single-CTA kernel (umma_common.cuh).
 #include <cstdlib>
 
+#include "sketch_epi.cuh"
 #include "umma_common.cuh"
 
 namespace hgr {
@@ -42,9 +43,10 @@ inline int pair_stages(int epi, int64_t B) {
     const char* e = getenv("HGR_STAGES");
     return e ? atoi(e) : 0;
   }();
-  const int most = epi == kEpiTopkDefer ? kDeferStages : kOtherStages;
+  const bool topk = epi == kEpiTopkDefer || epi == kEpiSketch;
+  const int most = topk ? kDeferStages : kOtherStages;
   if (forced >= 2 && forced <= most) return forced;
-  return (epi == kEpiTopkDefer && B >= 2048) ? most - 1 : most;
+  return (topk && B >= 2048) ? most - 1 : most;
 }
 constexpr int kDenseTileFloats = 32 * 33;                  // dense epilogue: one padded 32x32 transpose tile per warp
 constexpr int kPairBBytes = (kSubN / 2) * kBlockK * 2;     // 16 KB: half of the bank sub-tile
@@ -65,6 +67,7 @@ score_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
   constexpr int kEpiThreads = 128 * WPQ;
   constexpr int kQueueDepth = defer_depth(WPQ);    // deferred-insert queue entries per thread (+1 dud slot)
   constexpr int kQueueBytes = EPI == kEpiTopkQueue ? kChunk * kEpiThreads * 4
+                            : EPI == kEpiSketch ? kSkQueueBytes
                             : EPI == kEpiTopkDefer ? (kQueueDepth + 1) * kEpiThreads * 8
                             : EPI == kEpiDense ? (kEpiThreads / 32) * kDenseTileFloats * 4 : 0;
   const int kPairStages = p.stages;   // <= kPairStagesMax, chosen by the launcher (pair_stages)
@@ -91,7 +94,7 @@ score_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
     for (int b = 0; b < 2; ++b) {
       ptx::mbar_init(&ctl->tmem_full[b], 1);
       // deferred epilogue: the WPQ warps of a quarter take whole sub-tiles in turn, so 4 warps per CTA arrive
-      ptx::mbar_init(&ctl->tmem_empty[b], EPI == kEpiTopkDefer ? 2 * 4 : 2 * (kEpiThreads / 32));
+      ptx::mbar_init(&ctl->tmem_empty[b], (EPI == kEpiTopkDefer || EPI == kEpiSketch) ? 2 * 4 : 2 * (kEpiThreads / 32));
     }
     ptx::fence_mbar_init();
   }
@@ -178,6 +181,138 @@ score_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
         ++it;
       }
       if (lane == 0) stamp(p, 3);  // last MMA issued
+    }
+  } else if (EPI == kEpiSketch) {
+    // ===================== epilogue: floor sketch + candidate queue (sketch_epi.cuh) =====================
+    static_assert(EPI != kEpiSketch || WPQ == 1, "one epilogue warp per TMEM lane quarter");
+    const int quarter = warp & 3;
+    const int row_in_tile = static_cast<int>(rank) * kTileM + quarter * 32 + lane;
+    const int epi_tid = (warp - kEpiWarp0) * 32 + lane;
+    const uint32_t epoch = p.stats[1] + 1u;   // stays put until the last CTA of this launch has finished
+    TileWalker walk(p.sched, pair, p.C, p.rem_first);
+    SubTile t;
+    Sketch sk;
+    FloorSlots fs;
+    SkQueue q;
+    q.init(ptx::smem_u32(reinterpret_cast<uint2*>(queue_base) + epi_tid));
+    sk.init();
+    fs.init(nullptr, epoch, 0);
+    SkFloor floor;
+    floor.init();
+    int slot = 0;
+    bool solo = true;
+    int it = 0;
+    EpiClock ck(p.timeline != nullptr && epi_tid == 0);
+    SkProf prof;
+    prof.on = ck.on;
+    while (walk.next(t)) {
+      const int buf = it & 1;
+      const int64_t row = static_cast<int64_t>(t.mt) * (2 * kTileM) + row_in_tile;
+      const bool row_ok = row < p.B;
+      if (t.first) {
+        sk.init();
+        floor.init();
+        q.wr = q.base;
+        slot = pair - p.sched.first_cta(t.mt);
+        solo = p.sched.parts(t.mt) == 1;
+        fs.init(row_ok ? p.sk_floors + row * kSkSlots : nullptr, epoch, slot);
+      }
+      ck.start();
+      ptx::mbar_wait(&ctl->tmem_full[buf], (it >> 1) & 1);
+      ptx::tc_fence_after();
+      ck.lap(ck.wait);
+      if (epi_tid == 0 && it < 4) stamp(p, 4 + it);
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + buf * kSubN;
+      // The row's global floor words.  The workers of a row tile run in step: what the others published after their
+      // previous sub-tile is in by the time this accumulator is complete.  Fetch now, consume a few chunks further
+      // down, so that the L2 round trip hides behind the first chunks.
+      int fetch_at = 0, use_at = 2 * kChunk;
+      if (t.first) {
+        // A list that starts empty would take everything: one extra pass over the sub-tile (TMEM is re-readable)
+        // builds the sketch first, so that its own columns are already filtered against their floor.  The class
+        // maxima are published at once -- every list of the row does this at about the same time, so a few chunks
+        // into the filter pass the GLOBAL floor of the row's first sub-tiles is there and almost nothing passes.
+        for (int c0 = 0; c0 + kChunk <= t.nvalid; c0 += kChunk) {
+          uint32_t r[kChunk];
+          ptx::tmem_ld_x32(taddr + c0, r);
+          ptx::tmem_ld_wait();
+          sk.update(r);
+        }
+        floor.raise(sk.floor());
+        fs.publish(sk);
+        fetch_at = kChunk;
+        use_at = solo ? (1 << 30) : 3 * kChunk;
+        ck.lap(ck.warm);
+      }
+      bool fetched = false;
+      {
+        ck.start();
+        const long long t_scan0 = ck.on ? clock64() : 0;
+        for (int c0 = 0; c0 < t.nvalid; c0 += kChunk) {
+          uint32_t r[kChunk];
+          ptx::tmem_ld_x32(taddr + c0, r);
+          if (c0 == fetch_at && !solo) {
+            fs.fetch();
+            fetched = true;
+          }
+          ptx::tmem_ld_wait();
+          const int nv = t.nvalid - c0;
+          if (fetched && (c0 >= use_at || __any_sync(0xffffffffu, q.count() > kSkQueue - kChunk))) {
+            floor.raise(fs.floor());
+            fetched = false;
+          }
+          if (!t.first && nv >= kChunk) {
+            if (solo) {          // the only list of its rows: its own sketch is all there is
+              sk.update(r);
+              floor.raise(sk.floor());
+            } else {
+              sk.update_hi(r);
+            }
+          }
+          sk_filter_chunk(q, r, nv, t.col0 + c0, floor, p.stats, &prof);
+        }
+        ck.lap(ck.scan);
+        if (ck.on && blockIdx.x < 256 && t.seq < 3) p.timeline[blockIdx.x * kTimelineSlots + 24 + t.seq] = clock64() - t_scan0;
+      }
+      // this CTA's half of the accumulator buffer is drained: tell the leader's MMA thread
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (rank == 0) ptx::mbar_arrive(&ctl->tmem_empty[buf]);
+        else ptx::mbar_arrive_cluster(ptx::mapa_shared(ptx::smem_u32(&ctl->tmem_empty[buf]), 0));
+      }
+      ck.start();
+      if (!solo) fs.publish(sk);
+      if (fetched) floor.raise(fs.floor());
+      if (!t.last && __any_sync(0xffffffffu, q.count() > kSkQueue - kChunk)) sk_compact(q, floor.keep);
+      if (epi_tid == 0 && it < 4) stamp(p, 8 + it);
+      if (t.last) {
+        // the queue becomes the list: at most kSkCap entries, everything else is provably outside the row's top-K
+        sk_compact(q, floor.keep);
+        if (__any_sync(0xffffffffu, q.count() > kSkCap)) sk_select(q, floor, kSkCap, p.stats);
+        const int cnt = q.count();
+        const int maxc = __reduce_max_sync(0xffffffffu, cnt);
+        const int64_t li = static_cast<int64_t>(slot) * p.B + (row_ok ? row : 0);
+        if (row_ok) p.sk_cnt[li] = cnt;
+        uint2* out = p.sk_part + li * kSkCap;
+        uint32_t rd = q.base;
+        for (int e0 = 0; e0 < maxc; e0 += 4, rd += 4 * kSkStride) {
+          uint32_t xb[4], col[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) ptx::ld_shared_v2(rd + i * kSkStride, xb[i], col[i]);
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (row_ok && e0 + i < cnt) out[e0 + i] = make_uint2(xb[i], col[i]);
+        }
+      }
+      ck.lap(ck.drain);
+      ++it;
+    }
+    if (epi_tid == 0) stamp(p, 12);  // epilogue done
+    if (ck.on && blockIdx.x < 256) {
+      unsigned long long* tl = p.timeline + blockIdx.x * kTimelineSlots;
+      tl[16] = ck.wait, tl[17] = ck.warm, tl[18] = ck.ld, tl[19] = ck.scan, tl[20] = ck.drain;
+      tl[27] = prof.sel, tl[28] = prof.cmp, tl[29] = prof.crowded, tl[30] = prof.passes, tl[31] = prof.selects;
     }
   } else {
     // ===================== epilogue (both CTAs, own 128 rows each) =====================
@@ -343,12 +478,22 @@ score_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
     ptx::tmem_dealloc_cg2(tmem_base, kTmemCols);
   }
   if (threadIdx.x == 32) stamp(p, 13);  // exit
+  if (EPI == kEpiSketch && threadIdx.x == 0) {
+    // the last CTA to finish advances the workspace's epoch: the next launch starts with empty floor words
+    __threadfence();
+    if (atomicAdd(&p.stats[2], 1u) == gridDim.x - 1) {
+      p.stats[2] = 0;
+      __threadfence();
+      atomicAdd(&p.stats[1], 1u);
+    }
+  }
 }
 
 template <int EPI, int KL, int WPQ>
 int launch_one(const CUtensorMap& mx, const CUtensorMap& mb, const Params& p, cudaStream_t stream) {
   constexpr int threads = 64 + 128 * WPQ;
   constexpr size_t queue = EPI == kEpiTopkQueue ? static_cast<size_t>(kChunk) * 128 * WPQ * 4
+                         : EPI == kEpiSketch ? static_cast<size_t>(kSkQueueBytes)
                          : EPI == kEpiTopkDefer ? static_cast<size_t>(defer_depth(WPQ) + 1) * 128 * WPQ * 8
                          : EPI == kEpiDense ? static_cast<size_t>(4 * WPQ) * kDenseTileFloats * 4 : 0;
   Params pp = p;
@@ -357,7 +502,7 @@ int launch_one(const CUtensorMap& mx, const CUtensorMap& mb, const Params& p, cu
   auto kern = score_umma_pair_kernel<EPI, KL, WPQ>;
   // the opt-in limit is a per-function attribute: always ask for the deepest ring so that concurrent callers with
   // different stage counts cannot lower it under each other
-  const size_t smem_max = 1024 + static_cast<size_t>(EPI == kEpiTopkDefer ? kDeferStages : kOtherStages) * kPairStageBytes +
+  const size_t smem_max = 1024 + static_cast<size_t>((EPI == kEpiTopkDefer || EPI == kEpiSketch) ? kDeferStages : kOtherStages) * kPairStageBytes +
                           queue + sizeof(PairCtl);
   HGR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_max)));
   kern<<<2 * p.sched.G, threads, smem, stream>>>(mx, mb, pp);
@@ -386,6 +531,7 @@ int launch_pair_wpq(int epi, int KL, const CUtensorMap& mx, const CUtensorMap& m
                     cudaStream_t stream) {
   if (epi == kEpiDense) return launch_one<kEpiDense, 8, WPQ>(mx, mb, p, stream);
   if (epi == kEpiNull) return launch_one<kEpiNull, 8, WPQ>(mx, mb, p, stream);
+  if (epi == kEpiSketch) return launch_one<kEpiSketch, 8, 1>(mx, mb, p, stream);
   static const int forced = [] {
     const char* e = getenv("HGR_EPILOGUE");
     return e ? (e[0] == 'q' ? 1 : 2) : 0;   // 'q' = in-place queue, 'd' = deferred inserts

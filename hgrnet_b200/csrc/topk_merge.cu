@@ -408,6 +408,129 @@ topk_select_kernel(const MergeArgs a) {
               static_cast<unsigned long long>(s_hits[threadIdx.x]));
 }
 
+// ---- candidate-list merge (floor-sketch epilogue) ---------------------------------------------------------------
+// The lists of a row are short, UNSORTED and of different lengths (sk_cnt).  One warp per row: the lists are gathered
+// into shared memory (lane = list, one 8-byte entry per step), the K-th largest order key is found by bisection over
+// the gathered entries (stops early when a cut holds exactly K), ties at the cut resolve by ascending bank row, and the
+// <= K winners are ranked by counting on (key desc, bank row asc) -- the same documented order as the other paths.
+__global__ void __launch_bounds__(kMergeWarps * 32)
+topk_merge_counts_kernel(const MergeArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ int s_hits[HGR_NUM_HITS];
+  __shared__ unsigned long long s_win[kMergeWarps][32];
+  if (threadIdx.x < HGR_NUM_HITS) s_hits[threadIdx.x] = 0;
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int K = a.K, cap = a.sk_cap;
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * kMergeWarps + warp;
+  uint2* cand = reinterpret_cast<uint2*>(smem_raw) + static_cast<size_t>(warp) * a.P * cap;
+  if (row < a.B) {
+    int lists = static_cast<int>(a.P);
+    if (a.use_sched) lists = a.sched.parts(static_cast<int32_t>(row / a.sched.rows));
+    int N = 0;
+    for (int l0 = 0; l0 < lists; l0 += 32) {
+      const int l = l0 + lane;
+      int c = l < lists ? __ldg(a.sk_cnt + static_cast<int64_t>(l) * a.B + row) : 0;
+      c = c < 0 ? 0 : (c > cap ? cap : c);
+      int incl = c;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += v;
+      }
+      const uint2* src = a.sk_part + (static_cast<int64_t>(l < lists ? l : 0) * a.B + row) * cap;
+      uint2* dst = cand + N + incl - c;
+      const int maxc = __reduce_max_sync(0xffffffffu, c);
+      for (int k = 0; k < maxc; ++k)
+        if (k < c) dst[k] = __ldg(src + k);
+      N += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    __syncwarp();
+    // keys of this lane's entries: lane, lane + 32, ...
+    uint32_t kmax = 0, kmin = 0xFFFFFFFFu;
+    for (int e = lane; e < N; e += 32) {
+      const uint32_t k = f32_order_key(__uint_as_float(cand[e].x));
+      cand[e].x = k;   // keep the key: the value is recovered from it
+      kmax = k > kmax ? k : kmax;
+      kmin = k < kmin ? k : kmin;
+    }
+    __syncwarp();
+    kmax = __reduce_max_sync(0xffffffffu, kmax);
+    kmin = __reduce_min_sync(0xffffffffu, kmin);
+    const int ksel = N < K ? N : K;
+    float my_v = -INFINITY;
+    int32_t my_i = -1;
+    if (ksel > 0) {
+      // largest T with #{key >= T} >= ksel; done as soon as a cut holds exactly ksel entries
+      uint32_t lo = kmin, hi = kmax;
+      int c_lo = N;
+      while (lo < hi && c_lo != ksel) {
+        const uint32_t mid = lo + ((hi - lo + 1u) >> 1);
+        int c = 0;
+        for (int e = lane; e < N; e += 32) c += cand[e].x >= mid;
+        c = __reduce_add_sync(0xffffffffu, c);
+        if (c >= ksel) {
+          lo = mid;
+          c_lo = c;
+        } else {
+          hi = mid - 1u;
+        }
+      }
+      const uint32_t T = lo;
+      int need = 0;   // tied entries at T still to be taken (ascending bank row)
+      if (c_lo != ksel) {
+        int above = 0;
+        for (int e = lane; e < N; e += 32) above += cand[e].x > T;
+        need = ksel - __reduce_add_sync(0xffffffffu, above);
+      }
+      uint32_t tie_floor = 0;   // tied bank rows below this one are already taken
+      bool tie_any = false;
+      int base = 0;
+      // winners above the cut (or at it, when the cut is exact), compacted one per lane
+      for (int e0 = 0; e0 < N; e0 += 32) {
+        const int e = e0 + lane;
+        const bool sel = e < N && (c_lo == ksel ? cand[e].x >= T : cand[e].x > T);
+        const unsigned b = __ballot_sync(0xffffffffu, sel);
+        if (sel) {
+          const int pos = base + __popc(b & ((1u << lane) - 1u));
+          if (pos < 32) s_win[warp][pos] = (static_cast<unsigned long long>(cand[e].x) << 32) | static_cast<uint32_t>(~cand[e].y);
+        }
+        base += __popc(b);
+      }
+      for (; need > 0; --need) {
+        uint32_t best = 0xFFFFFFFFu;
+        for (int e = lane; e < N; e += 32)
+          if (cand[e].x == T && (!tie_any || cand[e].y > tie_floor) && cand[e].y < best) best = cand[e].y;
+        best = __reduce_min_sync(0xffffffffu, best);
+        if (lane == 0 && base < 32) s_win[warp][base] = (static_cast<unsigned long long>(T) << 32) | static_cast<uint32_t>(~best);
+        ++base;
+        tie_floor = best;
+        tie_any = true;
+      }
+      __syncwarp();
+      unsigned long long mine = 0;
+      int rank = 0;
+      if (lane < ksel) {
+        mine = s_win[warp][lane];
+        for (int j = 0; j < ksel; ++j) rank += s_win[warp][j] > mine;
+      }
+      __syncwarp();
+      if (lane < ksel) s_win[warp][rank] = mine;
+      __syncwarp();
+      if (lane < ksel) {
+        const unsigned long long w = s_win[warp][lane];
+        my_v = f32_from_order_key(static_cast<uint32_t>(w >> 32));
+        my_i = static_cast<int32_t>(~static_cast<uint32_t>(w));
+      }
+    }
+    finish_row(a, row, lane, my_v, my_i, false, nullptr, 0, s_hits);
+  }
+  __syncthreads();
+  if (a.hits && threadIdx.x < HGR_NUM_HITS && s_hits[threadIdx.x] != 0)
+    atomicAdd(reinterpret_cast<unsigned long long*>(a.hits) + threadIdx.x,
+              static_cast<unsigned long long>(s_hits[threadIdx.x]));
+}
+
 // ---- cross-GPU sequencing of the peer-memory exchange ---------------------------------------------------------
 // Every rank keeps `n` flag words (one per producer rank) in its exchange buffer.  After the kernel that wrote its
 // candidates into the peers' buffers, a rank launches peer_signal: thread g stores the rank's running sequence
@@ -479,6 +602,17 @@ int launch_peer_wait(const uint32_t* flags, int n, uint32_t* seq, cudaStream_t s
 
 int launch_topk_merge(const MergeArgs& args, cudaStream_t stream) {
   if (args.B == 0 || args.K == 0) return HGR_OK;
+  if (args.sk_part != nullptr) {
+    if (args.K > 32 || args.sk_cap < 1 || args.sk_cnt == nullptr)
+      return set_error(HGR_ERR_BAD_ARG, "topk merge (candidate lists): K = %d / cap = %d", args.K, args.sk_cap);
+    const int blocks = static_cast<int>((args.B + kMergeWarps - 1) / kMergeWarps);
+    const size_t smem = static_cast<size_t>(kMergeWarps) * args.P * args.sk_cap * 8;
+    if (smem > 200 * 1024) return set_error(HGR_ERR_UNSUPPORTED, "topk merge: %zu bytes of candidates per CTA", smem);
+    HGR_CHECK_CUDA(cudaFuncSetAttribute(topk_merge_counts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    topk_merge_counts_kernel<<<blocks, kMergeWarps * 32, smem, stream>>>(args);
+    HGR_CHECK_LAUNCH();
+    return HGR_OK;
+  }
   if (args.P > 320)
     return set_error(HGR_ERR_UNSUPPORTED, "topk merge: %lld lists per row exceed 320", (long long)args.P);
   if (args.K > HGR_TOPK_MAX || args.KL < 1)

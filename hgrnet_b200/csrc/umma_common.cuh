@@ -19,7 +19,7 @@ constexpr int kEpiWarp0 = 2;
 constexpr int kTmemCols = 512;
 constexpr int kChunk = 32;                          // accumulator columns per tcgen05.ld
 
-enum EpiMode { kEpiDense = 0, kEpiTopkReload = 1, kEpiTopkQueue = 2, kEpiNull = 3, kEpiTopkDefer = 4 };
+enum EpiMode { kEpiDense = 0, kEpiTopkReload = 1, kEpiTopkQueue = 2, kEpiNull = 3, kEpiTopkDefer = 4, kEpiSketch = 5 };
 
 // SubTile / TileWalker (the walk of one worker over its chunk of the schedule) live in sched.cuh: plain integer
 // arithmetic, shared with the host-side unit test of the schedule (tests/test_cpu_sched.py).
@@ -47,6 +47,10 @@ struct Params {
   int b_stage_bytes;   // bytes of one K block of a CTA's bank half sub-tile (sub_n / 2 rows x 64 bf16)
   int stage_kb;        // K blocks per bank ring stage
   int prefetch;        // L2 prefetch of the next sub-tile's bank boxes
+  // floor-sketch epilogue (sketch_epi.cuh); stats[1] = launch epoch of the workspace, stats[2] = finished CTAs
+  uint2* sk_part;                  // [slots][B][kSkCap] (value bits, bank row)
+  int32_t* sk_cnt;                 // [slots][B] entries of each list
+  unsigned long long* sk_floors;   // [B][kSkSlots] (epoch << 32 | order key)
 };
 
 // Geometry of the resident-A kernel for an embedding width (host side).

@@ -1,11 +1,12 @@
 """Hierarchy index structures, O(N + E).
 
-Produces exactly what the reference's ``gen_tree`` returns (utils.py:39-72) -- ``p2c``,
+Produces what the reference's ``gen_tree`` returns (utils.py:39-72) -- ``p2c``,
 ``c2p``, ``d2n`` (keys in first-occurrence order), ``nodes``, ``start_up`` -- from the same
 edge-list JSON (``[[parent_wnid, child_wnid], ...]``, root ``'fall11'``; format written by
 data/hierarchical.py:45 / data/remove_irrelevant.py:34), but with dictionary lookups instead
 of ``list.index`` (O(N^2) string compares at N ~ 18k in the reference, utils.py:16-20) and
-one BFS instead of N ``nx.shortest_path`` calls.  It also derives what the CUDA kernels
+one BFS instead of N ``nx.shortest_path`` calls (nodes with several shortest root paths replay networkx's
+own bidirectional search, so multi-parent DAGs give the reference's chains as well).  It also derives what the CUDA kernels
 consume: per-node depth, and CSR rows / weights for the class-bank aggregation kernel.
 """
 from __future__ import annotations
@@ -18,6 +19,58 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import numpy as np
 
 ROOT = "fall11"  # utils.py:45
+
+
+def _nx_bidirectional_path(succ, pred_of, source, target):
+    """The path `networkx.shortest_path(G, source, target)` returns on an unweighted DiGraph: a restatement of
+    networkx 3.6.1 `_bidirectional_pred_succ` / `bidirectional_shortest_path` (the dependency the reference calls at
+    utils.py:55; not vendored in the reference).  Two BFS fronts, the smaller one (forward on a tie) advances a whole
+    level; neighbours are visited in adjacency insertion order; the first node seen by both fronts joins the halves.
+    Pinned against networkx itself on random DAGs by tests/test_cpu_oracle_and_host.py."""
+    if source == target:
+        return [source]
+    pred = {source: None}
+    nxt = {target: None}
+    forward, reverse = [source], [target]
+    meet = None
+    while forward and reverse and meet is None:
+        if len(forward) <= len(reverse):
+            level, forward = forward, []
+            for v in level:
+                for w in succ[v]:
+                    if w not in pred:
+                        forward.append(w)
+                        pred[w] = v
+                    if w in nxt:
+                        meet = w
+                        break
+                if meet is not None:
+                    break
+        else:
+            level, reverse = reverse, []
+            for v in level:
+                for w in pred_of[v]:
+                    if w not in nxt:
+                        nxt[w] = v
+                        reverse.append(w)
+                    if w in pred:
+                        meet = w
+                        break
+                if meet is not None:
+                    break
+    if meet is None:
+        raise ValueError("no path between %r and %r" % (source, target))
+    path = []
+    w = meet
+    while w is not None:
+        path.append(w)
+        w = pred[w]
+    path.reverse()
+    w = nxt[path[-1]]
+    while w is not None:
+        path.append(w)
+        w = nxt[w]
+    return path
 
 
 class Hierarchy:
@@ -40,40 +93,52 @@ class Hierarchy:
         self.start_up: List[int] = [self.index[c] for c in succ[ROOT]]  # utils.py:46
         self.p2c: List[List[int]] = [[self.index[c] for c in succ[n]] for n in self.nodes]  # utils.py:48-51
 
-        # one BFS from the root: shortest root->node chain (unique on a tree); on a DAG the
-        # first-discovered parent wins (networkx's own tie-break is version dependent)
+        # Ancestor chains (utils.py:53-56): `nx.shortest_path(G, 'fall11', node)[1:-1]`.  One BFS from the root gives
+        # every node's distance and the NUMBER of shortest root paths.  Where that path is unique (every node of a
+        # tree) the chain is the BFS parent chain.  A node with several shortest paths (the real graph is a DAG:
+        # multi-parent wnids, data/remove_irrelevant.py) gets the path networkx itself would return: its
+        # bidirectional search is replayed for that node (`_nx_bidirectional_path`), so the OM anchor chains and the
+        # TOR/POR chains equal the reference's on real data too.
+        # nx.DiGraph keeps a node's predecessors in edge-insertion order
+        pred_of: Dict[str, List[str]] = {n: [] for n in succ}
+        seen_edge2 = set()
+        for u, v in edges:
+            if (u, v) not in seen_edge2:
+                seen_edge2.add((u, v))
+                pred_of[v].append(u)
         parent = {ROOT: None}
+        dist = {ROOT: 0}
+        npaths = {ROOT: 1}
         q = deque([ROOT])
         while q:
             u = q.popleft()
             for v in succ[u]:
                 if v not in parent:
                     parent[v] = u
+                    dist[v] = dist[u] + 1
+                    npaths[v] = npaths[u]
                     q.append(v)
+                elif dist[v] == dist[u] + 1:
+                    npaths[v] = min(npaths[v] + npaths[u], 2)
         missing = [n for n in self.nodes if n not in parent]
         if missing:
             raise ValueError("%d nodes unreachable from the root (e.g. %s)" % (len(missing), missing[0]))
         N = len(self.nodes)
-        self.parent_id = np.full(N, -1, dtype=np.int32)
-        for n in self.nodes:
-            p = parent[n]
-            if p != ROOT:
-                self.parent_id[self.index[n]] = self.index[p]
         self.c2p: List[List[int]] = [None] * N  # type: ignore
-        # chains root-side first (utils.py:53-56); built top-down so each is parent's chain + parent
-        order = []
-        q = deque(self.start_up)
-        visited = set(self.start_up)
-        while q:
-            i = q.popleft()
-            order.append(i)
-            for c in self.p2c[i]:
-                if c not in visited and self.parent_id[c] == i:
-                    visited.add(c)
-                    q.append(c)
-        for i in order:
-            p = int(self.parent_id[i])
-            self.c2p[i] = [] if p < 0 else self.c2p[p] + [p]
+        self.n_multipath = 0
+        for n in sorted(self.nodes, key=lambda x: dist[x]):        # shallow first: a unique chain extends its parent's
+            i = self.index[n]
+            if npaths[n] == 1:
+                p = parent[n]
+                self.c2p[i] = [] if p == ROOT else self.c2p[self.index[p]] + [self.index[p]]
+            else:
+                self.n_multipath += 1
+                path = _nx_bidirectional_path(succ, pred_of, ROOT, n)
+                self.c2p[i] = [self.index[x] for x in path[1:-1]]
+        self.parent_id = np.full(N, -1, dtype=np.int32)            # last node of the chain (the chain's own parent)
+        for i in range(N):
+            if self.c2p[i]:
+                self.parent_id[i] = self.c2p[i][-1]
         self.depth = np.array([len(c) for c in self.c2p], dtype=np.int32)
         self.d2n: "defaultdict[int, List[int]]" = defaultdict(list)     # utils.py:66-70
         for i in range(N):

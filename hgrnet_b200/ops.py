@@ -39,7 +39,7 @@ def _workspace(nbytes: int, device) -> torch.Tensor:
     key = (device.type, device.index, torch.cuda.current_stream().cuda_stream)
     ws = _workspaces.get(key)
     if ws is None or ws.numel() < nbytes:
-        ws = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        ws = torch.zeros(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)   # header words (epoch, counters) start at 0
         _workspaces[key] = ws
     return ws
 

@@ -55,6 +55,7 @@ extern "C" {
 #define HGR_IMPL_TCGEN05_1CTA_NULL 7 /* diagnostics: single-CTA main loop, trivial epilogue */
 #define HGR_IMPL_TCGEN05_STREAM 10      /* round-1 CTA-pair kernel (A re-streamed per sub-tile), for comparison */
 #define HGR_IMPL_TCGEN05_STREAM_NULL 11 /* its main loop with a trivial epilogue */
+#define HGR_IMPL_TCGEN05_SKETCH 12      /* streaming CTA-pair main loop + floor-sketch epilogue (exact, order-independent) */
 /* OR-ed into `impl`: run only the GEMM + fused top-k kernel and leave the per-CTA partial lists in
  * the workspace (outputs untouched).  Lets bench.py time the dominant kernel alone for the roofline. */
 #define HGR_IMPL_FLAG_NO_MERGE 0x100
