@@ -11,13 +11,12 @@ import os
 from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libhgr_b200.so")
+LIB_PATH = os.environ.get("HGR_LIB") or os.path.join(HERE, "lib", "libhgr_b200.so")   # HGR_LIB: kernel experiments
 
 HGR_OK = 0
 HGR_F32, HGR_BF16, HGR_F16 = 0, 1, 2
-HGR_IMPL_AUTO, HGR_IMPL_SIMT, HGR_IMPL_TCGEN05, HGR_IMPL_TCGEN05_RELOAD = 0, 1, 2, 3
-HGR_IMPL_TCGEN05_EXACT, HGR_IMPL_TCGEN05_NULL, HGR_IMPL_TCGEN05_1CTA, HGR_IMPL_TCGEN05_1CTA_NULL = 4, 5, 6, 7
-HGR_IMPL_TCGEN05_STREAM, HGR_IMPL_TCGEN05_STREAM_NULL, HGR_IMPL_TCGEN05_SKETCH = 10, 11, 12
+HGR_IMPL_AUTO, HGR_IMPL_SIMT, HGR_IMPL_TCGEN05 = 0, 1, 2
+HGR_IMPL_TCGEN05_EXACT, HGR_IMPL_TCGEN05_NULL, HGR_IMPL_TCGEN05_SKETCH = 4, 5, 12
 HGR_IMPL_FLAG_NO_MERGE = 0x100
 HGR_NUM_HITS = 5
 HGR_TOPK_MAX = 32
@@ -30,6 +29,7 @@ SIGNATURES = {
     "hgr_launch_count": (c_int64, []),
     "hgr_aggregate_normalize": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p,
                                         c_int64, c_void_p, c_int64, c_void_p, c_int, c_void_p, c_void_p]),
+    "hgr_normalize_rows_dual": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "hgr_score_topk_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64, c_int]),
     "hgr_score_topk_plan": (c_int, [c_int64, c_int64, c_int64, c_int, c_void_p]),
     "hgr_score_topk": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_int64, c_int64, c_int64,

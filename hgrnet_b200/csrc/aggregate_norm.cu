@@ -178,7 +178,8 @@ aggregate_normalize_kernel(const TIn* __restrict__ E, int D8, const int32_t* __r
 template <typename TIn, typename TOut, int MAXV>
 __global__ void __launch_bounds__(256, 2)
 normalize_rows_kernel(const TIn* __restrict__ E, int D8, const int32_t* __restrict__ row_map, int64_t n_out,
-                      TOut* __restrict__ out, float* __restrict__ out_norm) {
+                      TOut* __restrict__ out, float* __restrict__ out_norm, TOut* __restrict__ out2 = nullptr,
+                      const int32_t* __restrict__ dst_map = nullptr) {
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
@@ -215,6 +216,10 @@ normalize_rows_kernel(const TIn* __restrict__ E, int D8, const int32_t* __restri
       out_norm[row] = na;
       if (has2) out_norm[row2] = nb;
     }
+    // second destination (dual form): row r also lands at row dst_map[r] of out2 -- the test-class bank in its own
+    // row order, written by the same pass that writes the all-node bank
+    const int64_t d1 = dst_map ? dst_map[row] : -1;
+    const int64_t d2 = (dst_map && has2) ? dst_map[row2] : -1;
 #pragma unroll
     for (int v = 0; v < MAXV; ++v) {
       const int idx = lane + 32 * v;
@@ -223,10 +228,12 @@ normalize_rows_kernel(const TIn* __restrict__ E, int D8, const int32_t* __restri
 #pragma unroll
         for (int e = 0; e < 8; ++e) o[e] = __fdiv_rn(a[v][e], na);
         Vec8<TOut>::store(out + row * D + idx * 8, o);
+        if (d1 >= 0) Vec8<TOut>::store(out2 + d1 * D + idx * 8, o);
         if (has2) {
 #pragma unroll
           for (int e = 0; e < 8; ++e) o[e] = __fdiv_rn(b[v][e], nb);
           Vec8<TOut>::store(out + row2 * D + idx * 8, o);
+          if (d2 >= 0) Vec8<TOut>::store(out2 + d2 * D + idx * 8, o);
         }
       }
     }
@@ -403,6 +410,35 @@ int launch_normalize_bcast(const void* E, int e_dtype, int64_t n_rows, int64_t D
   if (e_dtype == HGR_F16) return dispatch_bcast<__half>(E, D, n_rows, row0, n_dst, dst, stream);
   if (e_dtype == HGR_BF16) return dispatch_bcast<__nv_bfloat16>(E, D, n_rows, row0, n_dst, dst, stream);
   return set_error(HGR_ERR_UNSUPPORTED, "hgr_normalize_rows_bcast: dtype %d not supported", e_dtype);
+}
+
+template <typename TIn>
+static int dual_dispatch(const void* E, int64_t n_rows, int64_t D, __nv_bfloat16* out, const int32_t* dst_map,
+                         __nv_bfloat16* out2, cudaStream_t stream) {
+  const int D8 = static_cast<int>(D / 8);
+  const int threads = 256;
+  const int64_t rows_per_block = threads / 32;
+  const int64_t capn = static_cast<int64_t>(num_sms()) * 4;
+  const int64_t wantn = (n_rows + 2 * rows_per_block - 1) / (2 * rows_per_block);
+  const int nb = static_cast<int>(wantn < capn ? (wantn < 1 ? 1 : wantn) : capn);
+  const TIn* e = static_cast<const TIn*>(E);
+  if (D8 <= 32) normalize_rows_kernel<TIn, __nv_bfloat16, 1><<<nb, threads, 0, stream>>>(e, D8, nullptr, n_rows, out, nullptr, out2, dst_map);
+  else if (D8 <= 64) normalize_rows_kernel<TIn, __nv_bfloat16, 2><<<nb, threads, 0, stream>>>(e, D8, nullptr, n_rows, out, nullptr, out2, dst_map);
+  else if (D8 <= 96) normalize_rows_kernel<TIn, __nv_bfloat16, 3><<<nb, threads, 0, stream>>>(e, D8, nullptr, n_rows, out, nullptr, out2, dst_map);
+  else normalize_rows_kernel<TIn, __nv_bfloat16, 4><<<nb, threads, 0, stream>>>(e, D8, nullptr, n_rows, out, nullptr, out2, dst_map);
+  HGR_CHECK_LAUNCH();
+  return HGR_OK;
+}
+
+int launch_normalize_dual(const void* E, int e_dtype, int64_t n_rows, int64_t D, void* out, const int32_t* dst_map,
+                          void* out2, cudaStream_t stream) {
+  if (D / 8 > 128) return set_error(HGR_ERR_UNSUPPORTED, "hgr_normalize_rows_dual: D = %lld > 1024", (long long)D);
+  __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out);
+  __nv_bfloat16* o2 = static_cast<__nv_bfloat16*>(out2);
+  if (e_dtype == HGR_F32) return dual_dispatch<float>(E, n_rows, D, o, dst_map, o2, stream);
+  if (e_dtype == HGR_BF16) return dual_dispatch<__nv_bfloat16>(E, n_rows, D, o, dst_map, o2, stream);
+  if (e_dtype == HGR_F16) return dual_dispatch<__half>(E, n_rows, D, o, dst_map, o2, stream);
+  return set_error(HGR_ERR_BAD_ARG, "hgr_normalize_rows_dual: unknown dtype %d", e_dtype);
 }
 
 int launch_aggregate_normalize(const void* E, int e_dtype, int64_t n_src, int64_t D, const int32_t* rowptr,

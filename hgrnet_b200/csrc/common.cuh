@@ -124,6 +124,8 @@ int launch_hier_metrics(const float* logits, int64_t ldl, int64_t B, const int32
                         const int8_t* level, int n_levels, const int32_t* first_out, const int32_t* chain,
                         const int32_t* chain_level, int L, int32_t* lvl_idx, int32_t* top1, int64_t* counts,
                         cudaStream_t stream);
+int launch_normalize_dual(const void* E, int e_dtype, int64_t n_rows, int64_t D, void* out, const int32_t* dst_map,
+                          void* out2, cudaStream_t stream);
 int launch_normalize_bcast(const void* E, int e_dtype, int64_t n_rows, int64_t D, int64_t row0, int n_dst,
                            void* const* dst, cudaStream_t stream);
 

@@ -73,6 +73,17 @@ int hgr_aggregate_normalize(const void* E, int e_dtype, int64_t n_src, int64_t D
                                     static_cast<cudaStream_t>(stream));
 }
 
+int hgr_normalize_rows_dual(const void* E, int e_dtype, int64_t n_rows, int64_t D, void* out, const int32_t* dst_map,
+                            void* out2, void* stream) {
+  HGR_CHECK_ARG(n_rows >= 0, "hgr_normalize_rows_dual: negative size");
+  HGR_CHECK_ARG(D > 0 && D % 8 == 0, "hgr_normalize_rows_dual: D = %lld must be a positive multiple of 8", (long long)D);
+  if (n_rows == 0) return HGR_OK;
+  HGR_CHECK_ARG(E && out, "hgr_normalize_rows_dual: null E/out");
+  HGR_CHECK_ARG((dst_map == nullptr) == (out2 == nullptr), "hgr_normalize_rows_dual: dst_map and out2 go together");
+  HGR_CHECK_ARG(aligned16(E) && aligned16(out) && aligned16(out2), "hgr_normalize_rows_dual: E/out/out2 must be 16-byte aligned");
+  return launch_normalize_dual(E, e_dtype, n_rows, D, out, dst_map, out2, static_cast<cudaStream_t>(stream));
+}
+
 size_t hgr_score_topk_workspace_bytes(int64_t B, int64_t C, int64_t D, int K) {
   if (B <= 0 || C <= 0 || K <= 0) return 16;
   size_t a = simt_score_workspace_bytes(B, C, K);
@@ -108,13 +119,13 @@ static int score_topk_impl(const void* X, const void* bank, const int32_t* col_i
   const bool skip_merge = (impl & HGR_IMPL_FLAG_NO_MERGE) != 0;
   impl &= ~HGR_IMPL_FLAG_NO_MERGE;
   const int which = pick_impl(impl, B, C, D, K);
-  if ((which >= HGR_IMPL_TCGEN05 && which <= HGR_IMPL_TCGEN05_1CTA_NULL) || which == HGR_IMPL_TCGEN05_STREAM ||
-      which == HGR_IMPL_TCGEN05_STREAM_NULL || which == HGR_IMPL_TCGEN05_SKETCH) {
+  if (which == HGR_IMPL_TCGEN05 || which == HGR_IMPL_TCGEN05_EXACT || which == HGR_IMPL_TCGEN05_NULL ||
+      which == HGR_IMPL_TCGEN05_SKETCH) {
     if (!umma_supported(B, C, D, K)) return set_error(HGR_ERR_UNSUPPORTED, "hgr_score_topk: shape not supported by the tcgen05 kernel");
-    const int variant = which - HGR_IMPL_TCGEN05;  // see launch_score_topk_umma
+    const int variant = which - HGR_IMPL_TCGEN05;  // umma::Variant
     return launch_score_topk_umma(static_cast<const __nv_bfloat16*>(X), static_cast<const __nv_bfloat16*>(bank), col_id,
                                   id_base, targets, B, C, D, scale, K, workspace, workspace_bytes, topk_val, topk_idx,
-                                  hits, variant, skip_merge || variant == 3 || variant == 5 || variant == 9, s, scatter);
+                                  hits, variant, skip_merge || which == HGR_IMPL_TCGEN05_NULL, s, scatter);
   }
   if (which == HGR_IMPL_SIMT)
     return launch_score_topk_simt(static_cast<const __nv_bfloat16*>(X), static_cast<const __nv_bfloat16*>(bank), col_id,

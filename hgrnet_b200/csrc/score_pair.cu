@@ -1,5 +1,9 @@
-// Kernel (2), CTA-pair variant: the same fused GEMM + top-K head as score_umma.cu, but two CTAs of
-// a cluster (one TPC) share every MMA -- tcgen05.mma.cta_group::2 with M = 256.
+// Kernel (2): image x class cosine logits on tcgen05 with the per-row running top-K fused into the epilogue -- the
+// B x C logit matrix never reaches HBM.  Two CTAs of a cluster (one TPC) share every MMA: tcgen05.mma.cta_group::2
+// with M = 256.  The same main loop with a store epilogue backs hgr_logits_dense.
+//
+// Reference: `feats @ self.zsl_weights.T` (model/clip_tree.py:331), `logits[:, test_index]` +
+// `.topk(20, 1, True, True)` (main.py:136-138); id mapping / hit test (main.py:139-147) run in topk_merge.cu.
 //
 // Why: a single-CTA 128 x 256 tile needs (128 + 256) x 64 x 2 B = 48 KB of operands per K block,
 // 96 B/clk/SM at the tensor core's issue rate, and the L2 -> SM path of this chip delivers ~50
@@ -13,7 +17,7 @@
 // Protocol: both producers signal the LEADER's `full` barrier (cp.async.bulk.tensor
 // .cta_group::2); the leader's single MMA thread commits with a cluster multicast to the `empty`
 // and `tmem_full` barriers of both CTAs; the epilogue warps of both CTAs arrive on the leader's
-// `tmem_empty`.  Epilogue and work split are shared with the single-CTA kernel (umma_common.cuh).
+// `tmem_empty`.  Epilogues: umma_common.cuh (deferred-insert lists), sketch_epi.cuh (floor sketch); work split: sched.cuh.
 #include <cstdlib>
 
 #include "sketch_epi.cuh"
@@ -39,13 +43,8 @@ constexpr int kOtherStages = 6;
 // stream's small kernels (normalise, merge, flags) share the SM with a resident GEMM CTA instead of waiting for it
 // (class-sharded pipeline: -5 % per step).  At cfg 2 (B = 512) the fifth stage is worth 0.7 us, so it stays.
 inline int pair_stages(int epi, int64_t B) {
-  static const int forced = [] {
-    const char* e = getenv("HGR_STAGES");
-    return e ? atoi(e) : 0;
-  }();
   const bool topk = epi == kEpiTopkDefer || epi == kEpiSketch;
   const int most = topk ? kDeferStages : kOtherStages;
-  if (forced >= 2 && forced <= most) return forced;
   return (topk && B >= 2048) ? most - 1 : most;
 }
 constexpr int kDenseTileFloats = 32 * 33;                  // dense epilogue: one padded 32x32 transpose tile per warp
@@ -66,8 +65,7 @@ score_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
                        const Params p) {
   constexpr int kEpiThreads = 128 * WPQ;
   constexpr int kQueueDepth = defer_depth(WPQ);    // deferred-insert queue entries per thread (+1 dud slot)
-  constexpr int kQueueBytes = EPI == kEpiTopkQueue ? kChunk * kEpiThreads * 4
-                            : EPI == kEpiSketch ? kSkQueueBytes
+  constexpr int kQueueBytes = EPI == kEpiSketch ? kSkQueueBytes
                             : EPI == kEpiTopkDefer ? (kQueueDepth + 1) * kEpiThreads * 8
                             : EPI == kEpiDense ? (kEpiThreads / 32) * kDenseTileFloats * 4 : 0;
   const int kPairStages = p.stages;   // <= kPairStagesMax, chosen by the launcher (pair_stages)
@@ -199,6 +197,7 @@ score_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
     fs.init(nullptr, epoch, 0);
     SkFloor floor;
     floor.init();
+    float floor_seen = -INFINITY;   // floor.keep at the last compaction
     int slot = 0;
     bool solo = true;
     int it = 0;
@@ -212,9 +211,10 @@ score_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
       if (t.first) {
         sk.init();
         floor.init();
-        q.wr = q.base;
+        floor_seen = -INFINITY;
+        q.reset();
         slot = pair - p.sched.first_cta(t.mt);
-        solo = p.sched.parts(t.mt) == 1;
+        solo = p.sched.parts(t.mt) == 1;   // the only list of its rows: no global floor, its own sketch is all there is
         fs.init(row_ok ? p.sk_floors + row * kSkSlots : nullptr, epoch, slot);
       }
       ck.start();
@@ -223,10 +223,14 @@ score_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
       ck.lap(ck.wait);
       if (epi_tid == 0 && it < 4) stamp(p, 4 + it);
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + buf * kSubN;
+      const int phase = t.col0 & 16;       // chunk starts are multiples of 32 from the sub-tile's first column
       // The row's global floor words.  The workers of a row tile run in step: what the others published after their
-      // previous sub-tile is in by the time this accumulator is complete.  Fetch now, consume a few chunks further
-      // down, so that the L2 round trip hides behind the first chunks.
-      int fetch_at = 0, use_at = 2 * kChunk;
+      // previous sub-tile is in by the time this accumulator is complete.  Fetch at chunk `fetch_at`, consume a few
+      // chunks further down (or at once when the queue is crowded), so that the L2 round trip hides behind the chunks
+      // in between.
+      // The words come in two halves (10 words = 20 registers in flight at a time): half 0 is fetched at chunk
+      // `fetch_at`, folded two chunks later while half 1 goes out, and the floor rises another two chunks on.
+      int fetch_at = 0;
       if (t.first) {
         // A list that starts empty would take everything: one extra pass over the sub-tile (TMEM is re-readable)
         // builds the sketch first, so that its own columns are already filtered against their floor.  The class
@@ -236,40 +240,39 @@ score_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
           uint32_t r[kChunk];
           ptx::tmem_ld_x32(taddr + c0, r);
           ptx::tmem_ld_wait();
-          sk.update(r);
+          sk.update(r, phase);
         }
         floor.raise(sk.floor());
-        fs.publish(sk);
+        if (!solo) fs.publish(sk);
         fetch_at = kChunk;
-        use_at = solo ? (1 << 30) : 3 * kChunk;
         ck.lap(ck.warm);
       }
-      bool fetched = false;
+      int stage = solo ? 3 : 0;      // 0: nothing out, 1: half 0 in flight, 2: half 1 in flight, 3: done
       {
         ck.start();
         const long long t_scan0 = ck.on ? clock64() : 0;
         for (int c0 = 0; c0 < t.nvalid; c0 += kChunk) {
           uint32_t r[kChunk];
           ptx::tmem_ld_x32(taddr + c0, r);
-          if (c0 == fetch_at && !solo) {
-            fs.fetch();
-            fetched = true;
+          if (stage == 0 && c0 >= fetch_at) {
+            fs.fetch(0);
+            stage = 1;
+          } else if (stage == 1 && c0 >= fetch_at + 2 * kChunk) {
+            fs.take(true);
+            fs.fetch(1);
+            stage = 2;
+          } else if (stage == 2 && c0 >= fetch_at + 4 * kChunk) {
+            fs.take(false);
+            floor.raise(fs.floor());
+            stage = 3;
           }
           ptx::tmem_ld_wait();
           const int nv = t.nvalid - c0;
-          if (fetched && (c0 >= use_at || __any_sync(0xffffffffu, q.count() > kSkQueue - kChunk))) {
-            floor.raise(fs.floor());
-            fetched = false;
+          if (!t.first && solo && nv >= kChunk) {
+            sk.update(r, phase);
+            floor.raise(sk.floor());
           }
-          if (!t.first && nv >= kChunk) {
-            if (solo) {          // the only list of its rows: its own sketch is all there is
-              sk.update(r);
-              floor.raise(sk.floor());
-            } else {
-              sk.update_hi(r);
-            }
-          }
-          sk_filter_chunk(q, r, nv, t.col0 + c0, floor, p.stats, &prof);
+          sk_filter_chunk(q, r, nv, t.col0 + c0, floor, floor_seen, p.stats, &prof);
         }
         ck.lap(ck.scan);
         if (ck.on && blockIdx.x < 256 && t.seq < 3) p.timeline[blockIdx.x * kTimelineSlots + 24 + t.seq] = clock64() - t_scan0;
@@ -282,9 +285,18 @@ score_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
         else ptx::mbar_arrive_cluster(ptx::mapa_shared(ptx::smem_u32(&ctl->tmem_empty[buf]), 0));
       }
       ck.start();
-      if (!solo) fs.publish(sk);
-      if (fetched) floor.raise(fs.floor());
-      if (!t.last && __any_sync(0xffffffffu, q.count() > kSkQueue - kChunk)) sk_compact(q, floor.keep);
+      // a short sub-tile: finish the fetch sequence now (the buffer is already back with the tensor core)
+      if (stage == 1) {
+        fs.take(true);
+        fs.fetch(1);
+        stage = 2;
+      }
+      if (stage == 2) {
+        fs.take(false);
+        floor.raise(fs.floor());
+      }
+      if (t.first) q.pub = q.wr;                                  // covered by the class maxima published above
+      else if (!t.last && !solo) sk_publish_new(q, fs, floor.keep);
       if (epi_tid == 0 && it < 4) stamp(p, 8 + it);
       if (t.last) {
         // the queue becomes the list: at most kSkCap entries, everything else is provably outside the row's top-K
@@ -320,8 +332,6 @@ score_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
     const int member = (warp - kEpiWarp0) >> 2;
     const int row_in_tile = static_cast<int>(rank) * kTileM + quarter * 32 + lane;
     const int epi_tid = (warp - kEpiWarp0) * 32 + lane;
-    const uint32_t qaddr = ptx::smem_u32(queue_base + epi_tid * kChunk);  // private 128-byte staging row
-    const uint32_t qswz = static_cast<uint32_t>(epi_tid) & 7u;
     TileWalker walk(p.sched, pair, p.C, p.rem_first);
     SubTile t;
     SortedList<KL> list;
@@ -352,10 +362,6 @@ score_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
       if (mine) {
         if (epi_tid == 0 && it < 4) stamp(p, 4 + it);  // accumulator of sub-tile `it` ready
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + buf * kSubN;
-        if (EPI == kEpiTopkQueue && t.seq < 2) {  // warm-up floor from the first two sub-tiles of a segment
-          floor_thr = fmaxf(floor_thr, warmup_floor<KL, WPQ>(taddr, member, t.nvalid));
-          ck.lap(ck.warm);
-        }
         float sub_thr = -INFINITY;
         if (EPI == kEpiTopkDefer) {
           if (t.seq < WPQ) floor_thr = warmup_floor_pairs<KL>(taddr, t.nvalid);  // this warp's first sub-tile
@@ -386,8 +392,6 @@ score_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
               for (int rr = 0; rr < nrows; ++rr) o[static_cast<int64_t>(rr) * p.ldo] = tile[rr * 33 + lane];
             }
             __syncwarp();
-          } else if (EPI == kEpiTopkQueue) {
-            scan_chunk_queue<KL>(list, r, nv, t.col0 + c0, qaddr, qswz, floor_thr, ck);
           } else if (EPI == kEpiTopkDefer) {
             if (kQueueDepth >= 2 * kChunk) {
               const bool roomy = __reduce_max_sync(0xffffffffu, cq.count()) <= kQueueDepth - kChunk;
@@ -492,8 +496,7 @@ score_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
 template <int EPI, int KL, int WPQ>
 int launch_one(const CUtensorMap& mx, const CUtensorMap& mb, const Params& p, cudaStream_t stream) {
   constexpr int threads = 64 + 128 * WPQ;
-  constexpr size_t queue = EPI == kEpiTopkQueue ? static_cast<size_t>(kChunk) * 128 * WPQ * 4
-                         : EPI == kEpiSketch ? static_cast<size_t>(kSkQueueBytes)
+  constexpr size_t queue = EPI == kEpiSketch ? static_cast<size_t>(kSkQueueBytes)
                          : EPI == kEpiTopkDefer ? static_cast<size_t>(defer_depth(WPQ) + 1) * 128 * WPQ * 8
                          : EPI == kEpiDense ? static_cast<size_t>(4 * WPQ) * kDenseTileFloats * 4 : 0;
   Params pp = p;
@@ -512,57 +515,25 @@ int launch_one(const CUtensorMap& mx, const CUtensorMap& mb, const Params& p, cu
 
 }  // namespace
 
-// Epilogue arrangement: ONE warp per TMEM lane quarter, one list per row, inserts deferred off the tensor core's
-// critical path.  The older arrangement (TWO warps per quarter, in-place queue) is kept behind HGR_WPQ=2 /
-// HGR_EPILOGUE=q for comparison.
-int pair_wpq(int KL) {
-  static const int forced = [] {
-    const char* e = getenv("HGR_WPQ");
-    return e ? (e[0] == '2' ? 2 : 1) : 0;
-  }();
-  if (forced) return forced;
-  (void)KL;
-  return 1;   // measured: one warp per quarter + deferred inserts wins for every list length (exact 20-entry lists at
-              // B = 4096: 40 / 57 / 87 / 154 us against 46 / 66 / 98 / 164 us for two warps with in-place inserts)
-}
-
-template <int WPQ>
-int launch_pair_wpq(int epi, int KL, const CUtensorMap& mx, const CUtensorMap& mb, const Params& p,
-                    cudaStream_t stream) {
-  if (epi == kEpiDense) return launch_one<kEpiDense, 8, WPQ>(mx, mb, p, stream);
-  if (epi == kEpiNull) return launch_one<kEpiNull, 8, WPQ>(mx, mb, p, stream);
-  if (epi == kEpiSketch) return launch_one<kEpiSketch, 8, 1>(mx, mb, p, stream);
-  static const int forced = [] {
-    const char* e = getenv("HGR_EPILOGUE");
-    return e ? (e[0] == 'q' ? 1 : 2) : 0;   // 'q' = in-place queue, 'd' = deferred inserts
-  }();
-  const bool defer = forced ? forced == 2 : (WPQ == 1);
-  if (defer) {
-    switch (KL) {
-      case 8: return launch_one<kEpiTopkDefer, 8, WPQ>(mx, mb, p, stream);
-      case 10: return launch_one<kEpiTopkDefer, 10, WPQ>(mx, mb, p, stream);
-      case 12: return launch_one<kEpiTopkDefer, 12, WPQ>(mx, mb, p, stream);
-      case 16: return launch_one<kEpiTopkDefer, 16, WPQ>(mx, mb, p, stream);
-      case 20: return launch_one<kEpiTopkDefer, 20, WPQ>(mx, mb, p, stream);
-      case 32: return launch_one<kEpiTopkDefer, 32, WPQ>(mx, mb, p, stream);
-    }
-  }
-  switch (KL) {
-    case 8: return launch_one<kEpiTopkQueue, 8, WPQ>(mx, mb, p, stream);
-    case 10: return launch_one<kEpiTopkQueue, 10, WPQ>(mx, mb, p, stream);
-    case 12: return launch_one<kEpiTopkQueue, 12, WPQ>(mx, mb, p, stream);
-    case 16: return launch_one<kEpiTopkQueue, 16, WPQ>(mx, mb, p, stream);
-    case 20: return launch_one<kEpiTopkQueue, 20, WPQ>(mx, mb, p, stream);
-    case 32: return launch_one<kEpiTopkQueue, 32, WPQ>(mx, mb, p, stream);
-  }
-  return set_error(HGR_ERR_UNSUPPORTED, "hgr_score_topk(tcgen05 pair): list length %d", KL);
-}
-
 int pair_ring_depth(int64_t B) { return pair_stages(kEpiTopkDefer, B); }
 
-int launch_pair_kernel(int epi, int KL, int wpq, const CUtensorMap& mx, const CUtensorMap& mb, const Params& p,
+// Epilogue arrangement of the top-K kernels: ONE warp per TMEM lane quarter, one list per row, inserts deferred off the
+// tensor core's critical path (measured against two warps per quarter with in-place inserts: exact 20-entry lists at
+// B = 4096 40 / 57 / 87 / 154 us against 46 / 66 / 98 / 164 us).  The dense epilogue uses two warps per quarter.
+int launch_pair_kernel(int epi, int KL, const CUtensorMap& mx, const CUtensorMap& mb, const Params& p,
                        cudaStream_t stream) {
-  return wpq == 2 ? launch_pair_wpq<2>(epi, KL, mx, mb, p, stream) : launch_pair_wpq<1>(epi, KL, mx, mb, p, stream);
+  if (epi == kEpiDense) return launch_one<kEpiDense, 8, 2>(mx, mb, p, stream);
+  if (epi == kEpiNull) return launch_one<kEpiNull, 8, 1>(mx, mb, p, stream);
+  if (epi == kEpiSketch) return launch_one<kEpiSketch, 8, 1>(mx, mb, p, stream);
+  switch (KL) {
+    case 8: return launch_one<kEpiTopkDefer, 8, 1>(mx, mb, p, stream);
+    case 10: return launch_one<kEpiTopkDefer, 10, 1>(mx, mb, p, stream);
+    case 12: return launch_one<kEpiTopkDefer, 12, 1>(mx, mb, p, stream);
+    case 16: return launch_one<kEpiTopkDefer, 16, 1>(mx, mb, p, stream);
+    case 20: return launch_one<kEpiTopkDefer, 20, 1>(mx, mb, p, stream);
+    case 32: return launch_one<kEpiTopkDefer, 32, 1>(mx, mb, p, stream);
+  }
+  return set_error(HGR_ERR_UNSUPPORTED, "hgr_score_topk(tcgen05): list length %d", KL);
 }
 
 }  // namespace umma

@@ -58,24 +58,31 @@ __device__ __forceinline__ float below_key(uint32_t k) {
 }
 __device__ __forceinline__ float below(float tau) { return below_key(okey(tau)); }
 
+// Column classes are a function of the ABSOLUTE bank row: class(col) = (col & 31) % 10, so that the warm-up pass (which
+// sees whole chunks) and the per-entry publishing (which sees single columns) agree.  A chunk starts at a multiple of
+// 16: PH = chunk start & 31 is 0 or 16 and register j of the chunk holds column class ((j + PH) & 31) % 10.
+__host__ __device__ constexpr int sk_class(int col) { return (col & 31) % kSkGroups; }
+
 struct Sketch {
   float hi[kSkGroups], lo[kSkGroups];
   __device__ __forceinline__ void init() {
 #pragma unroll
     for (int g = 0; g < kSkGroups; ++g) hi[g] = lo[g] = -INFINITY;
   }
-  __device__ __forceinline__ void update(const uint32_t (&r)[kChunk]) {
+  template <int PH>
+  __device__ __forceinline__ void update_ph(const uint32_t (&r)[kChunk]) {
 #pragma unroll
     for (int j = 0; j < kChunk; ++j) {
+      constexpr int dummy = 0;
+      (void)dummy;
       const float x = __uint_as_float(r[j]);
-      lo[j % kSkGroups] = fmaxf(lo[j % kSkGroups], fminf(hi[j % kSkGroups], x));
-      hi[j % kSkGroups] = fmaxf(hi[j % kSkGroups], x);
+      lo[sk_class(j + PH)] = fmaxf(lo[sk_class(j + PH)], fminf(hi[sk_class(j + PH)], x));
+      hi[sk_class(j + PH)] = fmaxf(hi[sk_class(j + PH)], x);
     }
   }
-  // class maxima only (what the row's global floor is built from); `lo` stays a valid but stale runner-up
-  __device__ __forceinline__ void update_hi(const uint32_t (&r)[kChunk]) {
-#pragma unroll
-    for (int j = 0; j < kChunk; ++j) hi[j % kSkGroups] = fmaxf(hi[j % kSkGroups], __uint_as_float(r[j]));
+  __device__ __forceinline__ void update(const uint32_t (&r)[kChunk], int phase) {
+    if (phase) update_ph<16>(r);
+    else update_ph<0>(r);
   }
   __device__ __forceinline__ float floor() const {   // valid filter threshold from this list's own columns
     float tau = lo[0];
@@ -89,46 +96,46 @@ struct Sketch {
 struct FloorSlots {
   unsigned long long* row;   // this row's slots (nullptr: row >= B, nothing is read or published)
   uint32_t epoch;
-  uint32_t pub[kSkGroups];   // keys known to be in the slots this list publishes to
   int par;                   // slot of class g = 2 g + par
-  unsigned long long v[kSkSlots];
+  unsigned long long v[kSkSlots / 2];   // one HALF of the words in flight at a time (register budget)
+  uint32_t kmin;
 
   __device__ __forceinline__ void init(unsigned long long* row_slots, uint32_t epoch_, int list) {
     row = row_slots;
     epoch = epoch_;
     par = list & 1;
-#pragma unroll
-    for (int g = 0; g < kSkGroups; ++g) pub[g] = 0;
   }
-  // issue the loads (their latency hides behind the wait for the accumulator)
-  __device__ __forceinline__ void fetch() {
+  // issue the loads of half h (0 / 1) of the row's words; their latency hides behind the chunks processed before
+  // the matching take()
+  __device__ __forceinline__ void fetch(int h) {
     if (row == nullptr) return;
 #pragma unroll
-    for (int i = 0; i < kSkSlots / 2; ++i)
-      asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(v[2 * i]), "=l"(v[2 * i + 1]) : "l"(row + 2 * i) : "memory");
+    for (int i = 0; i < kSkSlots / 4; ++i)
+      asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(v[2 * i]), "=l"(v[2 * i + 1]) : "l"(row + h * (kSkSlots / 2) + 2 * i) : "memory");
   }
-  // floor of the whole row from the words fetched last
-  __device__ __forceinline__ float floor() {
-    if (row == nullptr) return -INFINITY;
-    uint32_t kmin = 0xFFFFFFFFu;
+  // fold the half fetched last into the running minimum (start == first half)
+  __device__ __forceinline__ void take(bool start) {
+    uint32_t m = start ? 0xFFFFFFFFu : kmin;
 #pragma unroll
-    for (int i = 0; i < kSkSlots; ++i) {
+    for (int i = 0; i < kSkSlots / 2; ++i) {
       const uint32_t k = static_cast<uint32_t>(v[i] >> 32) == epoch ? static_cast<uint32_t>(v[i]) : 0u;
-      kmin = k < kmin ? k : kmin;
-      if ((i & 1) == par) pub[i >> 1] = k > pub[i >> 1] ? k : pub[i >> 1];
+      m = k < m ? k : m;
     }
-    return below_key(kmin);
+    kmin = m;
   }
-  __device__ __forceinline__ void publish(const Sketch& sk) {
+  // floor of the whole row once both halves are in
+  __device__ __forceinline__ float floor() const { return row == nullptr ? -INFINITY : below_key(kmin); }
+  __device__ __forceinline__ void red_max(int cls, uint32_t key) const {
+    const unsigned long long w = (static_cast<unsigned long long>(epoch) << 32) | key;
+    asm volatile("red.relaxed.gpu.global.max.u64 [%0], %1;" ::"l"(row + 2 * cls + par), "l"(w) : "memory");
+  }
+  // all class maxima of a fresh sketch (first sub-tile of a segment)
+  __device__ __forceinline__ void publish(const Sketch& sk) const {
     if (row == nullptr) return;
 #pragma unroll
     for (int g = 0; g < kSkGroups; ++g) {
       const uint32_t k = okey(sk.hi[g]);
-      if (k > pub[g] && k > kKeyNegInf) {
-        const unsigned long long w = (static_cast<unsigned long long>(epoch) << 32) | k;
-        asm volatile("red.relaxed.gpu.global.max.u64 [%0], %1;" ::"l"(row + 2 * g + par), "l"(w) : "memory");
-        pub[g] = k;
-      }
+      if (k > kKeyNegInf) red_max(g, k);
     }
   }
 };
@@ -147,20 +154,45 @@ struct SkFloor {
 
 struct SkQueue {
   uint32_t base, wr;   // shared-space byte addresses: entry 0 of this thread, next free entry
-  __device__ __forceinline__ void init(uint32_t b) { base = wr = b; }
+  uint32_t pub;        // first entry not yet published into the row's global floor words (base <= pub <= wr)
+  __device__ __forceinline__ void init(uint32_t b) { base = wr = pub = b; }
+  __device__ __forceinline__ void reset() { wr = pub = base; }
   __device__ __forceinline__ int count() const { return static_cast<int>((wr - base) / kSkStride); }
 };
+
+// largest value of a chunk (ragged tail: columns >= C are zero fill and must not count); 3-input maxima, 16 instructions
+__device__ __forceinline__ float max3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
+__device__ __forceinline__ float chunk_max(const uint32_t (&r)[kChunk], int nv) {
+  float a[11], b[4];
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const float x = (nv >= kChunk || 3 * i < nv) ? __uint_as_float(r[3 * i]) : -INFINITY;
+    const float y = (nv >= kChunk || 3 * i + 1 < nv) ? __uint_as_float(r[3 * i + 1]) : -INFINITY;
+    const float z = (nv >= kChunk || 3 * i + 2 < nv) ? __uint_as_float(r[3 * i + 2]) : -INFINITY;
+    a[i] = max3(x, y, z);
+  }
+  {
+    const float x = (nv >= kChunk || 30 < nv) ? __uint_as_float(r[30]) : -INFINITY;
+    const float y = (nv >= kChunk || 31 < nv) ? __uint_as_float(r[31]) : -INFINITY;
+    a[10] = fmaxf(x, y);
+  }
+  b[0] = max3(a[0], a[1], a[2]);
+  b[1] = max3(a[3], a[4], a[5]);
+  b[2] = max3(a[6], a[7], a[8]);
+  b[3] = fmaxf(a[9], a[10]);
+  return fmaxf(max3(b[0], b[1], b[2]), b[3]);
+}
 
 // Branch-free append of a chunk: EVERY value is stored at the cursor, the cursor only advances for survivors (the next
 // store overwrites a non-survivor) -- straight-line code, which is what a lone warp per scheduler needs: nothing else
 // would hide the latency of a data-dependent loop over the survivors (measured: ~150 cycles per survivor that way).
 // The queue has kSkQueue + 1 slots, so the cursor may rest on slot kSkQueue (duds only).
 // Pre-condition of the roomy form: count <= kSkQueue - kChunk in every lane.
-template <bool FULL>
+template <bool FULL, int J0 = 0, int J1 = kChunk>
 __device__ __forceinline__ void sk_append_roomy(SkQueue& q, const uint32_t (&r)[kChunk], int nv, int col_chunk, float floor) {
   uint32_t wr = q.wr;
 #pragma unroll
-  for (int j = 0; j < kChunk; ++j) {
+  for (int j = J0; j < J1; ++j) {
     const bool pass = (__uint_as_float(r[j]) > floor) && (FULL || j < nv);   // ragged tail: columns >= C are zero fill
     ptx::st_shared_v2(wr, r[j], static_cast<uint32_t>(col_chunk + j));
     wr += pass ? kSkStride : 0u;
@@ -184,11 +216,12 @@ __device__ __forceinline__ bool sk_append_sat(SkQueue& q, const uint32_t (&r)[kC
 }
 
 // Re-filter the queue against the floor, in place, keeping the stream order.  (One warp per scheduler: nothing hides
-// a shared-memory round trip, so four entries are in flight per step.)
+// a shared-memory round trip, so four entries are in flight per step.)  The published prefix stays a prefix.
 __device__ __forceinline__ void sk_compact(SkQueue& q, float floor) {
   const int cnt = q.count();
+  const int npub = static_cast<int>((q.pub - q.base) / kSkStride);
   const int maxc = __reduce_max_sync(0xffffffffu, cnt);
-  uint32_t rd = q.base, w = q.base;
+  uint32_t rd = q.base, w = q.base, wpub = q.base;
   for (int e0 = 0; e0 < maxc; e0 += 4) {
     uint32_t xb[4], col[4];
 #pragma unroll
@@ -198,9 +231,34 @@ __device__ __forceinline__ void sk_compact(SkQueue& q, float floor) {
     for (int i = 0; i < 4; ++i) {
       ptx::st_shared_v2(w, xb[i], col[i]);   // w <= the entry just read
       w += (e0 + i < cnt && __uint_as_float(xb[i]) > floor) ? kSkStride : 0u;
+      wpub = e0 + i < npub ? w : wpub;
     }
   }
   q.wr = w;
+  q.pub = wpub;
+}
+
+// New queue entries into the row's global floor words: entry (x, col) raises word 2 * class(col) + parity.  Only
+// survivors are ever published -- a value at or below the row's floor cannot raise a word (every word is >= the floor,
+// their minimum) -- and survivors are few, so no class maxima have to be tracked while filtering.
+__device__ __forceinline__ void sk_publish_new(SkQueue& q, const FloorSlots& fs, float floor) {
+  const int n = static_cast<int>((q.wr - q.pub) / kSkStride);
+  const int maxn = __reduce_max_sync(0xffffffffu, n);
+  uint32_t rd = q.pub;
+  for (int e0 = 0; e0 < maxn; e0 += 2) {
+    uint32_t xb[2], col[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      xb[i] = col[i] = 0;
+      if (e0 + i < n) ptx::ld_shared_v2(rd + i * kSkStride, xb[i], col[i]);   // other lanes may have more new entries
+    }
+    rd += 2 * kSkStride;
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+      if (e0 + i < n && fs.row != nullptr && __uint_as_float(xb[i]) > floor)
+        fs.red_max(sk_class(static_cast<int>(col[i])), okey(__uint_as_float(xb[i])));
+  }
+  q.pub = q.wr;
 }
 
 // Exact reduction of over-full queues (warp-uniform call; lanes with count <= limit keep everything).  For the
@@ -210,7 +268,7 @@ __device__ __forceinline__ void sk_compact(SkQueue& q, float floor) {
 // of that value loses the tie as well: the filter for new columns becomes the value of T itself (strict compare).
 // The keys of all 64 slots are held in registers: a counting pass is 64 compare-and-add with four accumulators.
 struct SkState {
-  uint32_t wr;
+  uint32_t wr, pub;
   float in, keep;
   int passes;
 };
@@ -219,7 +277,7 @@ struct SkProf {   // cycle accounting of one epilogue warp (timeline builds only
   int crowded = 0, passes = 0, selects = 0;
   bool on = false;
 };
-static __device__ __noinline__ SkState sk_select_impl(uint32_t q_base, uint32_t q_wr, float f_in, float f_keep, int limit,
+static __device__ __noinline__ SkState sk_select_impl(uint32_t q_base, uint32_t q_wr, uint32_t q_pub, float f_in, float f_keep, int limit,
                                                      unsigned int* stat) {
   const int lane = threadIdx.x & 31;
   if (lane == 0 && stat != nullptr) atomicAdd(stat, 1u);
@@ -264,8 +322,9 @@ static __device__ __noinline__ SkState sk_select_impl(uint32_t q_base, uint32_t 
     for (int e = 0; e < kSkQueue; ++e) gt += key[e] > lo ? 1 : 0;
     need = kSkKeep - gt;
   }
-  // compaction, keeping the stream order
-  uint32_t rd = q_base, w = q_base;
+  // compaction, keeping the stream order (and the published prefix a prefix)
+  const int npub = static_cast<int>((q_pub - q_base) / kSkStride);
+  uint32_t rd = q_base, w = q_base, wpub = q_base;
   for (int e0 = 0; e0 < maxc; e0 += 4) {
     uint32_t xb[4], col[4];
 #pragma unroll
@@ -282,11 +341,13 @@ static __device__ __noinline__ SkState sk_select_impl(uint32_t q_base, uint32_t 
         need -= (ties && tied && e0 + i < cnt) ? 1 : 0;
       }
       w += keep ? kSkStride : 0u;
+      wpub = e0 + i < npub ? w : wpub;
     }
   }
   SkState out;
   out.passes = passes;
   out.wr = w;
+  out.pub = wpub;
   out.in = f_in;
   out.keep = f_keep;
   if (act) {
@@ -300,35 +361,53 @@ static __device__ __noinline__ SkState sk_select_impl(uint32_t q_base, uint32_t 
 // (by value in, by value out: references would pin the caller's cursor and floors in local memory)
 __device__ __forceinline__ void sk_select(SkQueue& q, SkFloor& floor, int limit, unsigned int* stat, SkProf* prof = nullptr) {
   const long long t0 = (prof && prof->on) ? clock64() : 0;
-  const SkState s = sk_select_impl(q.base, q.wr, floor.in, floor.keep, limit, stat);
+  const SkState s = sk_select_impl(q.base, q.wr, q.pub, floor.in, floor.keep, limit, stat);
   if (prof && prof->on) {
     prof->sel += clock64() - t0;
     prof->passes += s.passes;
     prof->selects += 1;
   }
   q.wr = s.wr;
+  q.pub = s.pub;
   floor.in = s.in;
   floor.keep = s.keep;
 }
 
-// Filter one chunk of 32 accumulator columns into the queue.  Once a floor is in place most chunks hold no survivor in
-// any of the 32 rows of the warp: a pass mask (2 instructions per value) decides whether the append runs at all.
+// Filter one chunk of 32 accumulator columns into the queue.  Straight-line code wherever possible: a lone warp per
+// scheduler runs dependent, branchy code at a fraction of its issue rate (measured: a data-dependent loop over the
+// survivors ~150 cycles per survivor, a chunk-maximum gate in front of the append +100 cycles per chunk, the branch-free
+// store-all ~20 cycles per value).  A crowded queue (some lane above kSkQueue - kChunk) is compacted first when the
+// floor has risen since its entries were taken (`floor_seen`); otherwise the saturating append runs.
 __device__ __forceinline__ void sk_filter_chunk(SkQueue& q, const uint32_t (&r)[kChunk], int nv, int col_chunk,
-                                                SkFloor& floor, unsigned int* stat, SkProf* prof = nullptr) {
-  if (!__any_sync(0xffffffffu, pass_mask(r, floor.in, nv) != 0u)) return;
-  if (__reduce_max_sync(0xffffffffu, q.count()) <= kSkQueue - kChunk) {
+                                                SkFloor& floor, float& floor_seen, unsigned int* stat,
+                                                SkProf* prof = nullptr) {
+  bool roomy = __reduce_max_sync(0xffffffffu, q.count()) <= kSkQueue - kChunk;
+  if (!roomy && __any_sync(0xffffffffu, floor.keep > floor_seen)) {
+    sk_compact(q, floor.keep);
+    floor_seen = floor.keep;
+    roomy = __reduce_max_sync(0xffffffffu, q.count()) <= kSkQueue - kChunk;
+  }
+  if (roomy) {
     if (nv >= kChunk) sk_append_roomy<true>(q, r, nv, col_chunk, floor.in);
     else sk_append_roomy<false>(q, r, nv, col_chunk, floor.in);
     return;
   }
+  // half a chunk at a time needs only 16 free slots: keeps rows with few lists (20..40 live entries) on the fast form
   const uint32_t wr0 = q.wr;
+  if (__reduce_max_sync(0xffffffffu, q.count()) <= kSkQueue - kChunk / 2) {
+    sk_append_roomy<false, 0, kChunk / 2>(q, r, nv, col_chunk, floor.in);
+    if (__reduce_max_sync(0xffffffffu, q.count()) <= kSkQueue - kChunk / 2) {
+      sk_append_roomy<false, kChunk / 2, kChunk>(q, r, nv, col_chunk, floor.in);
+      return;
+    }
+    q.wr = wr0;   // the second half may not fit: take the whole chunk through the saturating form
+  }
   if (prof) prof->crowded += 1;
   if (sk_append_sat(q, r, nv, col_chunk, floor.in)) return;
   q.wr = wr0;                                   // a lane ran out of slots: rewind, make room, redo the chunk
-  const long long t0 = (prof && prof->on) ? clock64() : 0;
   sk_compact(q, floor.keep);
-  if (prof && prof->on) prof->cmp += clock64() - t0;
   if (__any_sync(0xffffffffu, q.count() > kSkQueue - kChunk)) sk_select(q, floor, kSkSelectTo, stat, prof);
+  floor_seen = floor.keep;
   sk_append_roomy<false>(q, r, nv, col_chunk, floor.in);
 }
 

@@ -621,8 +621,7 @@ int launch_topk_merge(const MergeArgs& args, cudaStream_t stream) {
     return set_error(HGR_ERR_BAD_ARG, "topk merge: speculative lists need X / bank / the schedule for the exact repair");
   const int blocks = static_cast<int>((args.B + kMergeWarps - 1) / kMergeWarps);
   const int64_t cand = args.P * args.KL;  // candidates per row (upper bound)
-  static const bool force_pway = getenv("HGR_MERGE_PWAY") != nullptr;
-  if (cand <= 320 && !force_pway) {
+  if (cand <= 320) {
     if (cand <= 128) topk_select_kernel<4><<<blocks, kMergeWarps * 32, 0, stream>>>(args);
     else if (cand <= 192) topk_select_kernel<6><<<blocks, kMergeWarps * 32, 0, stream>>>(args);
     else topk_select_kernel<10><<<blocks, kMergeWarps * 32, 0, stream>>>(args);

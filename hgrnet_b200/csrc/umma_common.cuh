@@ -1,5 +1,5 @@
-// Device-side pieces shared by the single-CTA (score_umma.cu) and CTA-pair (score_umma2.cu) tcgen05 kernels:
-// tile walker over the stream-K-style schedule, kernel parameters and the fused top-k epilogue.
+// Device-side pieces of the tcgen05 scoring kernel (score_pair.cu): kernel parameters and the deferred-insert top-K
+// epilogue (sorted per-row lists).  The work split lives in sched.cuh, the floor-sketch epilogue in sketch_epi.cuh.
 #pragma once
 #include <cuda.h>
 
@@ -19,7 +19,8 @@ constexpr int kEpiWarp0 = 2;
 constexpr int kTmemCols = 512;
 constexpr int kChunk = 32;                          // accumulator columns per tcgen05.ld
 
-enum EpiMode { kEpiDense = 0, kEpiTopkReload = 1, kEpiTopkQueue = 2, kEpiNull = 3, kEpiTopkDefer = 4, kEpiSketch = 5 };
+enum EpiMode { kEpiDense = 0, kEpiNull = 3, kEpiTopkDefer = 4, kEpiSketch = 5 };
+enum Variant { kVarProd = 0, kVarExact = 2, kVarNull = 3, kVarSketch = 10 };   // impl code - HGR_IMPL_TCGEN05
 
 // SubTile / TileWalker (the walk of one worker over its chunk of the schedule) live in sched.cuh: plain integer
 // arithmetic, shared with the host-side unit test of the schedule (tests/test_cpu_sched.py).
@@ -40,28 +41,11 @@ struct Params {
   unsigned long long* timeline;  // optional [CTA][24] %globaltimer stamps (HGR_TIMELINE=1), else nullptr
   int rem_first;       // sub-tile order inside a segment: remainder first (1) or last (0)
   int stages;          // operand ring depth of the CTA-pair kernel (set by its launcher)
-  // resident-A kernel (score_resident.cu)
-  int kb_tmem;         // K blocks of A held in tensor memory (the first kb_tmem of the K loop)
-  int a_slots;         // K blocks of A held in shared memory
-  int sub_n;           // bank rows per sub-tile = columns of one accumulator buffer
-  int b_stage_bytes;   // bytes of one K block of a CTA's bank half sub-tile (sub_n / 2 rows x 64 bf16)
-  int stage_kb;        // K blocks per bank ring stage
-  int prefetch;        // L2 prefetch of the next sub-tile's bank boxes
   // floor-sketch epilogue (sketch_epi.cuh); stats[1] = launch epoch of the workspace, stats[2] = finished CTAs
   uint2* sk_part;                  // [slots][B][kSkCap] (value bits, bank row)
   int32_t* sk_cnt;                 // [slots][B] entries of each list
   unsigned long long* sk_floors;   // [B][kSkSlots] (epoch << 32 | order key)
 };
-
-// Geometry of the resident-A kernel for an embedding width (host side).
-struct ResGeom {
-  int nkb, kb_tmem, a_slots, sub_n, b_stage_bytes, stage_kb, stages;
-  size_t smem;
-};
-bool resident_supported(int64_t D);
-ResGeom resident_geom(int64_t D, int epi);
-int launch_resident_kernel(int epi, int KL, const CUtensorMap& mx, const CUtensorMap& mb, const Params& p,
-                           const ResGeom& g, cudaStream_t stream);
 
 constexpr int kTimelineSlots = 32;
 constexpr int kWsHeaderBytes = 64 + 256 * kTimelineSlots * 8;  // statistics + timeline stamps in front of the partial lists
@@ -110,56 +94,15 @@ __device__ __forceinline__ void scan_chunk_reload(SortedList<KL>& list, const ui
   }
 }
 
-template <int KL, int J>
-struct SeedPrefix {  // unconditional inserts of columns 0..J-1 into an empty list, slot depth growing with j
-  static __device__ __forceinline__ void run(SortedList<KL>& list, const uint32_t (&r)[kChunk], int col_chunk) {
-    SeedPrefix<KL, J - 1>::run(list, r, col_chunk);
-    list.template insert_prefix<(J < KL ? J : KL)>(__uint_as_float(r[J - 1]), col_chunk + J - 1);
-  }
-};
-template <int KL>
-struct SeedPrefix<KL, 0> {
-  static __device__ __forceinline__ void run(SortedList<KL>&, const uint32_t (&)[kChunk], int) {}
-};
-
-// qaddr: shared-space byte address of this thread's column of the [kChunk][epilogue threads] fp32 staging
-// array; QSTRIDE_B: bytes between consecutive entries of one thread.  Columns < JSTART are skipped (already
-// seeded into the list).
-// Warm-up floor of a segment.  A list that starts empty accepts everything, and the insert body is what the
-// epilogue pays for (ALU pipe).  Before scanning the first sub-tile of a segment the warp therefore takes one
-// cheap extra pass over its chunks of that sub-tile (TMEM is re-readable): KL interleaved running maxima, one
-// FMNMX per value, no divergence.  Their minimum tau is a value that at least KL columns of this list's stream
-// reach, i.e. a valid lower bound of the list's final KL-th entry, so everything below tau can be dropped up
-// front without touching the certificate argument (dropped <= final last entry).  Returns the largest float
-// below tau (ties with tau must still enter), or -inf when the sub-tile is too small to fill every group.
-template <int KL, int WPQ>
-__device__ __forceinline__ float warmup_floor(uint32_t taddr, int member, int nvalid) {
-  if (nvalid - member * kChunk < kChunk) return -INFINITY;  // this warp's first chunk is ragged: skip
-  float gm[KL];
-#pragma unroll
-  for (int g = 0; g < KL; ++g) gm[g] = -INFINITY;
-  for (int c0 = member * kChunk; c0 < nvalid; c0 += WPQ * kChunk) {
-    uint32_t r[kChunk];
-    ptx::tmem_ld_x32(taddr + c0, r);
-    ptx::tmem_ld_wait();
-    const int nv = nvalid - c0;
-#pragma unroll
-    for (int j = 0; j < kChunk; ++j) {
-      const float x = (nv >= kChunk || j < nv) ? __uint_as_float(r[j]) : -INFINITY;
-      gm[j % KL] = fmaxf(gm[j % KL], x);
-    }
-  }
-  float tau = gm[0];
-#pragma unroll
-  for (int g = 1; g < KL; ++g) tau = fminf(tau, gm[g]);
-  return nextafterf(tau, -INFINITY);
-}
-
-// Tighter variant: G = KL / 2 interleaved groups, each tracking its TWO largest values (3 FMNMX per value).
-// tau = the smallest runner-up: at least 2 * G = KL columns reach it, so it is as valid a floor as the one above,
-// but it sits much closer to the true KL-th value (for KL = 8 over 256 columns ~14 values survive it instead of
-// ~21, and the worst lane of a warp -- what the lock-step drain pays for -- ~26 instead of ~42).  Full chunks
-// only: a ragged tail chunk is simply left out (any subset of the stream gives a valid bound).
+// Warm-up floor of a segment.  A list that starts empty accepts everything, and the insert body is what the epilogue
+// pays for (ALU pipe).  Before scanning the first sub-tile of a segment the warp therefore takes one cheap extra pass
+// over that sub-tile (TMEM is re-readable): G = KL / 2 interleaved groups, each tracking its TWO largest values
+// (3 FMNMX per value, no divergence).  tau = the smallest runner-up is reached by at least 2 * G = KL columns, i.e. it
+// is a valid lower bound of the list's final KL-th entry, so everything below tau can be dropped up front without
+// touching the certificate argument (dropped <= final last entry).  For KL = 8 over 256 columns ~14 values survive;
+// the worst lane of a warp -- what the lock-step drain pays for -- ~26.  Full chunks only: a ragged tail chunk is
+// simply left out (any subset of the stream gives a valid bound).  Returns the largest float below tau (ties with
+// tau must still enter), or -inf when the sub-tile is too small to fill every group.
 template <int KL>
 __device__ __forceinline__ float warmup_floor_pairs(uint32_t taddr, int nvalid) {
   constexpr int G = KL / 2;
@@ -183,41 +126,6 @@ __device__ __forceinline__ float warmup_floor_pairs(uint32_t taddr, int nvalid) 
 #pragma unroll
   for (int g = 1; g < G; ++g) tau = fminf(tau, lo[g]);
   return nextafterf(tau, -INFINITY);
-}
-
-// Scan one chunk of 32 accumulator columns of this thread's row.
-// row_addr: shared-space byte address of this thread's private 128-byte staging row; swz = thread id & 7.
-// 1) the 32 values are parked in the staging row with eight unconditional 128-bit stores (XOR-swizzled so
-//    that a warp's stores are conflict free) and a bit mask of the values that beat the current threshold is
-//    built with four independent OR chains -- no per-value predicated store, no pointer-bump dependency chain;
-// 2) dense drain: lanes walk their own masks in lock-step, so the (long) insert body runs max_lane(popc) times
-//    instead of once per column any lane hit; the value is re-read from the staging row by its column.
-template <int KL>
-__device__ __forceinline__ void scan_chunk_queue(SortedList<KL>& list, const uint32_t (&r)[kChunk], int nv,
-                                                 int col_chunk, uint32_t row_addr, uint32_t swz, float floor_thr,
-                                                 EpiClock& ck) {
-  const float thr = fmaxf(list.thr(), floor_thr);
-#pragma unroll
-  for (int q = 0; q < kChunk / 4; ++q)
-    ptx::st_shared_v4(row_addr + ((static_cast<uint32_t>(q) ^ swz) << 4), r[4 * q], r[4 * q + 1], r[4 * q + 2],
-                      r[4 * q + 3]);
-  uint32_t m4[4] = {0u, 0u, 0u, 0u};
-#pragma unroll
-  for (int j = 0; j < kChunk; ++j)
-    if (__uint_as_float(r[j]) > thr) m4[j >> 3] |= (1u << j);
-  uint32_t m = (m4[0] | m4[1]) | (m4[2] | m4[3]);
-  if (nv < kChunk) m &= (1u << nv) - 1u;  // ragged tail: columns >= C were zero-filled by TMA, drop them
-  const int maxc = __reduce_max_sync(0xffffffffu, __popc(m));
-  ck.lap(ck.scan);
-  for (int e = 0; e < maxc; ++e) {
-    if (m != 0u) {
-      const uint32_t j = __ffs(m) - 1;
-      m &= m - 1;
-      const float x = ptx::ld_shared_f32(row_addr + (((j >> 2) ^ swz) << 4) + ((j & 3u) << 2));
-      if (x > list.thr()) list.insert(x, col_chunk + static_cast<int>(j));
-    }
-  }
-  ck.lap(ck.drain);
 }
 
 // ---- deferred-insert epilogue -------------------------------------------------------------------------------
@@ -294,13 +202,9 @@ __device__ __forceinline__ void cand_drain(SortedList<KL>& list, CandQueue<NTHR,
   q.wr = q.base;
 }
 
-// CTA-pair kernel (score_umma2.cu)
-// wpq = epilogue warps per TMEM lane quarter (1 or 2).  The epilogue is bound by the ALU pipe (FSETP / FSEL /
-// SEL issue every other cycle per sub-partition), not by latency, so ONE warp per quarter keeping ONE list per
-// row is the cheapest arrangement: a second warp would halve each stream and pay the list warm-up twice.
-int pair_wpq(int KL);
+// score_pair.cu
 int pair_ring_depth(int64_t B);   // operand stages of the production (deferred-insert) kernel for a batch size
-int launch_pair_kernel(int epi, int KL, int wpq, const CUtensorMap& mx, const CUtensorMap& mb, const Params& p,
+int launch_pair_kernel(int epi, int KL, const CUtensorMap& mx, const CUtensorMap& mb, const Params& p,
                        cudaStream_t stream);
 
 }  // namespace umma

@@ -106,7 +106,7 @@ class _RawCuda:
         self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
 
 
-X_SLOTS = 2  # feature-ingest slots per exchange (two batches of a channel in flight are provably enough)
+X_SLOTS = 4  # feature-ingest slots per exchange (ring length per channel: _ring_len)
 
 
 def exchange_layout(B: int, K: int, world: int, slots: int, D: int = 0):
@@ -271,6 +271,15 @@ class PeerExchange:
             self._own = None
 
 
+def _ring_len(n_c: int, slots: int) -> int:
+    """Ring length <= slots for a channel that runs n_c >= 2 batches per replay: consecutive batches, including the
+    last one of a replay and the first one of the next, must use different slots: (n_c - 1) % ring != 0."""
+    for ring in range(slots, 1, -1):
+        if (n_c - 1) % ring != 0:
+            return ring
+    raise ValueError("no safe slot ring for %d batches per channel" % n_c)
+
+
 class ShardedEvalStream:
     """Software-pipelined, CUDA-graph captured class-sharded eval steps (one process per GPU).
 
@@ -290,7 +299,7 @@ class ShardedEvalStream:
 
     def __init__(self, bank_shard: torch.Tensor, id_base: int, *, batch: int, K: int = 20, steps: int = 8,
                  feat_dtype=torch.float32, banks=None, group=None, use_graph: bool = True, exchange: str = "p2p",
-                 channels: int = 4, host_io: bool = False):
+                 channels: int = 4, host_io: bool = False, col_id: Optional[torch.Tensor] = None):
         if exchange not in ("p2p", "nccl"):
             raise ValueError("exchange must be 'p2p' or 'nccl'")
         if host_io and exchange != "p2p":
@@ -299,6 +308,7 @@ class ShardedEvalStream:
         self.device = bank_shard.device
         self.banks = list(banks) if banks is not None else [bank_shard]
         self.id_base, self.K, self.B, self.steps, self.group = id_base, K, batch, steps, group
+        self.col_id = col_id          # node id of every bank row of this shard (None: id_base + row)
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         D = bank_shard.shape[1]
         if not host_io:
@@ -313,9 +323,20 @@ class ShardedEvalStream:
             # `channels` independent exchanges (own flags, counters, slots), one CUDA stream each: batch s runs on
             # channel s % channels, so the normalise / merge kernels of one batch fill the SMs the persistent GEMM
             # of the neighbouring batch leaves idle at its edges
-            self.channels = max(1, min(channels, steps))
+            # Slot reuse: a producer may overwrite a list slot of batch j once the owner has merged batch j, which it
+            # knows from the owner's NEXT signal -- so two consecutive batches of a channel must never share a slot,
+            # also across the replay boundary (a replay restarts at slot 0).  Every channel therefore gets at least two
+            # batches per replay and a ring length `_ring[c]` that its batch count does not wrap onto itself with.
+            if steps < 2:
+                raise ValueError("ShardedEvalStream needs steps >= 2 (two batches per exchange channel and replay)")
+            self.channels = max(1, min(channels, steps // 2))
             self.pxs = [PeerExchange(batch, K, self.device, group=group, slots=self.slots, D=D if host_io else 0)
                         for _ in range(self.channels)]
+            self._ring, self._xring = [], []
+            for c in range(self.channels):
+                n_c = (steps - c + self.channels - 1) // self.channels          # batches of channel c per replay
+                self._ring.append(_ring_len(n_c, self.slots))
+                self._xring.append(_ring_len(n_c, X_SLOTS))
             self.px = self.pxs[0]
             self.side = [torch.cuda.Stream(device=self.device) for _ in range(self.channels)]
             self.row_lo, self.row_hi = self.px.lo, self.px.hi
@@ -368,16 +389,18 @@ class ShardedEvalStream:
         if self.host_io:
             px, j = self.pxs[s % self.channels], s // self.channels
             self.dev_pack[s].copy_(self.host_pack[s], non_blocking=True)
-            x = px.ingest(self.dev_feats[s], j % X_SLOTS)
-            px.scatter(x, bank, self.id_base, j % self.slots)
+            x = px.ingest(self.dev_feats[s], j % self._xring[s % self.channels])
+            px.scatter(x, bank, self.id_base, j % self._ring[s % self.channels], col_id=self.col_id)
             return None
         x = ops.normalize_rows(self.dev_feats[s])
         if self.exchange == "p2p":
-            self.pxs[s % self.channels].scatter(x, bank, self.id_base, (s // self.channels) % self.slots)
+            self.pxs[s % self.channels].scatter(x, bank, self.id_base, (s // self.channels) % self._ring[s % self.channels],
+                                                col_id=self.col_id)
             return None
         if bank.shape[0] > 0:
             # results go straight into the send record (no pack copies)
-            ops.score_topk(x, bank, id_base=self.id_base, K=self.K, out=(self.send[s][0].view(torch.float32), self.send[s][1]))
+            ops.score_topk(x, bank, col_id=self.col_id, id_base=self.id_base, K=self.K,
+                           out=(self.send[s][0].view(torch.float32), self.send[s][1]))
         else:
             self.send[s][0].copy_(torch.full((self.B, self.K), float("-inf"), device=self.device).view(torch.int32))
             self.send[s][1].fill_(-1)
@@ -389,7 +412,7 @@ class ShardedEvalStream:
 
     def _merge(self, s: int, work):
         if self.exchange == "p2p":
-            self.pxs[s % self.channels].merge((s // self.channels) % self.slots, self.dev_labels[s], self.hits,
+            self.pxs[s % self.channels].merge((s // self.channels) % self._ring[s % self.channels], self.dev_labels[s], self.hits,
                                               out=(self.val[s], self.idx[s]), targets_local=self.host_io)
             if self.host_io:
                 self.host_hits[s].copy_(self.hits, non_blocking=True)

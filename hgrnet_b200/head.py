@@ -104,7 +104,22 @@ class tree_model(nn.Module):
         self.train_index = torch.tensor([index[c] for c in candidates_train], dtype=torch.long, device=self.device)
         self.test_index = torch.tensor([index[c] for c in candidates_test], dtype=torch.long, device=self.device)
         self._train_ids_host = [index[c] for c in candidates_train]
-        self._test_index_i32 = self.test_index.to(torch.int32)
+        # Row order of the test-class bank (kernel 2's B operand).  The reference's `nodes` order is graph order --
+        # siblings adjacent and similar -- so an image's top-20 concentrate in a few adjacent bank rows, the one
+        # case the narrow speculative lists of the scoring kernel are slow for (exact, but repaired on the CUDA
+        # cores).  A fixed pseudo-random permutation of the bank rows makes their order independent of the hierarchy;
+        # `_test_index_i32` (the kernel's col_id) maps bank rows back to node ids, so nothing else changes -- except
+        # that exact ties resolve by permuted row instead of by test_index position (torch.topk's tie order is
+        # unspecified anyway, main.py:138).  `opts.hgr_permute_bank = False` keeps test_index order.
+        C = self.test_index.numel()
+        if getattr(opts, "hgr_permute_bank", True) and C > 1:
+            perm = torch.randperm(C, generator=torch.Generator().manual_seed(0x48475221)).to(self.device)
+        else:
+            perm = torch.arange(C, device=self.device)
+        self._bank_order = self.test_index[perm]                         # node id of bank_test row j
+        self._test_index_i32 = self._bank_order.to(torch.int32)
+        self._bank_dst = torch.full((len(self.nodes),), -1, dtype=torch.int32, device=self.device)
+        self._bank_dst[self._bank_order] = torch.arange(C, dtype=torch.int32, device=self.device)   # node -> bank row
         self.max_depth = max(self.d2n.keys())
 
         if self.opts.weights == "adaptive":
@@ -154,28 +169,50 @@ class tree_model(nn.Module):
 
     # ------------------------------------------------------------------ class bank
     def _bank_csr(self):
-        if getattr(self.opts, "hgr_bank", "node") != "chain":
+        """CSR of the hierarchy-aggregated bank (north_star's extension; SURVEY section 0: the reference's own bank is the
+        identity CSR).  `opts.hgr_bank`: "node" (default, = reference), "chain" -- row c aggregates the last
+        ceil(out_ratio * len) nodes of c2p[c] + [c], deepest first, with the `--weights` level weights (the node set
+        and weights the OM loop uses, clip_tree.py:232-237 / :198-219) -- or "family": the chain plus the direct
+        children of c, which share a total weight of `in_ratio` (the descendant side)."""
+        mode = getattr(self.opts, "hgr_bank", "node")
+        if mode == "node":
             return None
+        if mode not in ("chain", "family"):
+            raise ValueError("opts.hgr_bank must be node, chain or family, got %r" % (mode,))
         lw = self._layer_weight_host()
         rp, col, w = self.hierarchy.chain_csr(self.opts.out_ratio,
-                                              lambda n: level_weights(self.opts.weights, n, lw).numpy())
+                                              lambda n: level_weights(self.opts.weights, n, lw).numpy(),
+                                              include_children=mode == "family", child_weight=float(self.opts.in_ratio))
         to = lambda a: torch.from_numpy(a).to(self.device)
         return to(rp), to(col), to(w)
 
     def update_classifier(self, chunk: int = 4096):
-        """clip_tree.py:318-325.  Text features are encoded in chunks (the reference: two halves) and
-        normalised -- or hierarchy-aggregated and normalised -- by kernel (1) into the bf16 bank."""
+        """clip_tree.py:318-325.  The reference encodes the prompts in two halves, concatenates and normalises.
+        Here every chunk of text features is normalised by kernel (1) STRAIGHT INTO its rows of the bf16 all-node bank
+        and, in the same pass, into its (permuted) rows of the test-class bank (`hgr_normalize_rows_dual`): no
+        concatenated copy of the text table, no second read.  With `--hgr_bank chain` the rows are hierarchy-aggregated
+        (CSR over ancestors), which needs the whole text table first."""
         with torch.no_grad():
             N = len(self.nodes)
-            feats = []
-            for s in range(0, N, chunk):
-                feats.append(self.clip_model.encode_text(self.node_tokens[s:s + chunk]))
-            text = torch.cat(feats) if len(feats) > 1 else feats[0]
             csr = self._bank_csr()
             if csr is None:
-                self.zsl_weights = ops.aggregate_normalize(text)
-                self.bank_test = ops.aggregate_normalize(text, row_map=self._test_index_i32)
+                zsl = bank = None
+                for s in range(0, N, chunk):
+                    feats = self.clip_model.encode_text(self.node_tokens[s:s + chunk])
+                    if zsl is None:
+                        D = feats.shape[1]
+                        zsl = torch.empty((N, D), dtype=torch.bfloat16, device=self.device)
+                        bank = torch.empty((self._bank_order.numel(), D), dtype=torch.bfloat16, device=self.device)
+                    e = s + feats.shape[0]
+                    ops.normalize_rows_dual(feats, zsl[s:e], self._bank_dst[s:e], bank)
+                self.zsl_weights, self.bank_test = zsl, bank
             else:
+                text = None
+                for s in range(0, N, chunk):
+                    feats = self.clip_model.encode_text(self.node_tokens[s:s + chunk])
+                    if text is None:
+                        text = torch.empty((N, feats.shape[1]), dtype=feats.dtype, device=self.device)
+                    text[s:s + feats.shape[0]] = feats
                 rp, col, w = csr
                 self.zsl_weights = ops.aggregate_normalize(text, rp, col, w)
                 self.bank_test = ops.aggregate_normalize(text, rp, col, w, row_map=self._test_index_i32)

@@ -11,12 +11,13 @@ from typing import Optional, Tuple
 import torch
 
 from . import _cabi
-from ._cabi import (HGR_IMPL_AUTO, HGR_IMPL_SIMT, HGR_IMPL_TCGEN05, HGR_IMPL_TCGEN05_RELOAD,  # noqa: F401
-                    HGR_IMPL_TCGEN05_EXACT, HGR_IMPL_TCGEN05_NULL, HGR_IMPL_TCGEN05_1CTA, HGR_IMPL_TCGEN05_1CTA_NULL,
+from ._cabi import (HGR_IMPL_AUTO, HGR_IMPL_SIMT, HGR_IMPL_TCGEN05,  # noqa: F401
+                    HGR_IMPL_TCGEN05_EXACT, HGR_IMPL_TCGEN05_NULL, HGR_IMPL_TCGEN05_SKETCH,
                     HGR_NUM_HITS)
 
 _DTYPE_CODE = {torch.float32: _cabi.HGR_F32, torch.bfloat16: _cabi.HGR_BF16, torch.float16: _cabi.HGR_F16}
 _workspaces = {}
+_retired = []   # outgrown workspaces, kept alive for graphs that captured them
 
 
 def _stream() -> int:
@@ -39,6 +40,11 @@ def _workspace(nbytes: int, device) -> torch.Tensor:
     key = (device.type, device.index, torch.cuda.current_stream().cuda_stream)
     ws = _workspaces.get(key)
     if ws is None or ws.numel() < nbytes:
+        if ws is not None:
+            # a CUDA graph captured on this stream may have baked the old pointer in (EvalStream, ShardedEvalStream;
+            # torch hands out pooled stream handles, so another stream object can land on the same key): never free a
+            # workspace that has been handed out
+            _retired.append(ws)
         ws = torch.zeros(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)   # header words (epoch, counters) start at 0
         _workspaces[key] = ws
     return ws
@@ -94,6 +100,28 @@ def aggregate_normalize(E: torch.Tensor, rowptr: Optional[torch.Tensor] = None,
 def normalize_rows(x: torch.Tensor, out_dtype=torch.bfloat16, return_norm: bool = False):
     """Row L2-normalise (``x / x.norm(dim=-1, keepdim=True)``, model/clip_tree.py:330)."""
     return aggregate_normalize(x, out_dtype=out_dtype, return_norm=return_norm)
+
+
+def normalize_rows_dual(E: torch.Tensor, out: torch.Tensor, dst_map: Optional[torch.Tensor] = None,
+                        out2: Optional[torch.Tensor] = None) -> None:
+    """One pass of the bank refresh (clip_tree.py:318-325 + main.py:136): ``out[r] = E[r] / |E[r]|`` (``out``: the
+    chunk's rows of the all-node bf16 bank, written in place) and, where ``dst_map[r] >= 0``, the same row into
+    ``out2[dst_map[r]]`` (the test-class bank in its own row order)."""
+    lib = _cabi.load()
+    E = _require(E, "E")
+    if E.dtype not in _DTYPE_CODE:
+        raise TypeError("E dtype %s not supported" % E.dtype)
+    n, D = E.shape
+    if out.dtype != torch.bfloat16 or tuple(out.shape) != (n, D) or not out.is_contiguous() or not out.is_cuda:
+        raise ValueError("out must be a contiguous CUDA bf16 [n, D] tensor (a row slice of the bank)")
+    if (dst_map is None) != (out2 is None):
+        raise ValueError("dst_map and out2 go together")
+    if dst_map is not None:
+        dst_map = _require(dst_map, "dst_map", torch.int32)
+        if dst_map.numel() != n or out2.dtype != torch.bfloat16 or out2.shape[1] != D or not out2.is_contiguous():
+            raise ValueError("dst_map [n] int32 / out2 bf16 [*, D] contiguous expected")
+    _cabi.check(lib.hgr_normalize_rows_dual(_ptr(E), _DTYPE_CODE[E.dtype], n, D, _ptr(out), _ptr(dst_map), _ptr(out2),
+                                            _stream()))
 
 
 def score_topk(X: torch.Tensor, bank: torch.Tensor, *, col_id: Optional[torch.Tensor] = None, id_base: int = 0,

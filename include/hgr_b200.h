@@ -47,15 +47,14 @@ extern "C" {
 /* implementation selector of hgr_score_topk (all compute the same result) */
 #define HGR_IMPL_AUTO 0
 #define HGR_IMPL_SIMT 1     /* CUDA-core kernel: any shape, exactness fallback and debug aid */
-#define HGR_IMPL_TCGEN05 2  /* TMA + tcgen05/TMEM CTA-pair kernel (cta_group::2) with fused top-k epilogue */
-#define HGR_IMPL_TCGEN05_RELOAD 3 /* single-CTA kernel, simplest epilogue, exact lists (kept as a cross-check) */
-#define HGR_IMPL_TCGEN05_EXACT 4  /* production kernel with speculation off: every list holds K entries */
+#define HGR_IMPL_TCGEN05 2  /* production: TMA + tcgen05/TMEM CTA-pair kernel (cta_group::2), fused top-k epilogue with
+                             * deferred-insert lists; narrow (speculative) lists where provably cheap, certified and
+                             * repaired exactly by the merge kernel */
+#define HGR_IMPL_TCGEN05_EXACT 4  /* the same kernel with speculation off: every list holds K entries */
 #define HGR_IMPL_TCGEN05_NULL 5   /* diagnostics: production main loop, trivial epilogue; outputs untouched */
-#define HGR_IMPL_TCGEN05_1CTA 6   /* single-CTA (cta_group::1) kernel with the production epilogue */
-#define HGR_IMPL_TCGEN05_1CTA_NULL 7 /* diagnostics: single-CTA main loop, trivial epilogue */
-#define HGR_IMPL_TCGEN05_STREAM 10      /* round-1 CTA-pair kernel (A re-streamed per sub-tile), for comparison */
-#define HGR_IMPL_TCGEN05_STREAM_NULL 11 /* its main loop with a trivial epilogue */
-#define HGR_IMPL_TCGEN05_SKETCH 12      /* streaming CTA-pair main loop + floor-sketch epilogue (exact, order-independent) */
+#define HGR_IMPL_TCGEN05_SKETCH 12 /* the same main loop with the floor-sketch epilogue (K <= 20): unsorted candidate lists
+                                    * filtered against a per-row floor shared by all workers through global memory --
+                                    * exact by construction, cost independent of the bank order (no repair pass) */
 /* OR-ed into `impl`: run only the GEMM + fused top-k kernel and leave the per-CTA partial lists in
  * the workspace (outputs untouched).  Lets bench.py time the dominant kernel alone for the roofline. */
 #define HGR_IMPL_FLAG_NO_MERGE 0x100
@@ -87,6 +86,16 @@ int hgr_aggregate_normalize(const void* E, int e_dtype, int64_t n_src, int64_t D
                             const int32_t* rowptr, const int32_t* col, const float* w,
                             int64_t n_rows, const int32_t* row_map, int64_t n_out,
                             void* out, int out_dtype, float* out_norm, void* stream);
+
+/*
+ * Bank refresh in ONE pass (model/clip_tree.py:318-325 + the `logits[:, test_index]` gather of main.py:136): a chunk
+ * of text features is row-normalised straight into its rows of the all-node bank `out` (bf16 [n_rows, D] -- pass the
+ * chunk's slice of `zsl_weights`), and every row r with dst_map[r] >= 0 is ALSO written to row dst_map[r] of `out2`,
+ * the test-class bank in its own (e.g. permuted) row order.  Replaces the reference's two halves + `torch.cat` +
+ * normalise and a second pass for the gathered bank.  dst_map / out2 may both be NULL.
+ */
+int hgr_normalize_rows_dual(const void* E, int e_dtype, int64_t n_rows, int64_t D, void* out, const int32_t* dst_map,
+                            void* out2, void* stream);
 
 /*
  * Fused eval head: logits = scale * X @ bank^T are produced tile by tile on the tensor

@@ -160,3 +160,18 @@ def test_peer_exchange_setup_failure_is_agreed_on_by_all_ranks(stage):
         assert [r[1] for r in res] == ["unavailable", "unavailable"], res
         if stage == "open":
             assert ("free", 0x1000) in res[0][3] and ("close", 0x100001) in res[0][3]    # the healthy rank cleaned up
+
+
+def test_exchange_slot_rings_never_reuse_a_slot_back_to_back():
+    """ShardedEvalStream: a producer may overwrite a list slot of batch j only after the owner's next signal, so two
+    consecutive batches of a channel -- including the last of one graph replay and the first of the next -- must use
+    different slots (hgrnet_b200.dist._ring_len)."""
+    from hgrnet_b200.dist import X_SLOTS, _ring_len
+    for slots in (4, X_SLOTS):
+        for n_c in range(2, 13):
+            ring = _ring_len(n_c, slots)
+            assert 2 <= ring <= slots
+            seq = [j % ring for j in range(n_c)] * 3            # three replays back to back
+            assert all(a != b for a, b in zip(seq, seq[1:])), (n_c, ring)
+    with pytest.raises(ValueError):
+        _ring_len(13, 4)

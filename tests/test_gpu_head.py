@@ -11,7 +11,7 @@ import pytest
 import torch
 
 from oracle import cases, hgr_oracle as orc
-from tests.util import bf16_input_atol, compare_topk
+from tests.util import bf16_input_atol, compare_topk, hits_from_idx
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -61,7 +61,11 @@ def test_eval_matches_reference_run(spec, tmp_path, golden, golden_dir, monkeypa
     got = model.zsl_weights[::step].float().cpu()
     ref = torch.from_numpy(z["bank_rows"])
     assert (got - ref).abs().max() <= 2 ** -8 * ref.abs().max()      # bf16 bank: half-ulp of the largest element
-    assert torch.equal(model.bank_test, model.zsl_weights[torch.tensor(test_ids, device=DEV)])
+    # the test-class bank: the same rows, written by the same pass, in the fixed pseudo-random order `_bank_order`
+    assert sorted(model._bank_order.tolist()) == sorted(test_ids)
+    assert model._bank_order.tolist() != sorted(test_ids) or len(test_ids) < 3
+    assert torch.equal(model.bank_test, model.zsl_weights[model._bank_order])
+    assert torch.equal(model._test_index_i32.long(), model._bank_order)
 
     # forward (clip_tree.py:328-333): dense logits of batch 0 vs the reference's
     logits = model(batches[0][0].to(DEV), None)
@@ -174,3 +178,39 @@ def test_main_cli_runs_eval_and_training_on_synthetic_data(tmp_path, monkeypatch
     main.main(["--train", "True", "--epochs", "1", "--weights", "adaptive", "--out_ratio", "0.5", "--test_after_train"] + common)
     out = capsys.readouterr().out
     assert "loss:" in out and "Model saved." in out and "Top@20(%):" in out
+
+
+@pytest.mark.parametrize("permute,mode", [(True, "chain"), (False, "chain"), (True, "family")])
+def test_update_classifier_chain_bank_matches_oracle(tmp_path, permute, mode):
+    """north_star's hierarchy-aggregated bank (`opts.hgr_bank = 'chain'`): row c = normalize(sum_j w_j * E[n_j]) over the
+    last ceil(out_ratio * len) nodes of c2p[c] + [c], deepest first, weighted like the OM loop weights its levels
+    (clip_tree.py:232-237, :198-219).  Model-level check of kernel (1)'s CSR path against the oracle's restatement,
+    and of the fused scorer on that bank."""
+    spec = cases.EVAL_CASES[0]
+    n_nodes = sum(spec["levels"])
+    test_ids = cases.test_ids(spec, n_nodes)
+    table = cases.text_table(spec, n_nodes, normalize=False)
+    model, h = _model(spec, tmp_path, table, test_ids, weights="increasing", out_ratio=0.5, in_ratio=0.25, hgr_bank=mode,
+                      hgr_permute_bank=permute)
+    model.update_classifier()
+    from hgrnet_b200.levels import level_weights
+    rp, col, w = h.chain_csr(0.5, lambda n: level_weights("increasing", n, None).numpy(),
+                             include_children=mode == "family", child_weight=0.25)
+    assert int(rp[-1]) > n_nodes                                   # rows really aggregate several nodes
+    if mode == "family":                                           # the children of node 0 share a weight of in_ratio
+        kids = h.p2c[0]
+        row0 = list(zip(col[rp[0]:rp[1]].tolist(), w[rp[0]:rp[1]].tolist()))
+        assert kids and abs(sum(x for c_, x in row0 if c_ in kids) - 0.25) < 1e-6
+    want = orc.aggregate_normalize(table, rp.tolist(), col.tolist(), w.tolist())
+    got = model.zsl_weights.float().cpu()
+    assert (got - want).abs().max() <= 2 ** -8 * want.abs().max()
+    assert torch.equal(model.bank_test, model.zsl_weights[model._bank_order])
+    if not permute:
+        assert model._bank_order.tolist() == test_ids
+    feats, label = cases.eval_batches(spec, test_ids)[0]
+    tg = torch.full((feats.shape[0],), label, dtype=torch.long, device=DEV)
+    hits = torch.zeros(5, dtype=torch.int64, device=DEV)
+    val, idx = model.score_topk(feats.to(DEV), tg, hits=hits)
+    ref_logits = orc.forward_logits(feats, want)[:, test_ids]
+    compare_topk(val, idx, ref_logits, test_ids, 20, rtol=1e-3, atol=2 * bf16_input_atol(spec["D"]))
+    assert hits.tolist() == hits_from_idx(idx, tg.cpu())

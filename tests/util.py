@@ -73,3 +73,47 @@ def oracle_hits(oracle_logits, col_ids, targets, cuts=(1, 2, 5, 10, 20)):
     K = min(max(cuts), oracle_logits.shape[1])
     oi = oracle_logits.topk(K, 1, True, True)[1]
     return hits_from_idx(torch.as_tensor(col_ids).long()[oi], targets, cuts)
+
+
+def _unit_bf16(w):
+    return (w / w.norm(dim=-1, keepdim=True).clamp_min(1e-12)).to(torch.bfloat16)
+
+
+def hostile_bank(C, D, kind, seed=3):
+    """Class banks whose row order is NOT random (what narrow speculative lists assume):
+    clustered -- siblings adjacent and similar (child = parent + noise, rows in tree order, like the reference's `nodes`);
+    ascending -- every image's logits rise along the bank;  equal -- all rows identical (every logit of a row ties);
+    dups -- 40 copies of every distinct row;  zeros -- mostly zero rows (padding) and a few real ones;  iid -- control."""
+    g = torch.Generator().manual_seed(seed)
+    if kind == "iid":
+        return _unit_bf16(torch.randn(C, D, generator=g))
+    if kind == "clustered":
+        centers = torch.randn((C + 63) // 64, D, generator=g)
+        return _unit_bf16(centers.repeat_interleave(64, 0)[:C] + 0.15 * torch.randn(C, D, generator=g))
+    if kind == "ascending":
+        base = torch.randn(1, D, generator=g)
+        t = torch.linspace(0.0, 1.0, C).unsqueeze(1)
+        return _unit_bf16(t * base + (1 - t) * torch.randn(1, D, generator=g) + 0.01 * torch.randn(C, D, generator=g))
+    if kind == "equal":
+        return _unit_bf16(torch.randn(1, D, generator=g).repeat(C, 1))
+    if kind == "dups":
+        return _unit_bf16(torch.randn((C + 39) // 40, D, generator=g)).repeat_interleave(40, 0)[:C].contiguous()
+    if kind == "zeros":
+        w = torch.zeros(C, D)
+        w[::97] = torch.randn(len(range(0, C, 97)), D, generator=g)
+        return _unit_bf16(w)
+    raise ValueError(kind)
+
+
+def hostile_queries(w, B, kind, seed=11):
+    """Image features that land in the hostile region of the bank (near a leaf / near the end); `w` on the device."""
+    g = torch.Generator(device=w.device).manual_seed(seed)
+    C, D = w.shape
+    if kind == "ascending":
+        x = w[-1:].float() + 0.02 * torch.randn(B, D, device=w.device, generator=g)
+    elif kind == "clustered":
+        pick = torch.randint(0, C, (B,), device=w.device, generator=g)
+        x = w[pick].float() + 0.3 * torch.randn(B, D, device=w.device, generator=g) / D ** 0.5
+    else:
+        x = torch.randn(B, D, device=w.device, generator=g)
+    return _unit_bf16(x)

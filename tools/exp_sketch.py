@@ -71,7 +71,7 @@ if __name__ == "__main__":
             kinds = ["iid", "clustered", "ascending", "equal", "dups", "zeros"] if B * C < 3e7 else ["iid", "clustered"]
             for kind in kinds:
                 check(B, C, D, kind)
-    for (B, C, D) in [(512, 21841, 1024), (4096, 21841, 1024), (1024, 10450, 512), (4096, 2731, 1024), (4096, 5461, 1024)]:
+    for (B, C, D) in [(512, 21841, 1024), (4096, 21841, 1024), (1024, 10450, 512), (4096, 2731, 1024), (4096, 5461, 1024)][:int(os.environ.get("HGR_EXP_SHAPES", "5"))]:
         nb = min(6, max(2, int(1.6 * 126e6 / (C * D * 2)) + 1))
         flops = 2.0 * B * C * D
         for kind in ("iid", "clustered"):

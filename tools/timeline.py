@@ -52,7 +52,7 @@ for (B, C, D, impl, tag) in CASES:
     if (tl[:, 24] > 0).any():
         for j in range(3):
             print("  scan loop of sub-tile %d: median %8.0f cycles" % (j, tl[:, 24 + j].float().median()))
-        for j, n in ((27, "select cycles"), (28, "compact cycles"), (29, "crowded chunks"), (30, "bisection passes"), (31, "selections")):
+        for j, n in ((27, "select cycles"), (28, "compact cycles"), (29, "crowded chunks"), (30, "bisection passes"), (31, "selections"), (14, "global floor reads"), (15, "  finite"), (23, "  raised the floor"), (21, "sub-tile 1 chunks"), (2, "  ld+wait cycles"), (3, "  filter cycles"), (22, "gate cycles (all)")):
             print("  warp 2: %-18s median %8.0f  mean %8.1f" % (n, tl[:, j].float().median(), tl[:, j].float().mean()))
     d = rel[:, 13] - rel[:, 0]
     print("  CTA lifetime     min %7.2f  median %7.2f  max %7.2f" % (d.min(), d.median(), d.max()))
