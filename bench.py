@@ -7,7 +7,9 @@ Metric (BASELINE.json): scored images/s at 21,841 classes.  A STEP is one pass o
 over one batch of synthetic image features: row-normalise the batch (kernel 1), fused
 logits + top-20 + Hit@k against the class bank (kernel 2 + merge).  N=1 runs BASELINE cfg 2
 (B=512, C=21,841, D=1024); N>1 runs the class-sharded sweep of cfg 5 (B=4096, bank row-sharded
-over the ranks, one all-gather per batch) -- ``config.workload`` names which.
+over the ranks) -- ``config.workload`` names which.  Because the two differ, the N=1 line also
+carries ``cfg5_single_gpu`` (cfg 5 on this one GPU) and every N>1 line ``single_gpu_same_workload``
+(cfg 5 with the whole bank on rank 0's GPU, measured in the same run) and ``speedup_vs_1gpu``.
 
 ``value``   device-timed throughput with inputs resident in HBM (CUDA events, max over ranks).
 ``e2e``     the same metric through the public API (``tree_model.score_topk``) with pinned HOST
@@ -38,6 +40,28 @@ WORKLOADS = {
 }
 K = 20
 METRIC = "scored images/sec @21,841 classes"
+
+
+def _config(wl, gpus):
+    """`config` of both arms (identical keys and values, so that the driver can match them); implementation details of
+    the GPU arm live in the separate `impl` object."""
+    return {"workload": wl["name"], "B": wl["B"], "C": wl["C"], "D": wl["D"], "K": K,
+            "l2": "GPU arm: inputs larger than L2 -- %d bank copies and 8 feature batches rotated, never the same "
+                  "operands in consecutive steps" % _n_bank(wl, gpus)}
+
+
+def _n_bank(wl, gpus):
+    if gpus > 1:
+        return 2
+    return max(2, -(-int(1.6 * 126e6) // (wl["C"] * wl["D"] * 2)))
+
+
+def _graph_steps(steps):
+    """Batches per CUDA graph of the class-sharded evaluator: a divisor of `steps`, so that exactly `steps` are timed."""
+    for d in (8, 10, 9, 7, 6, 5, 4, 3, 2):
+        if steps % d == 0:
+            return d
+    return steps if 2 <= steps <= 32 else 8
 
 
 def _peaks():
@@ -147,7 +171,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": args.gpus,
             "steps": steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
             "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": wl["name"], "B": wl["B"], "C": wl["C"], "D": wl["D"], "K": K},
+            "config": _config(wl, args.gpus),
             "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": "port",
                              "sample": "%d batches of %d images (one batch per step), torch CPU fp32" % (steps, wl["B"])},
             "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -196,9 +220,10 @@ def run_ours(args):
     torch.cuda.synchronize()
 
     # inputs larger than L2 (126 MB): rotate over several bank copies and feature batches
-    n_bank = max(2, -(-int(1.6 * 126e6) // (C * D * 2))) if world == 1 else 2
+    n_bank = _n_bank(wl, world)
     lo, hi = shard_bounds(C, world)[rank]
     shard = model.bank_test[lo:hi]
+    shard_ids = model._test_index_i32[lo:hi].contiguous()          # node id of every bank row of this shard
     banks = [shard.clone() for _ in range(n_bank)]
     n_feat = 8
     feats_host = [synthetic_embeddings(B, D, 100 + i, normalize=False).pin_memory() for i in range(n_feat)]
@@ -208,14 +233,14 @@ def run_ours(args):
                    for _ in range(n_feat)]
     labels_dev = [l.to(dev).to(torch.int32) for l in labels_host]
     hits = ops.new_hits(dev)
-    scorers = [ShardedScorer(b, None, id_base=lo, K=K) for b in banks] if world > 1 else None
+    scorers = [ShardedScorer(b, shard_ids, id_base=lo, K=K) for b in banks] if world > 1 else None
 
     pending = []
 
     def step_eager(i):
         x = ops.normalize_rows(feats_dev[i % n_feat])
         if world == 1:
-            ops.score_topk(x, banks[i % n_bank], targets=labels_dev[i % n_feat], K=K, hits=hits)
+            ops.score_topk(x, banks[i % n_bank], col_id=shard_ids, targets=labels_dev[i % n_feat], K=K, hits=hits)
         else:
             sc = scorers[i % n_bank]
             sc.submit(x, labels_dev[i % n_feat])
@@ -250,6 +275,22 @@ def run_ours(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t)
         return ms
+
+    def timed_blocks(fn, n, flush=None, begin=None, min_ms=60.0, max_blocks=400):
+        """`value` protocol: the block of exactly `n` steps is timed (device events, max over ranks) repeatedly until
+        >= min_ms of device time has been covered; the MEDIAN block decides.  A single 20-step block of this head is
+        under a millisecond -- too short for a stable clock."""
+        first = timed(fn, n, flush, begin)
+        blocks = [first]
+        reps = int(min(max_blocks, max(2, math.ceil(min_ms / max(first, 1e-3)))))
+        if world > 1:
+            t = torch.tensor([reps], device=dev)
+            dist.broadcast(t, 0)
+            reps = int(t)
+        for _ in range(reps - 1):
+            blocks.append(timed(fn, n, flush, begin))
+        blocks.sort()
+        return blocks[len(blocks) // 2], len(blocks), blocks[0], blocks[-1]
 
     def graphed(fn, n_variants, n_streams=1):
         """One CUDA graph per rotation index, replayed round-robin on `n_streams` streams (a step is a single
@@ -303,15 +344,16 @@ def run_ours(args):
         res_begin, res_end, hits_src = es_res.begin, es_res.end, es_res.hits
     else:
         from hgrnet_b200.dist import ShardedEvalStream
-        G_STEPS = 8
+        G_STEPS = _graph_steps(steps)
         from hgrnet_b200.dist import PeerMemoryUnavailable
         try:
-            ses = ShardedEvalStream(banks[0], lo, batch=B, K=K, steps=G_STEPS, banks=banks, exchange=args.exchange)
+            ses = ShardedEvalStream(banks[0], lo, batch=B, K=K, steps=G_STEPS, banks=banks, exchange=args.exchange,
+                                    col_id=shard_ids)
         except PeerMemoryUnavailable as e:      # raised on every rank alike: fall back together
             if rank == 0:
                 print("bench: %s -- falling back to the NCCL exchange" % (e,), file=sys.stderr)
             args.exchange = "nccl"
-            ses = ShardedEvalStream(banks[0], lo, batch=B, K=K, steps=G_STEPS, banks=banks, exchange="nccl")
+            ses = ShardedEvalStream(banks[0], lo, batch=B, K=K, steps=G_STEPS, banks=banks, exchange="nccl", col_id=shard_ids)
         for s_ in range(G_STEPS):
             ses.dev_feats[s_].copy_(feats_dev[s_ % n_feat])
             ses.dev_labels[s_].copy_(labels_dev[s_ % n_feat])
@@ -326,10 +368,10 @@ def run_ours(args):
         def step_resident(i):                    # one replay = G_STEPS batches; issue it on every G_STEPS-th step
             if i % G_STEPS == 0:
                 ses.run()
-        steps = max(G_STEPS, steps // G_STEPS * G_STEPS)
-        warmup = max(G_STEPS, warmup // G_STEPS * G_STEPS)
+        steps = max(G_STEPS, steps // G_STEPS * G_STEPS)            # == args.steps whenever it has a divisor <= 10
+        warmup_run = -(-warmup // G_STEPS) * G_STEPS                 # at least `warmup` steps, whole replays
         res_begin, res_end, hits_src = (lambda: None), (lambda: None), ses.hits
-    for i in range(warmup):
+    for i in range(warmup_run if world > 1 else warmup):
         step_resident(i)
     res_end()
     torch.cuda.synchronize()
@@ -337,11 +379,12 @@ def run_ours(args):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ms = timed(step_resident, steps, res_end, res_begin)
+    ms, n_blocks, ms_best, ms_worst = timed_blocks(step_resident, steps, res_end, res_begin)
     launches = kernels_per_step * steps
     ms_per_step = ms / steps
     value = B / (ms_per_step * 1e-3)
     hits_resident = (ses.all_reduce_hits() if world > 1 else hits_src).tolist()   # p2p: per-rank row blocks, summed once
+    hits_resident = [h // n_blocks for h in hits_resident]                        # per block of `steps` batches
 
     # ---- dominant kernel alone (GEMM + fused top-k, no merge), one stream: the roofline figure
     Cs = hi - lo
@@ -374,6 +417,110 @@ def run_ours(args):
     sus_ms = timed(step_resident, n_sus, res_end, res_begin) / n_sus
     clocks = sampler.stop() if rank == 0 else None
 
+    # ---- local (single-GPU, no collective) timing helpers
+    def time_graph_us(fn, variants, min_ms=40.0):
+        """`variants` back-to-back calls of fn(i) in ONE CUDA graph on a side stream, replayed for >= min_ms: us per call."""
+        st = torch.cuda.Stream()
+        st.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(st):
+            fn(0)
+            st.synchronize()
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr, stream=st):
+                for i in range(variants):
+                    fn(i)
+        torch.cuda.current_stream().wait_stream(st)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for _ in range(3):
+            gr.replay()
+        e0.record()
+        gr.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        reps = int(max(3, min_ms / max(e0.elapsed_time(e1), 1e-3)))
+        e0.record()
+        for _ in range(reps):
+            gr.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / (reps * variants) * 1e3
+
+    def single_gpu_point(Bx, full_bank, ids):
+        """The same head on THIS GPU alone with the whole bank: streaming evaluator (device-resident inputs) and the
+        dominant kernel alone.  No collective inside: the other ranks wait at the next barrier."""
+        nb = _n_bank(dict(C=full_bank.shape[0], D=D), 1)
+        fb = [full_bank] + [full_bank.clone() for _ in range(nb - 1)]
+        from hgrnet_b200.stream import EvalStream
+        slots = nb * n_feat // math.gcd(nb, n_feat)
+        es1 = EvalStream(full_bank, col_id=ids, batch=Bx, K=K, slots=slots, streams=n_streams, banks=fb, host_io=False)
+        gx = torch.Generator().manual_seed(5)
+        fx = [torch.randn(Bx, D, generator=gx).to(dev) for _ in range(n_feat)]
+        for s_ in range(slots):
+            es1.dev_feats[s_].copy_(fx[s_ % n_feat])
+            es1.dev_labels[s_].fill_(int(ids[s_ % ids.numel()]))
+        for i in range(2 * slots):
+            es1.step(i % slots)
+        es1.end()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        blocks = []
+        n_it = max(steps, slots)
+        for _ in range(12):
+            e0.record()
+            es1.begin()
+            for i in range(n_it):
+                es1.step(i % slots)
+            es1.end()
+            e1.record()
+            torch.cuda.synchronize()
+            blocks.append(e0.elapsed_time(e1) / n_it)
+        blocks.sort()
+        msx = blocks[len(blocks) // 2]
+        xn = [ops.normalize_rows(f) for f in fx]
+        kus = time_graph_us(lambda i: ops.score_topk(xn[i % n_feat], fb[i % nb], K=K, impl=nomerge), slots)
+        fl = 2.0 * Bx * full_bank.shape[0] * D
+        del es1, fb
+        return {"value": Bx / (msx * 1e-3), "unit": "images/s", "ms_per_step": msx, "B": Bx, "C": int(full_bank.shape[0]),
+                "kernel_us": kus, "kernel_frac_of_peak": fl / (kus * 1e-6) / 1e12 / tf_peak}
+
+    same_wl = None
+    if rank == 0 and (world > 1 or wl_key == "cfg2"):
+        # cfg 5 (B = 4096, the whole 21,841-class bank) on one GPU: the 1-GPU point of the scaling sweep
+        same_wl = single_gpu_point(WORKLOADS["cfg5"]["B"], model.bank_test, model._test_index_i32)
+    if world > 1:
+        dist.barrier()
+
+    # ---- bank row order (N = 1): the scoring kernel + merge on an i.i.d. bank, on a hierarchy-ordered (clustered)
+    # bank as the reference's `nodes` order would give it, and on the same bank in the pseudo-random row order that
+    # update_classifier applies; plus the floor-sketch kernel (exact by construction) on the un-permuted bank
+    bank_order = None
+    if world == 1 and rank == 0 and not args.no_cpu_baseline:
+        from hgrnet_b200.synthetic import clustered_bank, near_leaf_features
+        cb = clustered_bank(C, D, 3)
+        cbd = cb.to(dev).to(torch.bfloat16)
+        perm = torch.randperm(C, generator=torch.Generator().manual_seed(9)).to(dev)
+        cbp = cbd[perm].contiguous()
+        qs = [ops.normalize_rows(near_leaf_features(cb, B, 20 + i).to(dev)) for i in range(4)]
+        iid = banks[0]
+
+        def one(bank_, impl_):
+            us_ = time_graph_us(lambda i: ops.score_topk(qs[i % 4], bank_, K=K, impl=impl_), 8, min_ms=20.0)
+            ops.score_topk(qs[0], bank_, K=K, impl=impl_)
+            torch.cuda.synchronize()
+            return us_, ops.last_rescan_count()
+        a_us, a_rs = one(iid, ops.HGR_IMPL_TCGEN05)
+        b_us, b_rs = one(cbp, ops.HGR_IMPL_TCGEN05)
+        c_us, c_rs = one(cbd, ops.HGR_IMPL_TCGEN05)
+        d_us, d_rs = one(cbd, ops.HGR_IMPL_TCGEN05_SKETCH)
+        bank_order = {"unit": "us per call (scoring kernel + merge, one stream), near-leaf queries",
+                      "iid_bank": a_us, "clustered_bank_permuted_rows": b_us, "clustered_bank_tree_order": c_us,
+                      "clustered_bank_tree_order_sketch_kernel": d_us,
+                      "rows_repaired": {"iid": a_rs, "permuted": b_rs, "tree_order": c_rs},
+                      "permuted_over_iid": b_us / a_us,
+                      "note": "tree_model.update_classifier stores the test bank in the permuted order (head.py)"}
+        del cbd, cbp
+
     # ---- end to end through the public API with pinned HOST buffers
     if world == 1:
         es = model.make_eval_stream(batch=B, slots=cycle, streams=n_streams, banks=banks)   # stream.EvalStream
@@ -386,7 +533,7 @@ def run_ours(args):
     elif args.exchange == "p2p":
         # host-fed sharded evaluator: per batch every rank copies ITS block of image rows (+ labels) from pinned
         # host memory, NVLink replicates the normalised rows, Hit@k counters are read back after every batch
-        ses_h = ShardedEvalStream(banks[0], lo, batch=B, K=K, steps=G_STEPS, banks=banks, host_io=True)
+        ses_h = ShardedEvalStream(banks[0], lo, batch=B, K=K, steps=G_STEPS, banks=banks, host_io=True, col_id=shard_ids)
         for s_ in range(G_STEPS):
             ses_h.host_feats[s_].copy_(feats_host[s_ % n_feat][ses_h.row_lo:ses_h.row_hi])
             ses_h.host_labels[s_].copy_(labels_host[s_ % n_feat][ses_h.row_lo:ses_h.row_hi].to(torch.int32))
@@ -408,7 +555,7 @@ def run_ours(args):
         step_e2e(i)
     if e2e_end:
         e2e_end()
-    e2e_ms = timed(step_e2e, steps, e2e_end, e2e_begin) / steps
+    e2e_ms = timed_blocks(step_e2e, steps, e2e_end, e2e_begin)[0] / steps
     e2e_value = B / (e2e_ms * 1e-3)
 
     # same protocol with fp16 host features (the dtype the reference's GPU encoder emits, clip/model.py:371-392):
@@ -422,7 +569,7 @@ def run_ours(args):
         for i in range(warmup):
             es16.step(i % cycle)
         es16.end()
-        ms16 = timed(lambda i: es16.step(i % cycle), steps, es16.end, es16.begin) / steps
+        ms16 = timed_blocks(lambda i: es16.step(i % cycle), steps, es16.end, es16.begin)[0] / steps
         e2e16 = {"value": B / (ms16 * 1e-3), "unit": "images/s", "ms_per_step": ms16,
                  "h2d_bytes_per_step": B * D * 2 + B * 4, "d2h_bytes_per_step": 5 * 8}
 
@@ -434,22 +581,24 @@ def run_ours(args):
                    "sample": "%d batches of %d images, torch CPU fp32 (reference ops of clip_tree.py:330-331 + main.py:136-147)"
                              % (40 if wl_key == "cfg2" else 8, wl["B"])}
         line = {
-            "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+            "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak" if world == 1 else "strong",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": wl["name"], "B": B, "C": C, "D": D, "K": K,
-                       "sharding": "none" if world == 1 else "class dimension row-sharded over %d ranks" % world,
-                       "streams": n_streams if world == 1 else 1,
-                       "pipeline": ("EvalStream: 1 CUDA graph per batch on %d round-robin streams" % n_streams) if world == 1
-                                   else ("ShardedEvalStream: 8 batches per %s; %s" % (
-                                       "CUDA graph" if multi_graph else "eager issue",
-                                       "peer-memory exchange: final lists stored into the row owner's buffer over NVLink, "
-                                       "flag-ordered, owner merges its rows (no collective on the data path)"
-                                       if args.exchange == "p2p" else
-                                       "NCCL all-gather of batch i overlaps the GEMM of batch i+1")),
-                       "exchange": None if world == 1 else args.exchange,
-                       "l2": "inputs larger than L2: %d bank copies (%.0f MB) + %d feature batches rotated" %
-                             (n_bank, n_bank * Cs * D * 2 / 1e6, n_feat)},
+            "config": _config(wl, world),
+            "impl": {"sharding": "none" if world == 1 else "class dimension row-sharded over %d ranks" % world,
+                     "streams": n_streams if world == 1 else 1,
+                     "pipeline": ("EvalStream: 1 CUDA graph per batch on %d round-robin streams" % n_streams) if world == 1
+                                 else ("ShardedEvalStream: %d batches per %s; %s" % (
+                                     G_STEPS, "CUDA graph" if multi_graph else "eager issue",
+                                     "peer-memory exchange: final lists stored into the row owner's buffer over NVLink, "
+                                     "flag-ordered, owner merges its rows (no collective on the data path)"
+                                     if args.exchange == "p2p" else
+                                     "NCCL all-gather of batch i overlaps the GEMM of batch i+1")),
+                     "exchange": None if world == 1 else args.exchange,
+                     "bank_rows": "pseudo-random order (tree_model.update_classifier), col_id maps back to node ids",
+                     "timing": "value = median of %d blocks of %d steps (fastest %.4f ms, slowest %.4f ms per block)"
+                               % (n_blocks, steps, ms_best, ms_worst),
+                     "warmup_steps_run": warmup_run if world > 1 else warmup},
             "e2e": {"value": e2e_value, "unit": "images/s", "ms_per_step": e2e_ms,
                     # whole job: with the peer exchange every image row crosses PCIe once (on the rank that owns it);
                     # with the NCCL exchange every rank copies the whole batch
@@ -465,13 +614,21 @@ def run_ours(args):
                          # DRAM bytes of one launch from the committed `ncu --set full` capture of this workload
                          # (profiles/r01c_ncu_summary.md); compulsory bytes = bank + features + lists
                          "traffic": NCU_DRAM_BYTES.get((B, Cs, D)),
-                         "traffic_unit": "bytes/launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)",
+                         "traffic_unit": "bytes/launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, offline capture "
+                                         "under profiles/ -- a profiler cannot run inside the timed region)",
                          "compulsory_bytes": Cs * D * 2 + B * D * 2,
                          "kernel": "score_umma_pair_kernel (TMA + tcgen05 GEMM + fused top-20)",
                          "kernel_ms": kms, "flops_per_launch": flops, "peak_source": peak_src},
             "cpu_baseline": cpu,
             "clocks": clocks,
         }
+        if same_wl is not None and world > 1:
+            line["single_gpu_same_workload"] = same_wl
+            line["speedup_vs_1gpu"] = value / same_wl["value"]
+        elif same_wl is not None:
+            line["cfg5_single_gpu"] = same_wl
+        if bank_order is not None:
+            line["bank_order"] = bank_order
         print(json.dumps(line))
     if world > 1:
         # CUDA graphs hold NCCL kernels: tear down without destroy_process_group (which can block on them)

@@ -28,6 +28,24 @@ def synthetic_embeddings(n: int, d: int, seed: int, device="cpu", normalize: boo
     return bf16_valued(x).to(device)
 
 
+def clustered_bank(n: int, d: int, seed: int, fan: int = 64, sigma: float = 0.15) -> torch.Tensor:
+    """A class bank whose ROW ORDER follows a hierarchy: child = parent + sigma * noise, siblings adjacent -- like the
+    reference's `nodes` (graph order, utils.py:44-45) with real CLIP text embeddings.  An image near a leaf then has
+    its whole top-20 in a few adjacent bank rows.  Row-normalised, bf16-valued fp32, raw (unnormalised) when used as a
+    text table is fine too."""
+    g = torch.Generator().manual_seed(seed)
+    centers = torch.randn((n + fan - 1) // fan, d, generator=g)
+    w = centers.repeat_interleave(fan, 0)[:n] + sigma * torch.randn(n, d, generator=g)
+    return bf16_valued(w / w.norm(dim=-1, keepdim=True))
+
+
+def near_leaf_features(bank: torch.Tensor, b: int, seed: int, noise: float = 0.3) -> torch.Tensor:
+    """Image features drawn near randomly chosen rows of `bank` (unnormalised fp32)."""
+    g = torch.Generator().manual_seed(seed)
+    pick = torch.randint(0, bank.shape[0], (b,), generator=g)
+    return bank[pick].float() + noise * torch.randn(b, bank.shape[1], generator=g) / bank.shape[1] ** 0.5
+
+
 class TableEncoder(nn.Module):
     """Duck-typed CLIP: ``encode_text`` gathers rows of a learnable table by node id (token column 0),
     ``encode_image`` passes pre-computed features through a unit gain.  ``logit_scale`` initialises to
