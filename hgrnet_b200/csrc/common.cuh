@@ -140,4 +140,10 @@ int launch_masked_ce(const float* logits, int64_t ldl, int64_t B, int64_t U, con
                      const int32_t* set_col, const int32_t* label_pos, const float* weight, int64_t T,
                      float* loss, float* dlogits, void* ws, size_t ws_bytes, cudaStream_t stream);
 
+size_t om_backward_workspace_bytes(int64_t B, int64_t U, int64_t D);
+int launch_om_backward(const float* dlogits, const float* logits, int64_t ldl, int64_t B, int64_t U, int64_t D,
+                       const __nv_bfloat16* x, const float* x_norm, const __nv_bfloat16* tn, const float* t_norm,
+                       float scale, float* d_img, float* d_text, float* d_log_scale, void* ws, size_t ws_bytes,
+                       cudaStream_t stream);
+
 }  // namespace hgr

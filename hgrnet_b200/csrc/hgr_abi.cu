@@ -300,4 +300,19 @@ int hgr_masked_ce(const float* logits, int64_t ldl, int64_t B, int64_t U, const 
                           workspace_bytes, static_cast<cudaStream_t>(stream));
 }
 
+size_t hgr_om_backward_workspace_bytes(int64_t B, int64_t U, int64_t D) { return om_backward_workspace_bytes(B, U, D) + 16; }
+
+int hgr_om_backward(const float* dlogits, const float* logits, int64_t ldl, int64_t B, int64_t U, int64_t D, const void* x,
+                    const float* x_norm, const void* tn, const float* t_norm, float scale, float* d_img, float* d_text,
+                    float* d_log_scale, void* workspace, size_t workspace_bytes, void* stream) {
+  HGR_CHECK_ARG(B > 0 && U > 0 && D > 0, "hgr_om_backward: bad sizes B=%lld U=%lld D=%lld", (long long)B, (long long)U, (long long)D);
+  HGR_CHECK_ARG(ldl >= U, "hgr_om_backward: ldl < U");
+  HGR_CHECK_ARG(dlogits && logits && x && x_norm && tn && t_norm && d_img && d_text, "hgr_om_backward: null pointer");
+  HGR_CHECK_ARG(aligned16(x) && aligned16(tn) && aligned16(d_img) && aligned16(d_text) && aligned16(workspace),
+                "hgr_om_backward: x / tn / d_img / d_text / workspace must be 16-byte aligned");
+  return launch_om_backward(dlogits, logits, ldl, B, U, D, static_cast<const __nv_bfloat16*>(x), x_norm,
+                            static_cast<const __nv_bfloat16*>(tn), t_norm, scale, d_img, d_text, d_log_scale, workspace,
+                            workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

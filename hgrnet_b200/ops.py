@@ -350,3 +350,35 @@ def masked_ce(logits: torch.Tensor, set_ptr: torch.Tensor, set_col: torch.Tensor
                                   _ptr(label_pos), _ptr(weight), T, _ptr(loss), _ptr(dl), _ptr(ws), ws.numel(),
                                   _stream()))
     return loss, dl
+
+
+def om_backward(dlogits: torch.Tensor, logits: torch.Tensor, x: torch.Tensor, x_norm: torch.Tensor, tn: torch.Tensor,
+                t_norm: torch.Tensor, scale: float, d_log_scale: Optional[torch.Tensor] = None):
+    """Backward of ``logits = scale * x @ tn^T`` and of the two row normalisations (clip_tree.py:276 / :263 / :225,262 /
+    :280) on the tcgen05 GEMM kernel.  Returns ``(d_img_raw [B,D] fp32, d_text_raw [U,D] fp32)``; ``d_log_scale``
+    (fp32 [1], optional) is ACCUMULATED into."""
+    lib = _cabi.load()
+    dlogits = _require(dlogits, "dlogits", torch.float32)
+    logits = _require(logits, "logits", torch.float32)
+    x = _require(x, "x", torch.bfloat16)
+    tn = _require(tn, "tn", torch.bfloat16)
+    x_norm = _require(x_norm, "x_norm", torch.float32)
+    t_norm = _require(t_norm, "t_norm", torch.float32)
+    B, U = dlogits.shape
+    D = x.shape[1]
+    if logits.shape != dlogits.shape or x.shape[0] != B or tn.shape != (U, D):
+        raise ValueError("om_backward: shapes disagree")
+    d_img = torch.empty((B, D), dtype=torch.float32, device=x.device)
+    d_text = torch.empty((U, D), dtype=torch.float32, device=x.device)
+    nbytes = lib.hgr_om_backward_workspace_bytes(B, U, D)
+    key = ("om_bwd", x.device.index, torch.cuda.current_stream().cuda_stream)
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < nbytes:
+        if ws is not None:
+            _retired.append(ws)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+        _workspaces[key] = ws
+    _cabi.check(lib.hgr_om_backward(_ptr(dlogits), _ptr(logits), dlogits.stride(0), B, U, D, _ptr(x), _ptr(x_norm), _ptr(tn),
+                                    _ptr(t_norm), float(scale), _ptr(d_img), _ptr(d_text), _ptr(d_log_scale), _ptr(ws),
+                                    ws.numel(), _stream()))
+    return d_img, d_text

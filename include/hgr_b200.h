@@ -231,6 +231,23 @@ int hgr_masked_ce(const float* logits, int64_t ldl, int64_t B, int64_t U,
                   const float* weight, int64_t T, float* loss, float* dlogits,
                   void* workspace, size_t workspace_bytes, void* stream);
 
+/*
+ * Backward of the OM step's logits (model/clip_tree.py:276 through :263, :225/:262, then :280): with dlogits from
+ * hgr_masked_ce (the T iterations already summed over the union of the sampled classes)
+ *     d_img  [B, D] fp32 = d/d(raw image features)  of  x  = raw / |raw|,  via  d_x  = scale * dlogits   @ tn
+ *     d_text [U, D] fp32 = d/d(raw text features)   of  tn = raw / |raw|,  via  d_tn = scale * dlogits^T @ x
+ *     d_log_scale[0] += sum(dlogits * logits)        (d/d logit_scale of scale = exp(logit_scale); may be NULL)
+ * Both gradient GEMMs run on the tcgen05 kernel of the scoring head (bf16 operands, fp32 accumulation).
+ *  dlogits, logits [B, U] fp32 (ld = ldl); x [B, D], tn [U, D] bf16 unit rows with their pre-normalisation norms
+ *  x_norm [B], t_norm [U] fp32 (hgr_aggregate_normalize's out_norm); D % 8 == 0.
+ *  workspace at least hgr_om_backward_workspace_bytes(B, U, D) bytes.
+ */
+size_t hgr_om_backward_workspace_bytes(int64_t B, int64_t U, int64_t D);
+int hgr_om_backward(const float* dlogits, const float* logits, int64_t ldl, int64_t B, int64_t U, int64_t D,
+                    const void* x, const float* x_norm, const void* tn, const float* t_norm, float scale,
+                    float* d_img, float* d_text, float* d_log_scale, void* workspace, size_t workspace_bytes,
+                    void* stream);
+
 #ifdef __cplusplus
 }
 #endif
