@@ -47,26 +47,32 @@ class HierMetrics:
         self.path_all_count = 0
         depth = torch.from_numpy(model.hierarchy.depth).to(torch.int64)
         self.n_levels = int(depth.max()) + 1 if depth.numel() else 1
-        self._level = depth.to(torch.int8).to(dev)
-        self._cols = model.train_index.to(torch.int32).contiguous()
-        # first position of train_index that is NOT at level l: where the reference's -1 fill (main.py:171) sits first
-        dt = depth[model.train_index.cpu()]
+        # Only the TRAIN columns enter TOR / POR (main.py:143,155,174): the dense logits are taken against the train
+        # rows of the bank alone ([B, M], M = 983 of 18,278 classes on ImageNet-21K-D) instead of all N nodes, and the
+        # kernel works in train POSITIONS: level per position, the label's chain as positions (-1: not a train class).
+        train = model.train_index.cpu()
+        dt = depth[train]
         M = dt.numel()
+        self._level = dt.to(torch.int8).to(dev)
+        self._pos_of = {int(n): j for j, n in enumerate(train.tolist())}
+        # first position of train_index that is NOT at level l: where the reference's -1 fill (main.py:171) sits first
         first_out = []
         for l in range(self.n_levels):
             out = (dt != l).nonzero()
             first_out.append(int(out[0]) if out.numel() else M)
         self._first_out = torch.tensor(first_out, dtype=torch.int32, device=dev)
 
-    def update(self, logits: torch.Tensor, target: int):
+    def update(self, logits_train: torch.Tensor, target: int):
+        """``logits_train`` [B, M]: cosine logits against ``model.bank_train`` (column j = node train_index[j])."""
         m = self.model
-        B = logits.shape[0]
+        B = logits_train.shape[0]
         parents = list(m.c2p[target]) + [target]
         L = len(parents)
-        chain = torch.tensor(parents, dtype=torch.int32).to(logits.device, non_blocking=True)
-        chain_level = torch.tensor([len(m.c2p[p]) for p in parents], dtype=torch.int32).to(logits.device, non_blocking=True)
-        counts = torch.zeros(3, dtype=torch.int64, device=logits.device)
-        ops.hier_metrics(logits, self._cols, self._level, self.n_levels, self._first_out, chain, chain_level, counts)
+        dev = logits_train.device
+        chain = torch.tensor([self._pos_of.get(p, -1) for p in parents], dtype=torch.int32).to(dev, non_blocking=True)
+        chain_level = torch.tensor([len(m.c2p[p]) for p in parents], dtype=torch.int32).to(dev, non_blocking=True)
+        counts = torch.zeros(3, dtype=torch.int64, device=dev)
+        ops.hier_metrics(logits_train, None, self._level, self.n_levels, self._first_out, chain, chain_level, counts)
         c = counts.double()
         self.hits_all += c[0]                                               # main.py:158-160
         self.path_all += c[2] if L == 1 else c[2] / (L - 1)                 # main.py:179-190
@@ -100,8 +106,8 @@ def test(opts, model, device, splits=None, loader: Optional[Iterable] = None, lo
             model.score_topk(None, targets, hits=hits, feats_normalized=x)   # main.py:135-147, fused
             num_sample += len(targets)
             if hier is not None:
-                logits = ops.logits_dense(x, model.zsl_weights)              # clip_tree.py:331 (for TOR/POR only)
-                hier.update(logits, int(data["label"][0][0]))
+                logits_train = ops.logits_dense(x, model.bank_train)         # clip_tree.py:331, train columns only
+                hier.update(logits_train, int(data["label"][0][0]))
             if i % opts.print_freq == 0:
                 out_str = _format(hits, num_sample, hier)
                 print(out_str, flush=True)

@@ -129,7 +129,8 @@ class tree_model(nn.Module):
             self.layer_weight = nn.Parameter(layer_weight_init(self.d2n, self.opts.scale).to(self.device))
 
         self.zsl_weights: Optional[torch.Tensor] = None   # [N, D] bf16 class bank
-        self.bank_test: Optional[torch.Tensor] = None     # [C, D] bf16 rows of test_index
+        self.bank_test: Optional[torch.Tensor] = None     # [C, D] bf16 rows of test_index (in `_bank_order`)
+        self.bank_train: Optional[torch.Tensor] = None    # [M, D] bf16 rows of train_index
         self._rng = random  # Python's global RNG, as the reference (clip_tree.py:82,134,189)
         self._contra_cache = {}  # depth window -> candidate set (sampling.contra_topk)
 
@@ -206,6 +207,7 @@ class tree_model(nn.Module):
                     e = s + feats.shape[0]
                     ops.normalize_rows_dual(feats, zsl[s:e], self._bank_dst[s:e], bank)
                 self.zsl_weights, self.bank_test = zsl, bank
+                self.bank_train = zsl.index_select(0, self.train_index)      # TOR / POR columns (evaluate.HierMetrics)
             else:
                 text = None
                 for s in range(0, N, chunk):
@@ -216,6 +218,7 @@ class tree_model(nn.Module):
                 rp, col, w = csr
                 self.zsl_weights = ops.aggregate_normalize(text, rp, col, w)
                 self.bank_test = ops.aggregate_normalize(text, rp, col, w, row_map=self._test_index_i32)
+                self.bank_train = self.zsl_weights.index_select(0, self.train_index)
 
     # ------------------------------------------------------------------ eval
     def encode_image_normalized(self, inputs):

@@ -341,6 +341,13 @@ def test_hier_metrics_match_oracle(levels, B, train_every):
                          torch.tensor(parents, dtype=torch.int32, device=DEV),
                          torch.tensor([len(h.c2p[p]) for p in parents], dtype=torch.int32, device=DEV), counts,
                          lvl_idx=lvl, top1=top1)
+        # position mode (evaluate.HierMetrics): logits of the train columns only, chain as train positions
+        pos_of = {int(n): j for j, n in enumerate(train_index.tolist())}
+        counts2 = torch.zeros(3, dtype=torch.int64, device=DEV)
+        ops.hier_metrics(logits[:, train_index].contiguous().to(DEV), None, dt.to(torch.int8).to(DEV), n_levels, first_out,
+                         torch.tensor([pos_of.get(p, -1) for p in parents], dtype=torch.int32, device=DEV),
+                         torch.tensor([len(h.c2p[p]) for p in parents], dtype=torch.int32, device=DEV), counts2)
+        assert counts2.tolist() == counts.tolist()
         c = counts.tolist()
         assert c[0] == int(tor)
         assert abs((c[2] if L == 1 else c[2] / (L - 1)) - path_add) < 1e-9

@@ -154,9 +154,9 @@ def main():
     Bt = 512
     xt = ops.normalize_rows(synthetic_embeddings(Bt, D, 7, normalize=False).to(DEV))
     model.update_classifier()
-    dense = ops.logits_dense(xt, model.zsl_weights)
+    dense = ops.logits_dense(xt, model.bank_train)           # train columns only (here: every node is a train class)
     hm = HierMetrics(model)
-    us_dense = graph_us(lambda i: ops.logits_dense(xt, model.zsl_weights, out=dense))
+    us_dense = graph_us(lambda i: ops.logits_dense(xt, model.bank_train, out=dense))
     us_fused = events(lambda: hm.update(dense, target), 50)
     parents = list(model.c2p[target]) + [target]
     depth_t = torch.from_numpy(hier.depth).to(DEV)
@@ -172,7 +172,7 @@ def main():
     kb = Bt * N * 4 + N * 5
     ch_, cl_ = torch.zeros(12, dtype=torch.int32, device=DEV), torch.arange(12, dtype=torch.int32, device=DEV)
     cnt_ = torch.zeros(3, dtype=torch.int64, device=DEV)
-    us_kernel = graph_us(lambda i: ops.hier_metrics(dense, hm._cols, hm._level, hm.n_levels, hm._first_out, ch_, cl_, cnt_))
+    us_kernel = graph_us(lambda i: ops.hier_metrics(dense, None, hm._level, hm.n_levels, hm._first_out, ch_, cl_, cnt_))
     out["hier_metrics_f1"] = {"B": Bt, "N": N, "L": len(parents), "us_kernel_plus_host_glue": us_fused,
                               "us_kernel_call": us_kernel, "kernel_bytes": kb, "kernel_GBs": kb / us_kernel / 1e3,
                               "frac_hbm": kb / us_kernel / 1e3 / HBM, "us_dense_logits": us_dense,
