@@ -466,6 +466,55 @@ def run_ours(args):
                       "note": "tree_model.update_classifier stores the test bank in the permuted order (head.py)"}
         del cbd, cbp
 
+    # ---- BASELINE cfg 3 (N = 1): one OM training step of the head -- batch 256, --sample_strategy topk, out 0.25 / in 0.5,
+    # adaptive weights, deepest-level target of the same 12-level hierarchy (T = 17 iterations) -- through
+    # tree_model.train_batch (kernel 1, tcgen05 logits, fused masked CE, tcgen05 backward), with the reference's loop
+    # (oracle port, fp32) timed on the host beside it
+    om = None
+    if world == 1 and rank == 0 and not args.no_cpu_baseline and wl_key == "cfg2":
+        import random as _random
+        import numpy as _np
+        from oracle import hgr_oracle as orc
+        from hgrnet_b200.levels import layer_weight_init
+        o3 = parse_args([])
+        o3.device, o3.folder = local_rank, "/tmp/hgr_bench_out_om"
+        o3.weights, o3.out_ratio, o3.in_ratio, o3.k, o3.num_compare, o3.weighting, o3.scale = "adaptive", 0.25, 0.5, 1, 256, "both", 1.0
+        table3 = (table * 0.05).to(torch.bfloat16).float()
+        m3 = tree_model(o3, hier.nodes, hier.nodes, clip_model=TableEncoder(table3).to(dev), hierarchy=hier,
+                        node_tokens=node_id_tokens(C)).to(dev)
+        B3 = 256
+        img3 = synthetic_embeddings(B3, D, 82, normalize=False)
+        tgt = max(range(C), key=lambda i: len(hier.c2p[i]))
+        x3 = img3.to(dev).requires_grad_(True)
+        t3 = torch.full((B3,), tgt, dtype=torch.long, device=dev)
+        _random.seed(17)
+        for _ in range(3):
+            loss3 = m3.train_batch(x3, t3, "OM", "topk")
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(15):
+            t0 = time.perf_counter()
+            loss3 = m3.train_batch(x3, t3, "OM", "topk")
+            torch.cuda.synchronize()
+            ts.append(time.perf_counter() - t0)
+        ts.sort()
+        _random.seed(17)
+        t0 = time.perf_counter()
+        n_cpu = 3
+        for _ in range(n_cpu):
+            ref3 = orc.om_step(img3, table3, torch.tensor(float(_np.log(1 / 0.07))), hier.c2p, hier.d2n, tgt, out_ratio=0.25,
+                               in_ratio=0.5, weights="adaptive", weighting="both", k=1, num_compare=256,
+                               layer_weight=layer_weight_init(hier.d2n, 1.0))
+        cpu_s = (time.perf_counter() - t0) / n_cpu
+        om = {"workload": "OM training step: --sample_strategy topk, in_ratio 0.5, out_ratio 0.25, adaptive weights, batch 256, "
+                          "RN50 dim 1024, T = %d iterations" % len(m3.last_losses),
+              "ms_per_step": ts[len(ts) // 2] * 1e3, "steps_per_s": 1.0 / ts[len(ts) // 2], "loss": loss3,
+              "cpu_baseline": {"ms_per_step": cpu_s * 1e3, "kind": "port", "cores": torch.get_num_threads(),
+                               "sample": "%d steps of the reference loop (oracle port), torch CPU fp32" % n_cpu,
+                               "loss": float(ref3["loss"])},
+              "note": "wall clock per step incl. the host-side sampling (random.sample draws identical to the reference's)"}
+        del m3
+
     # ---- end to end through the public API with pinned HOST buffers
     if world == 1:
         es = model.make_eval_stream(batch=B, slots=cycle, streams=n_streams, banks=banks)   # stream.EvalStream
@@ -591,6 +640,8 @@ def run_ours(args):
             line["cfg5_single_gpu"] = same_wl
         if bank_order is not None:
             line["bank_order"] = bank_order
+        if om is not None:
+            line["om_step_cfg3"] = om
         print(json.dumps(line))
     if world > 1:
         # CUDA graphs hold NCCL kernels: tear down without destroy_process_group (which can block on them)
