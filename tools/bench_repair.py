@@ -1,5 +1,5 @@
 """Cost of the exact repair path (speculative lists that cannot be certified), to calibrate the constant of the
-speculation rule in csrc/score_umma.cu (`t_repair`, currently 0.6 us per bank row of 1024 elements).
+speculation rule in csrc/score_launch.cu (`t_repair`, currently 0.6 us per bank row of 1024 elements).
 
 An adversarial bank (a block of adjacent rows close to the mean image direction) overflows one speculative list of
 many image rows at once; the script reports the number of repaired rows, the time of the fused call with and

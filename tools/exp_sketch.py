@@ -78,8 +78,8 @@ if __name__ == "__main__":
             bk = [banks(C, D, kind, 2 + i).cuda() for i in range(nb)]
             xs = [emb(B, D, 10 + i).cuda() for i in range(4)]
             res = []
-            for name, impl in (("sketch", SK | NM), ("sketch+merge", SK), ("defer", _cabi.HGR_IMPL_TCGEN05_STREAM | NM),
-                               ("defer+merge", _cabi.HGR_IMPL_TCGEN05_STREAM), ("null", _cabi.HGR_IMPL_TCGEN05_STREAM_NULL)):
+            for name, impl in (("sketch", SK | NM), ("sketch+merge", SK), ("defer", ops.HGR_IMPL_TCGEN05 | NM),
+                               ("defer+merge", ops.HGR_IMPL_TCGEN05), ("null", ops.HGR_IMPL_TCGEN05_NULL)):
                 us = timeit(lambda i: ops.score_topk(xs[i % 4], bk[i % nb], K=20, impl=impl))
                 res.append("%s %.2f us (%.3f)" % (name, us, flops / us / 1e6 / 1658.5))
             print("[time] B=%d C=%d D=%d %-9s %s" % (B, C, D, kind, " | ".join(res)), flush=True)

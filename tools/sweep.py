@@ -58,7 +58,7 @@ def main():
     NM = _cabi.HGR_IMPL_FLAG_NO_MERGE
     variants = [("prod+merge", ops.HGR_IMPL_TCGEN05), ("prod", ops.HGR_IMPL_TCGEN05 | NM),
                 ("exact", ops.HGR_IMPL_TCGEN05_EXACT | NM), ("null", ops.HGR_IMPL_TCGEN05_NULL),
-                ("stream", _cabi.HGR_IMPL_TCGEN05_STREAM | NM), ("stream_null", _cabi.HGR_IMPL_TCGEN05_STREAM_NULL)]
+                ("sketch", ops.HGR_IMPL_TCGEN05_SKETCH | NM), ("sketch+merge", ops.HGR_IMPL_TCGEN05_SKETCH)]
     out = []
     for (B, C, D) in ((512, 21841, 1024), (4096, 21841, 1024), (1024, 10450, 512), (4096, 2731, 1024), (512, 2731, 1024)):
         nb = max(2, int(1.6 * 126e6 / (C * D * 2)) + 1)

@@ -15,8 +15,7 @@ def emb(n, d, seed):
 
 
 names = ["entry", "setup", "first_full", "last_mma_issued", "acc0", "acc1", "acc2", "acc3", "epi0", "epi1", "epi2", "epi3",
-         "epi_done", "exit", "-", "-", "-", "-", "-", "-", "-", "-", "-", "a_copies_done", "mma_a_first", "mma_a_last",
-         "a_copy_first", "a_loads_issued", "-", "-", "-", "-"]
+         "epi_done", "exit"] + ["-"] * 18
 NM = int(os.environ.get('HGR_TL_IMPL', ops.HGR_IMPL_TCGEN05)) | _cabi.HGR_IMPL_FLAG_NO_MERGE
 CASES = ((512, 21841, 1024, NM, "prod"), (512, 21841, 1024, ops.HGR_IMPL_TCGEN05_NULL, "null"),
          (512, 2731, 1024, ops.HGR_IMPL_TCGEN05_NULL, "null-small"))
@@ -45,14 +44,10 @@ for (B, C, D, impl, tag) in CASES:
     cyc = tl[:, 16:21].float()
     for j, n in enumerate(["wait acc", "warm-up pass", "tmem ld", "scan", "drain"]):
         print("  cycles %-14s median %8.0f  (%.2f us at 1.9 GHz)" % (n, cyc[:, j].median(), cyc[:, j].median() / 1900))
-    even = tl[0::2]                       # leader CTAs: MMA-warp cycle accounting (resident kernel)
-    if (even[:, 22] > 0).any():
-        for j, n in ((14, "wait bank stage"), (15, "wait accumulator buffer"), (21, "wait A operand"), (22, "MMA warp total")):
-            print("  MMA warp cycles %-24s median %8.0f" % (n, even[:, j].float().median()))
     if (tl[:, 24] > 0).any():
         for j in range(3):
             print("  scan loop of sub-tile %d: median %8.0f cycles" % (j, tl[:, 24 + j].float().median()))
-        for j, n in ((27, "select cycles"), (28, "compact cycles"), (29, "crowded chunks"), (30, "bisection passes"), (31, "selections"), (14, "global floor reads"), (15, "  finite"), (23, "  raised the floor"), (21, "sub-tile 1 chunks"), (2, "  ld+wait cycles"), (3, "  filter cycles"), (22, "gate cycles (all)")):
+        for j, n in ((27, "select cycles"), (28, "compact cycles"), (29, "crowded chunks"), (30, "bisection passes"), (31, "selections")):
             print("  warp 2: %-18s median %8.0f  mean %8.1f" % (n, tl[:, j].float().median(), tl[:, j].float().mean()))
     d = rel[:, 13] - rel[:, 0]
     print("  CTA lifetime     min %7.2f  median %7.2f  max %7.2f" % (d.min(), d.median(), d.max()))
