@@ -736,7 +736,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", dest="no_cpu_baseline", action="store_true")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="N > 1: peer-memory exchange (default) or NCCL all-gather of the per-rank candidate lists")
-    ap.add_argument("--streams", type=int, default=3, help="round-robin CUDA streams of the streaming evaluator")
+    ap.add_argument("--streams", type=int, default=6, help="round-robin CUDA streams of the streaming evaluator (measured 2/3/4/6: 14.2 / 15.6 / 16.6 / 17.4 M images/s at cfg 2)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
