@@ -5,24 +5,26 @@
 // accumulator columns at a time, and has to hand the merge kernel every column that can be in the row's top-K.
 //
 // What a row keeps:
-//  * a SKETCH of the stream: kSkGroups interleaved column classes (column j of a chunk -> class j % 10), each with its
+//  * a SKETCH of its first sub-tile: kSkGroups = 10 column classes (class of bank row c = (c & 31) % 10), each with its
 //    two largest values (3 FMNMX per value).  The smallest runner-up tau is reached by >= 20 distinct columns, so
 //    nothing below tau can be among the row's top-20: `floor` = the largest float below tau is a valid filter.  No
-//    data-dependent control flow, no sorted insert.
+//    data-dependent control flow, no sorted insert.  (A list that is the ONLY one of its rows keeps sketching.)
 //  * a share in the row's GLOBAL floor: the row's columns are streamed by several workers at once (one list per
 //    worker and row).  Every worker publishes its class maxima into kSkSlots = 20 words per row in global memory
-//    (`red.max`; class g of list l -> slot 2 g + (l & 1), so distinct slots hold distinct columns) and reads the 20
+//    (`red.max`; class g of list l -> word 2 g + (l & 1), so distinct words hold distinct columns) and reads the 20
 //    words back once per sub-tile: their minimum is a valid floor for the whole row -- it reflects every column any
 //    worker has seen so far, not just this list's.  After the first sub-tile almost nothing passes the filter, however
 //    many lists a row is split into and whatever order the bank rows come in (no speculation, no certificate, no
-//    repair pass: the result is exact by construction).  Slots carry the launch's epoch in their upper half, so a
-//    workspace never has to be cleared between launches.
-//  * a QUEUE of (value, column) candidates in shared memory: the columns that passed the filter, in stream order.
-//    When it runs full it is re-filtered against the (risen) floor; if that does not make room, an exact selection
-//    (bisection on order-preserving integer keys, ties by ascending column) cuts it down to 20..kSkCap entries and
-//    raises the row's private floor.  At the end of a segment the queue (<= kSkCap entries) IS the list.
-// The filter itself is register-only: a 32-bit pass mask per chunk, survivors picked with a select tree -- no
-// store-all staging that would compete with TMA and the tensor core for shared-memory bandwidth.
+//    repair pass: the result is exact by construction).  Later on only SURVIVORS are published (from the queue, at
+//    the end of a sub-tile): a value at or below the floor cannot raise a word, every word being >= their minimum.
+//    Words carry the launch's epoch in their upper half, so a workspace never has to be cleared between launches.
+//  * a QUEUE of (value, bank row) candidates in shared memory: the columns that passed the filter, in stream order
+//    (branch-free store-all append).  When it is crowded it is re-filtered against the (risen) floor; if that does
+//    not make room, an exact selection (bisection on order-preserving integer keys held in registers, ties by
+//    ascending column) cuts it down to 20..24 entries and raises the row's private floor.  At the end of a segment
+//    the queue (<= kSkCap entries) IS the list; topk_merge_counts_kernel selects the row's top-K from its lists.
+// Status: exact on every bank order (tests/test_gpu_kernels.py::test_hostile_bank_orders) but slower than the
+// deferred-insert lists on shuffled banks -- not the production path; measurements in profiles/r02_sketch_experiments.md.
 #pragma once
 #include "umma_common.cuh"
 
@@ -73,8 +75,6 @@ struct Sketch {
   __device__ __forceinline__ void update_ph(const uint32_t (&r)[kChunk]) {
 #pragma unroll
     for (int j = 0; j < kChunk; ++j) {
-      constexpr int dummy = 0;
-      (void)dummy;
       const float x = __uint_as_float(r[j]);
       lo[sk_class(j + PH)] = fmaxf(lo[sk_class(j + PH)], fminf(hi[sk_class(j + PH)], x));
       hi[sk_class(j + PH)] = fmaxf(hi[sk_class(j + PH)], x);
@@ -159,29 +159,6 @@ struct SkQueue {
   __device__ __forceinline__ void reset() { wr = pub = base; }
   __device__ __forceinline__ int count() const { return static_cast<int>((wr - base) / kSkStride); }
 };
-
-// largest value of a chunk (ragged tail: columns >= C are zero fill and must not count); 3-input maxima, 16 instructions
-__device__ __forceinline__ float max3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
-__device__ __forceinline__ float chunk_max(const uint32_t (&r)[kChunk], int nv) {
-  float a[11], b[4];
-#pragma unroll
-  for (int i = 0; i < 10; ++i) {
-    const float x = (nv >= kChunk || 3 * i < nv) ? __uint_as_float(r[3 * i]) : -INFINITY;
-    const float y = (nv >= kChunk || 3 * i + 1 < nv) ? __uint_as_float(r[3 * i + 1]) : -INFINITY;
-    const float z = (nv >= kChunk || 3 * i + 2 < nv) ? __uint_as_float(r[3 * i + 2]) : -INFINITY;
-    a[i] = max3(x, y, z);
-  }
-  {
-    const float x = (nv >= kChunk || 30 < nv) ? __uint_as_float(r[30]) : -INFINITY;
-    const float y = (nv >= kChunk || 31 < nv) ? __uint_as_float(r[31]) : -INFINITY;
-    a[10] = fmaxf(x, y);
-  }
-  b[0] = max3(a[0], a[1], a[2]);
-  b[1] = max3(a[3], a[4], a[5]);
-  b[2] = max3(a[6], a[7], a[8]);
-  b[3] = fmaxf(a[9], a[10]);
-  return fmaxf(max3(b[0], b[1], b[2]), b[3]);
-}
 
 // Branch-free append of a chunk: EVERY value is stored at the cursor, the cursor only advances for survivors (the next
 // store overwrites a non-survivor) -- straight-line code, which is what a lone warp per scheduler needs: nothing else
