@@ -1,6 +1,6 @@
 // CUDA-core implementation of the scoring head (HGR_IMPL_SIMT).
 //
-// Same contract as the tcgen05 kernel (score_umma.cu): logits = X @ bank^T, per-row sorted
+// Same contract as the tcgen05 kernel (score_pair.cu): logits = X @ bank^T, per-row sorted
 // top-K, never materialising B x C.  It accepts any shape (D % 8 == 0) and exists for three
 // reasons: (a) shapes the tensor-core kernel does not take, (b) an on-device cross-check of
 // the tcgen05 path in the GPU tests, (c) its row scan (simt_row.cuh) is the exact re-scan of
