@@ -123,4 +123,6 @@ class EvalStream:
     def hit_counts(self):
         """Hit@{1,2,5,10,20} so far (synchronises)."""
         self.synchronize()
-        return self.host_hits.tolist() if self.host_io else self.hits.tolist()
+        # (the per-step D2H copies of several streams land in the same 40 bytes in no particular order: read the
+        # counters once more now that every stream is idle)
+        return self.hits.tolist()

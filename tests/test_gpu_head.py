@@ -214,3 +214,40 @@ def test_update_classifier_chain_bank_matches_oracle(tmp_path, permute, mode):
     ref_logits = orc.forward_logits(feats, want)[:, test_ids]
     compare_topk(val, idx, ref_logits, test_ids, 20, rtol=1e-3, atol=2 * bf16_input_atol(spec["D"]))
     assert hits.tolist() == hits_from_idx(idx, tg.cpu())
+
+
+@pytest.mark.parametrize("feat_dtype", [torch.float32, torch.float16])
+def test_eval_stream_matches_direct_calls(tmp_path, feat_dtype):
+    """hgrnet_b200.stream.EvalStream (what bench.py's `value` / `e2e` run): graph-replayed batches on several streams,
+    host features in fp32 or fp16, must give the hit counters and top-20 of direct score_topk calls (main.py:131-148)."""
+    spec = cases.EVAL_CASES[0]
+    n_nodes = sum(spec["levels"])
+    test_ids = cases.test_ids(spec, n_nodes)
+    table = cases.text_table(spec, n_nodes)
+    model, h = _model(spec, tmp_path, table, test_ids, weights="equal")
+    model.update_classifier()
+    batches = cases.eval_batches(spec, test_ids)
+    B = batches[0][0].shape[0]
+    es = model.make_eval_stream(batch=B, slots=4, streams=3, feat_dtype=feat_dtype)
+    want = torch.zeros(5, dtype=torch.int64, device=DEV)
+    es.begin()
+    n = 0
+    for rep in range(3):
+        for i, (feats, label) in enumerate(batches):
+            if feats.shape[0] != B:
+                continue
+            s = n % es.slots
+            if n >= es.slots:
+                es.synchronize()                       # the slot's previous batch has been consumed
+            es.host_feats[s].copy_(feats.to(feat_dtype))
+            es.host_labels[s].fill_(label)
+            es.step(s)
+            tg = torch.full((B,), label, dtype=torch.long, device=DEV)
+            v, ix = model.score_topk(feats.to(feat_dtype).to(DEV), tg, hits=want)
+            if rep == 0:
+                es.synchronize()
+                assert torch.equal(es.idx[s], ix)
+                torch.testing.assert_close(es.val[s], v, rtol=0, atol=0)
+            n += 1
+    es.end()
+    assert es.hit_counts() == want.tolist() and n >= 3
