@@ -27,7 +27,8 @@ import torch.nn as nn
 from . import ops
 from .hierarchy import Hierarchy
 from .levels import layer_weight_init, level_weights
-from .sampling import contra_brothers, contra_random, contra_topk, hierarchical_schedule, om_schedule
+from .sampling import (contra_brothers, contra_random, contra_topk, hierarchical_schedule, om_schedule,
+                       sample_stream)
 
 TEMPLATE_SIMPLE = "a photo of a {}."  # data/templates.py:98-100 (TEMPLATES_SIMPLE[0], hard-wired at clip_tree.py:52)
 
@@ -140,14 +141,15 @@ class tree_model(nn.Module):
         torch.save(self.clip_model.state_dict(), self.save_path + "clip_{}".format(epoch))
 
     # ------------------------------------------------------------------ sampling / weights
-    def _contra_ids(self, method, target, depth=None, parents=None):
+    def _contra_ids(self, method, target, depth=None, parents=None, rng=None):
+        rng = self._rng if rng is None else rng       # `rng`: Python's global generator or a SampleStream over it
         if method == "topk":
-            return contra_topk(self.d2n, target, depth, parents, self.opts.k, self.opts.num_compare, self._rng,
+            return contra_topk(self.d2n, target, depth, parents, self.opts.k, self.opts.num_compare, rng,
                                cache=self._contra_cache)
         if method == "random":
-            return contra_random(self._train_ids_host, target, self.opts.num_compare, self._rng)
+            return contra_random(self._train_ids_host, target, self.opts.num_compare, rng)
         if method == "brothers":
-            return contra_brothers(self.p2c, self.start_up, target, depth, parents, self.opts.num_compare, self._rng)
+            return contra_brothers(self.p2c, self.start_up, target, depth, parents, self.opts.num_compare, rng)
         raise NotImplementedError(
             "sample_strategy %r: the reference's 'simi'/'near_simi' branches (clip_tree.py:91-114,143-178) mix "
             "python lists with tensors and cannot run as published; supported: topk, random, brothers" % method)
@@ -250,20 +252,23 @@ class tree_model(nn.Module):
     def _iterations(self, training_method, sample_strategy, target):
         """Host-side expansion of the loop nest into T (ids, label position, weight-recipe) records."""
         its = []
-        if training_method == "OM":
-            for (k_loop, m_loop, p_out, depth, parents_in, n_out, n_in) in om_schedule(
-                    self.c2p, target, self.opts.out_ratio, self.opts.in_ratio):
-                ids, pos = self._contra_ids(sample_strategy, p_out, depth, parents_in)
-                weighting = self.opts.weighting                                  # clip_tree.py:265-273
-                m_in = "equal" if weighting == "out" else self.opts.weights
-                m_out = "equal" if weighting == "in" else self.opts.weights
-                its.append((ids, pos, ((m_in, n_in, m_loop), (m_out, n_out, k_loop))))
-        elif training_method == "hierarchical":
-            for (j, t_in, depth, parents, n_lvl) in hierarchical_schedule(self.c2p, target):
-                ids, pos = self._contra_ids(sample_strategy, t_in, depth, parents)
-                its.append((ids, pos, ((self.opts.weights, n_lvl, j),)))         # clip_tree.py:304-305
-        else:
+        if training_method not in ("OM", "hierarchical"):
             raise NotImplementedError("training_method %r (the reference implements OM and hierarchical)" % training_method)
+        # every `random.sample` of the step runs on one SampleStream: same draws and same generator state afterwards
+        # as the reference's per-iteration calls (clip_tree.py:134), at a fraction of the host time
+        with sample_stream(self._rng) as rng:
+            if training_method == "OM":
+                for (k_loop, m_loop, p_out, depth, parents_in, n_out, n_in) in om_schedule(
+                        self.c2p, target, self.opts.out_ratio, self.opts.in_ratio):
+                    ids, pos = self._contra_ids(sample_strategy, p_out, depth, parents_in, rng)
+                    weighting = self.opts.weighting                                  # clip_tree.py:265-273
+                    m_in = "equal" if weighting == "out" else self.opts.weights
+                    m_out = "equal" if weighting == "in" else self.opts.weights
+                    its.append((ids, pos, ((m_in, n_in, m_loop), (m_out, n_out, k_loop))))
+            else:
+                for (j, t_in, depth, parents, n_lvl) in hierarchical_schedule(self.c2p, target):
+                    ids, pos = self._contra_ids(sample_strategy, t_in, depth, parents, rng)
+                    its.append((ids, pos, ((self.opts.weights, n_lvl, j),)))         # clip_tree.py:304-305
         return its
 
     @staticmethod

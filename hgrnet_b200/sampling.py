@@ -18,6 +18,152 @@ from typing import List, Optional, Sequence, Tuple
 _LIST_CACHE_ENTRIES = 512
 
 
+# ---- draw-identical fast `random.sample` ------------------------------------------------------------------------
+# The reference draws its negatives with Python's `random.sample` (clip_tree.py:134), ~0.15 ms per call at
+# ImageNet-21K level sizes -- 17 calls per OM step, by far the largest item of the step once the GPU side is fused.
+# A `SampleStream` replays those calls several times faster with IDENTICAL results: the Mersenne-Twister words the
+# reference would consume one `getrandbits` call at a time are fetched in bulk (a k-bit `getrandbits` concatenates
+# consecutive 32-bit outputs, least significant first), CPython's two selection algorithms run on that word array
+# (numpy for the set-based one, a tight loop for the pool-based one), and when the stream is closed the generator is
+# rewound and advanced by exactly the number of words the reference calls consume -- so `random` is in the same state
+# afterwards as after the reference's step.  Restates CPython's `Random.sample` / `_randbelow_with_getrandbits`
+# (3.8 - 3.13); `_fast_sample_ok` checks the restatement against the running interpreter once and falls back to
+# `rng.sample` on any mismatch.
+def _sample_setsize(k: int) -> int:
+    setsize = 21
+    if k > 5:
+        setsize += 4 ** math.ceil(math.log(k * 3, 4))
+    return setsize
+
+
+class SampleStream:
+    """Bulk view of the words `rng` will produce.  Use as a context manager around a run of `sample` calls; nothing
+    else may draw from `rng` in between."""
+
+    def __init__(self, rng):
+        self.rng = rng
+        self.state = None
+        self.words = None
+        self.pos = 0          # words consumed so far
+
+    def __enter__(self):
+        import numpy as np
+        self.state = self.rng.getstate()
+        self.words = np.empty(0, dtype="<u4")
+        self.pos = 0
+        return self
+
+    def ensure(self, m: int):
+        """At least `m` unconsumed words in the buffer."""
+        import numpy as np
+        have = self.words.shape[0] - self.pos
+        if have < m:
+            extra = max(m - have, 4096)
+            new = np.frombuffer(self.rng.getrandbits(32 * extra).to_bytes(4 * extra, "little"), dtype="<u4")
+            self.words = np.concatenate([self.words[self.pos:], new])
+            self._base = getattr(self, "_base", 0) + self.pos
+            self.pos = 0
+
+    def consumed(self) -> int:
+        return getattr(self, "_base", 0) + self.pos
+
+    def __exit__(self, *exc):
+        # the generator is ahead by everything fetched: rewind, then take exactly what the reference calls consume
+        used = self.consumed()
+        self.rng.setstate(self.state)
+        if used:
+            self.rng.getrandbits(32 * used)
+        return False
+
+    # -- random.sample(population, k) on the stream
+    def sample(self, population, k: int):
+        import numpy as np
+        n = len(population)
+        if not 0 <= k <= n:
+            raise ValueError("Sample larger than population or is negative")
+        if n <= _sample_setsize(k):
+            # pool algorithm: j = randbelow(n - i); result[i] = pool[j]; pool[j] = pool[n - i - 1]
+            m = 2 * k + 64
+            while True:
+                self.ensure(m)
+                words = self.words[self.pos:self.pos + m].tolist()
+                pool = list(population)
+                result = [None] * k
+                p = 0
+                try:
+                    for i in range(k):
+                        left = n - i
+                        sh = 32 - left.bit_length()
+                        r = words[p] >> sh
+                        p += 1
+                        while r >= left:
+                            r = words[p] >> sh
+                            p += 1
+                        result[i] = pool[r]
+                        pool[r] = pool[left - 1]
+                except IndexError:        # more rejections than the window covers: look further ahead
+                    m *= 2
+                    continue
+                self.pos += p
+                return result
+        # set algorithm: j = randbelow(n), redrawn while already selected; result[i] = population[j]
+        sh = 32 - n.bit_length()
+        m = int(k * (1 << n.bit_length()) / n * 1.25) + 64
+        while True:
+            self.ensure(m)
+            r = self.words[self.pos:self.pos + m] >> np.uint32(sh)
+            pos = np.flatnonzero(r < n)                      # words that survive randbelow's rejection
+            vals = r[pos]
+            # first occurrence of every distinct index: scatter the positions in reverse, so the earliest one sticks
+            order = np.arange(vals.shape[0])
+            owner = np.empty(n, dtype=np.intp)
+            owner[vals[::-1]] = order[::-1]
+            first = np.flatnonzero(owner[vals] == order)
+            if first.shape[0] >= k:
+                first = first[:k]
+                self.pos += int(pos[first[-1]]) + 1
+                return [population[j] for j in vals[first].tolist()]
+            m *= 2
+
+
+_FAST_SAMPLE = None
+
+
+def _fast_sample_ok() -> bool:
+    global _FAST_SAMPLE
+    if _FAST_SAMPLE is None:
+        try:
+            ok = True
+            a, b = _random.Random(11), _random.Random(11)
+            with SampleStream(b) as st:
+                for (n, k) in ((300, 256), (1045, 256), (1046, 256), (5500, 256), (40, 7), (4097, 64), (21841, 256)):
+                    pop = list(range(1000, 1000 + n))
+                    ok = ok and a.sample(pop, k) == st.sample(pop, k)
+            _FAST_SAMPLE = ok and a.getstate() == b.getstate()
+        except Exception:
+            _FAST_SAMPLE = False
+    return _FAST_SAMPLE
+
+
+def sample_stream(rng):
+    """A `SampleStream` over `rng` when the restatement matches this interpreter, else a pass-through whose `sample` is
+    `rng.sample` -- either way: same lists, same generator state after the `with` block."""
+    if hasattr(rng, "getstate") and hasattr(rng, "getrandbits") and _fast_sample_ok():
+        return SampleStream(rng)
+    return _PassThrough(rng)
+
+
+class _PassThrough:
+    def __init__(self, rng):
+        self.rng = rng
+
+    def __enter__(self):
+        return self.rng
+
+    def __exit__(self, *exc):
+        return False
+
+
 def contra_topk(d2n, target: int, depth: int, parents: Sequence[int], k: int, num_compare: int,
                 rng=_random, cache: Optional[dict] = None) -> Tuple[List[int], int]:
     """model/clip_tree.py:116-141.  Returns ``(compare_idx, label_position)``.
@@ -55,7 +201,7 @@ def contra_topk(d2n, target: int, depth: int, parents: Sequence[int], k: int, nu
             order.append(lkey)
             cache[lkey] = base
     if len(base) > num_compare:
-        compare_idx = rng.sample(base, num_compare)   # a new list; the cached one is never modified
+        compare_idx = rng.sample(base, num_compare)   # a new list; the cached one is never modified (rng may be a SampleStream)
     else:
         compare_idx = list(base)
     if target not in compare_idx:
@@ -65,7 +211,7 @@ def contra_topk(d2n, target: int, depth: int, parents: Sequence[int], k: int, nu
 
 def contra_random(train_ids: Sequence[int], target: int, num_compare: int, rng=_random) -> Tuple[List[int], int]:
     """model/clip_tree.py:81-89."""
-    compare_idx = rng.sample(list(train_ids), num_compare)
+    compare_idx = rng.sample(list(train_ids), num_compare)          # rng: `random` or a SampleStream over it
     if target not in compare_idx:
         compare_idx.append(target)
     return compare_idx, compare_idx.index(target)

@@ -405,3 +405,33 @@ def test_other_strategies_match_live_reference():
         ce = torch.nn.functional.cross_entropy(logits, torch.full((B,), pos))
         total += float(ce * level_weights("increasing", n_lvl, None)[j])
     assert abs(total - ref_loss) <= 1e-5 * abs(ref_loss), (total, ref_loss)
+
+
+def test_sample_stream_is_draw_identical_to_random_sample():
+    """hgrnet_b200.sampling.SampleStream replays runs of `random.sample` calls (clip_tree.py:134) in bulk: every list
+    and the generator state afterwards must equal what the plain calls give -- pool algorithm (n <= setsize), set
+    algorithm, mixed runs, and Python's global generator."""
+    from hgrnet_b200 import sampling
+    assert sampling._fast_sample_ok()
+    for seed in range(60):
+        rnd = random.Random(seed)
+        a, b = random.Random(seed * 7 + 1), random.Random(seed * 7 + 1)
+        calls = []
+        for _ in range(rnd.randint(1, 12)):
+            n = rnd.choice([17, 40, 257, 300, 1000, 1045, 1046, 2000, 5500, 21841, 70000])
+            k = min(rnd.choice([1, 5, 6, 16, 17, 64, 255, 256]), n)
+            calls.append(([rnd.randrange(10 ** 6) for _ in range(n)], k))
+        want = [a.sample(p_, k) for p_, k in calls]
+        with sampling.sample_stream(b) as st:
+            got = [st.sample(p_, k) for p_, k in calls]
+        assert got == want and a.getstate() == b.getstate() and a.random() == b.random()
+    random.seed(5)
+    want = [random.sample(range(9000), 256) for _ in range(3)]
+    s1 = random.getstate()
+    random.seed(5)
+    with sampling.sample_stream(random) as st:
+        got = [st.sample(range(9000), 256) for _ in range(3)]
+    assert got == want and random.getstate() == s1
+    with pytest.raises(ValueError):
+        with sampling.sample_stream(random.Random(1)) as st:
+            st.sample([1, 2, 3], 4)
