@@ -28,38 +28,12 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void fence_mbar_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
-__device__ __forceinline__ void fence_proxy_async_smem() {
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred P;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, P;\n\t}"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-// Bounded wait: a protocol bug must surface as a launch failure, never as a hung GPU.
-__device__ __forceinline__ bool mbar_try_wait_suspend(uint32_t bar_addr, uint32_t parity, uint32_t hint_ns) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred P;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
-      "selp.u32 %0, 1, 0, P;\n\t}"
-      : "=r"(ok)
-      : "r"(bar_addr), "r"(parity), "r"(hint_ns)
-      : "memory");
-  return ok != 0;
 }
 static __device__ __noinline__ void mbar_timeout_trap(uint32_t parity) {
   printf("hgr_b200: mbarrier wait timed out (block %d thread %d parity %u)\n", (int)blockIdx.x, (int)threadIdx.x,
@@ -82,22 +56,6 @@ __device__ __forceinline__ bool mbar_try_wait_addr(uint32_t bar_addr, uint32_t p
       : "memory");
   return ok != 0;
 }
-// Blocking wait as ONE asm statement (the retry loop lives inside it): the compiler sees no data-dependent branch,
-// so everything the issue loops compute around it stays provably warp-uniform and lives in uniform registers
-// (a visible `while (!try_wait)` makes the loop-carried stage / phase / descriptor cursors "divergent": every
-// use then costs an R2UR).  Unbounded -- used only by the producer / MMA warps; the epilogue warps of the same CTA
-// wait with the bounded mbar_wait and trap the launch if the pipeline ever stops.
-__device__ __forceinline__ void mbar_wait_spin(uint32_t bar_addr, uint32_t parity) {
-  asm volatile(
-      "{\n\t.reg .pred P;\n"
-      "HGR_WAIT:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P, [%0], %1;\n\t"
-      "@P bra HGR_DONE;\n\t"
-      "bra HGR_WAIT;\n"
-      "HGR_DONE:\n\t}"
-      ::"r"(bar_addr), "r"(parity)
-      : "memory");
-}
 // Out-of-line blocking wait for the issue loops, whose instruction count is their throughput (a single warp retires
 // one instruction every ~6-8 cycles there): the hot path is `if (!ready) mbar_wait_cold(...)` with `ready` probed
 // one stage ahead by mbar_test.
@@ -111,29 +69,6 @@ static __device__ __noinline__ void mbar_wait_cold(uint32_t bar_addr, uint32_t p
       else if (now - t0 > 4000000000LL) mbar_timeout_trap(parity);
     }
   }
-}
-__device__ __forceinline__ bool mbar_test_addr(uint32_t bar_addr, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred P;\n\t"
-      "mbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, P;\n\t}"
-      : "=r"(ok)
-      : "r"(bar_addr), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-// Non-blocking probe of a phase (mbarrier.test_wait): issued ahead of time, its latency overlaps what follows.
-__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred P;\n\t"
-      "mbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, P;\n\t}"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok != 0;
 }
 // Bounded: a protocol bug must surface as a launch failure, never as a hung GPU (the clock is consulted only every
 // 1024 failed tries).
@@ -151,20 +86,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
-__device__ __forceinline__ void st_shared_f32(uint32_t addr, float v) {
-  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
-}
-__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
 __device__ __forceinline__ void st_shared_v2(uint32_t addr, uint32_t a, uint32_t b) {
   asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
 }
 __device__ __forceinline__ void ld_shared_v2(uint32_t addr, uint32_t& a, uint32_t& b) {
   asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(a), "=r"(b) : "r"(addr) : "memory");
-}
-__device__ __forceinline__ void ld_shared_v4(uint32_t addr, uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d) {
-  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(addr) : "memory");
 }
 __device__ __forceinline__ float ld_shared_f32(uint32_t addr) {
   float v;
@@ -176,69 +102,17 @@ __device__ __forceinline__ float ld_shared_f32(uint32_t addr) {
 __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
-// 2-D tiled load, completes `bytes of box` on `bar`.  c0 = innermost (K) coordinate, c1 = row.
-__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar,
-                                            int32_t c0, int32_t c1, uint64_t cache_policy) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
-      " [%0], [%1, {%3, %4}], [%2], %5;"
-      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0),
-      "r"(c1), "l"(cache_policy)
-      : "memory");
-}
-// L2 prefetch of one box (no shared-memory destination, no completion): pulls HBM lines ahead of the real load
-__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int32_t c0, int32_t c1) {
-  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];"
-               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1)
-               : "memory");
-}
-__device__ __forceinline__ uint64_t policy_evict_first() {
-  uint64_t p;
-  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
-  return p;
-}
 __device__ __forceinline__ uint64_t policy_evict_last() {
   uint64_t p;
   asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
   return p;
 }
-__device__ __forceinline__ uint64_t policy_evict_normal() {
-  uint64_t p;
-  asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
-  return p;
-}
 
-// ------------------------------------------------------------------ tcgen05 / TMEM
-__device__ __forceinline__ void tmem_alloc(uint32_t* smem_result, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)),
-               "r"(ncols)
-               : "memory");
-}
-__device__ __forceinline__ void tmem_relinquish() {
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
 __device__ __forceinline__ void tc_fence_before() {
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
 }
 __device__ __forceinline__ void tc_fence_after() {
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-}
-// D[tmem] (+)= A[smem] * B[smem]; one thread issues for the whole CTA.
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                          uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// mbarrier arrive once every previously issued tcgen05.mma of this thread has completed.
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -256,31 +130,6 @@ __device__ __forceinline__ void tmem_ld_x32(uint32_t taddr, uint32_t (&r)[32]) {
         "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr)
       : "memory");
-}
-__device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]),
-        "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
-}
-// Warp-collective: lane l writes 32 consecutive 32-bit columns of TMEM lane (lane_base + l).
-__device__ __forceinline__ void tmem_st_x32(uint32_t taddr, const uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
-      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
-        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]),
-        "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]),
-        "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
-      : "memory");
-}
-__device__ __forceinline__ void tmem_st_wait() {
-  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 __device__ __forceinline__ uint32_t tmem_ld_x1(uint32_t taddr) {
   uint32_t r;
@@ -329,25 +178,6 @@ __device__ __forceinline__ void tmem_relinquish_cg2() {
 __device__ __forceinline__ void tmem_dealloc_cg2(uint32_t taddr, uint32_t ncols) {
   asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
-// D[tmem of both CTAs] (+)= A[rows 0-127: leader smem, 128-255: peer smem] * B[N/2 rows from each CTA's smem]
-__device__ __forceinline__ void umma_bf16_cg2(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                              uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// Same with the A operand read from TENSOR MEMORY: each CTA's 128 rows live in its own TMEM lanes, two bf16 of
-// consecutive k per 32-bit column (K = 16 of one instruction = 8 columns starting at `tmem_a`).
-__device__ __forceinline__ void umma_bf16_cg2_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
-                                                 uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
 // arrive (once the issuing thread's prior MMAs retire) on the barrier at this offset in every CTA of `cta_mask`
 __device__ __forceinline__ void umma_commit_cg2_mc(uint64_t* bar, uint16_t cta_mask) {
   asm volatile(
@@ -376,60 +206,6 @@ __device__ __forceinline__ void umma_bf16_cg2_lo(uint32_t tmem_d, uint32_t a_lo,
       ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kDescHiSw128)
       : "memory");
 }
-__device__ __forceinline__ void umma_bf16_cg2_ts_lo(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_lo, uint32_t idesc,
-                                                    uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "mov.b64 db, {%2, %5};\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], db, %3, p;\n\t}"
-      ::"r"(tmem_d), "r"(tmem_a), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kDescHiSw128)
-      : "memory");
-}
-// smem -> TMEM copy of 128 rows x 256 bits (16 bf16 of K per row: the A operand of ONE K = 16 MMA) described by the
-// same K-major SWIZZLE_128B descriptor the SS MMA would read; row r lands in TMEM lane r, 8 columns from `taddr`.
-// cta_group::2: executed by both CTAs of the pair on their own shared / tensor memory, ordered with the MMAs of the
-// issuing thread (tcgen05.cp and tcgen05.mma form one in-order pipe).
-__device__ __forceinline__ void tmem_cp_128x256b_cg2_lo(uint32_t taddr, uint32_t desc_lo) {
-  asm volatile(
-      "{\n\t.reg .b64 d;\n\tmov.b64 d, {%1, %2};\n\t"
-      "tcgen05.cp.cta_group::2.128x256b [%0], d;\n\t}"
-      ::"r"(taddr), "r"(desc_lo), "r"(kDescHiSw128)
-      : "memory");
-}
-// The four K = 16 MMAs of one 64-wide K block in ONE statement (descriptor low words advance by 2 = 32 bytes, the
-// TMEM A address by 8 columns per step); `acc_first` = 0 only for the very first MMA of an accumulator.
-__device__ __forceinline__ void umma_kblock_cg2_ss(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc,
-                                                   uint32_t acc_first) {
-  asm volatile(
-      "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t.reg .b32 a, b;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\tsetp.eq.u32 q, %0, %0;\n\t"
-      "mov.b64 da, {%1, %5};\n\tmov.b64 db, {%2, %5};\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, p;\n\t"
-      "add.u32 a, %1, 2;\n\tadd.u32 b, %2, 2;\n\tmov.b64 da, {a, %5};\n\tmov.b64 db, {b, %5};\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, q;\n\t"
-      "add.u32 a, %1, 4;\n\tadd.u32 b, %2, 4;\n\tmov.b64 da, {a, %5};\n\tmov.b64 db, {b, %5};\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, q;\n\t"
-      "add.u32 a, %1, 6;\n\tadd.u32 b, %2, 6;\n\tmov.b64 da, {a, %5};\n\tmov.b64 db, {b, %5};\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, q;\n\t}"
-      ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(acc_first), "r"(kDescHiSw128)
-      : "memory");
-}
-__device__ __forceinline__ void umma_kblock_cg2_ts(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_lo, uint32_t idesc,
-                                                   uint32_t acc_first) {
-  asm volatile(
-      "{\n\t.reg .pred p, q;\n\t.reg .b64 db;\n\t.reg .b32 a, b;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\tsetp.eq.u32 q, %0, %0;\n\t"
-      "mov.b64 db, {%2, %5};\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], db, %3, p;\n\t"
-      "add.u32 a, %1, 8;\n\tadd.u32 b, %2, 2;\n\tmov.b64 db, {b, %5};\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], [a], db, %3, q;\n\t"
-      "add.u32 a, %1, 16;\n\tadd.u32 b, %2, 4;\n\tmov.b64 db, {b, %5};\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], [a], db, %3, q;\n\t"
-      "add.u32 a, %1, 24;\n\tadd.u32 b, %2, 6;\n\tmov.b64 db, {b, %5};\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], [a], db, %3, q;\n\t}"
-      ::"r"(tmem_d), "r"(tmem_a), "r"(b_lo), "r"(idesc), "r"(acc_first), "r"(kDescHiSw128)
-      : "memory");
-}
 // commit with the barrier given as a shared-space address
 __device__ __forceinline__ void umma_commit_cg2_mc_addr(uint32_t bar_addr, uint16_t cta_mask) {
   asm volatile(
@@ -438,23 +214,6 @@ __device__ __forceinline__ void umma_commit_cg2_mc_addr(uint32_t bar_addr, uint1
       : "memory");
 }
 
-// ------------------------------------------------------------------ UMMA descriptors
-// Shared-memory matrix descriptor for a K-major bf16 tile stored as rows of 128 bytes
-// (64 elements) with the 128-byte swizzle TMA writes (CU_TENSOR_MAP_SWIZZLE_128B):
-//   bits [0,14)  start address >> 4
-//   bits [16,30) leading-dim byte offset >> 4 (ignored for swizzled K-major; canonical 1)
-//   bits [32,46) stride byte offset >> 4 = 1024 B between 8-row groups
-//   bits [46,48) descriptor version = 1 on sm_100
-//   bits [61,64) layout type: 2 = SWIZZLE_128B
-__device__ __forceinline__ uint64_t umma_smem_desc_sw128(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
-  d |= static_cast<uint64_t>(1) << 16;
-  d |= static_cast<uint64_t>(1024 >> 4) << 32;
-  d |= static_cast<uint64_t>(1) << 46;
-  d |= static_cast<uint64_t>(2) << 61;
-  return d;
-}
 // Instruction descriptor, kind::f16: D = fp32, A = B = bf16, both K-major, dense.
 //   [4,6) c_format = 1 (F32)   [7,10) a_format = 1 (BF16)   [10,13) b_format = 1 (BF16)
 //   [15] a_major = 0 (K)       [16] b_major = 0 (K)
