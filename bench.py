@@ -395,8 +395,21 @@ def run_ours(args):
     nomerge = ops.HGR_IMPL_TCGEN05 | _cabi.HGR_IMPL_FLAG_NO_MERGE
     xs = [ops.normalize_rows(f) for f in feats_dev]
 
+    global_cert = world > 1 and getattr(ses, "certify", "local") == "global"
+    list_len = ops.score_topk_plan(B, Cs, D, K)["list_len"] if Cs > 0 else K
+    if global_cert:
+        # the kernel a rank really runs: lists sized for the GLOBAL certificate (hgr_score_topk_scatter_bounded);
+        # NO_MERGE: the scoring kernel alone, nothing is scattered (the block tables are not dereferenced)
+        list_len = ops.global_list_len(B, Cs, D, K, C)
+        dummy = [xs[0].data_ptr()] * world
+        blk = (B + world - 1) // world
+
     def kern_eager(i):
-        ops.score_topk(xs[i % n_feat], banks[i % n_bank], K=K, impl=nomerge)
+        if global_cert:
+            ops.score_topk_scatter(xs[i % n_feat], ses.banks[i % n_bank], dummy, dummy, blk, K=K, impl=nomerge,
+                                   bound_block_ptrs=dummy, C_total=C)
+        else:
+            ops.score_topk(xs[i % n_feat], banks[i % n_bank], K=K, impl=nomerge)
 
     # ONE graph holding `cycle` back-to-back launches (rotating inputs): a launch's duration, not a graph launch's
     kst = torch.cuda.Stream()
@@ -686,6 +699,11 @@ def run_ours(args):
                                      if args.exchange == "p2p" else
                                      "NCCL all-gather of batch i overlaps the GEMM of batch i+1")),
                      "exchange": None if world == 1 else args.exchange,
+                     "lists": ("%d-entry lists per (row, worker), sized for the row's GLOBAL stream and certified by the row "
+                               "owner against the global K-th value (hgr_score_topk_scatter_bounded / "
+                               "hgr_topk_merge_certified); rows repaired on rank 0 in this run: %d"
+                               % (list_len, int(ses.repairs.item()))) if global_cert
+                              else "%d-entry lists per (row, worker), certificate + exact repair inside the call" % list_len,
                      "bank_rows": "pseudo-random order (tree_model.update_classifier), col_id maps back to node ids",
                      "timing": "value = median of %d blocks of %d steps (fastest %.4f ms, slowest %.4f ms per block)"
                                % (n_blocks, steps, ms_best, ms_worst),

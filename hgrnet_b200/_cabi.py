@@ -43,6 +43,13 @@ SIGNATURES = {
     "hgr_peer_free": (c_int, [c_void_p]),
     "hgr_score_topk_scatter": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int64, c_int64, c_int64, c_float, c_int,
                                        c_void_p, c_size_t, c_int64, c_int, c_void_p, c_void_p, c_int, c_void_p]),
+    "hgr_score_topk_global_list_len": (c_int, [c_int64, c_int64, c_int64, c_int, c_int64]),
+    "hgr_score_topk_scatter_bounded": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int64, c_int64, c_int64, c_float,
+                                               c_int, c_void_p, c_size_t, c_int64, c_int, c_void_p, c_void_p, c_void_p,
+                                               c_int64, c_int, c_void_p]),
+    "hgr_topk_merge_certified": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int64, c_int64,
+                                         c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_float,
+                                         c_void_p, c_void_p]),
     "hgr_normalize_rows_bcast": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_int, c_void_p, c_void_p]),
     "hgr_peer_signal": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
     "hgr_peer_wait": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),

@@ -66,11 +66,15 @@ int launch_aggregate_normalize(const void* E, int e_dtype, int64_t n_src, int64_
 // dense [block_rows, K] array).  The pointers may be PEER memory (another GPU's exchange buffer mapped over NVLink):
 // the class-sharded head writes every rank's candidates straight into the buffers of the rank that owns the rows.
 constexpr int kMaxScatterBlocks = 16;
+// `bound` (global certificate of the class-sharded head, see hgr_score_topk_scatter_bounded): next to the final list of
+// a row the producer stores an upper bound of every candidate its narrow lists may have dropped (-inf: none).
 struct OutScatter {
   int n_blocks = 0;
+  int emit_bound = 0;
   int64_t block_rows = 0;
   float* val[kMaxScatterBlocks];
   int32_t* idx[kMaxScatterBlocks];
+  float* bound[kMaxScatterBlocks];
 };
 
 struct MergeArgs {
@@ -99,6 +103,17 @@ struct MergeArgs {
   const uint2* sk_part = nullptr;
   const int32_t* sk_cnt = nullptr;
   int sk_cap = 0;
+  // owner side of the global certificate (hgr_topk_merge_certified): list p comes from class shard p, and everything
+  // that shard dropped for a row is <= part_bound[p * bound_stride + row].  A row whose merged K-th value does not
+  // beat every bound strictly is repaired exactly: the doubtful shards are re-scanned (shards[p], device memory,
+  // possibly a peer's bank over NVLink) with the row's features xrows[row] and the producers' logit scale.
+  const float* part_bound = nullptr;
+  int64_t bound_stride = 0;
+  const hgr_shard_t* shards = nullptr;
+  const void* xrows = nullptr;
+  int xD8 = 0;
+  float shard_scale = 1.f;
+  unsigned int* repair_count = nullptr;
 };
 int launch_topk_merge(const MergeArgs& args, cudaStream_t stream);
 
@@ -114,11 +129,14 @@ int launch_logits_simt(const __nv_bfloat16* X, const __nv_bfloat16* bank, int64_
 size_t umma_score_workspace_bytes(int64_t B, int64_t C, int K);
 bool umma_supported(int64_t B, int64_t C, int64_t D, int K);
 void umma_plan(int64_t B, int64_t C, int64_t D, int K, int32_t* plan);
+// C_total > 0 (with scatter->emit_bound): the lists are sized for a row's GLOBAL stream of C_total classes, of which
+// this bank is one shard -- no local certificate / repair, the owner of the row certifies against the global K-th value
 int launch_score_topk_umma(const __nv_bfloat16* X, const __nv_bfloat16* bank, const int32_t* col_id,
                            int32_t id_base, const int32_t* targets, int64_t B, int64_t C, int64_t D,
                            float scale, int K, void* ws, size_t ws_bytes, float* topk_val,
                            int32_t* topk_idx, int64_t* hits, int variant, bool skip_merge,
-                           cudaStream_t stream, const OutScatter* scatter = nullptr);
+                           cudaStream_t stream, const OutScatter* scatter = nullptr, int64_t C_total = 0);
+int umma_global_list_len(int64_t B, int64_t C, int64_t D, int K, int64_t C_total);
 
 int launch_hier_metrics(const float* logits, int64_t ldl, int64_t B, const int32_t* cols, int64_t M,
                         const int8_t* level, int n_levels, const int32_t* first_out, const int32_t* chain,

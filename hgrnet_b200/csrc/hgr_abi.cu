@@ -94,7 +94,7 @@ size_t hgr_score_topk_workspace_bytes(int64_t B, int64_t C, int64_t D, int K) {
 static int score_topk_impl(const void* X, const void* bank, const int32_t* col_id, int32_t id_base, const int32_t* targets,
                            int64_t B, int64_t C, int64_t D, float scale, int K, void* workspace, size_t workspace_bytes,
                            float* topk_val, int32_t* topk_idx, int64_t* hits, int impl, void* stream,
-                           const OutScatter* scatter) {
+                           const OutScatter* scatter, int64_t C_total = 0) {
   HGR_CHECK_ARG(B >= 0 && C >= 0, "hgr_score_topk: negative size");
   HGR_CHECK_ARG(D > 0 && D % 8 == 0, "hgr_score_topk: D = %lld must be a positive multiple of 8", (long long)D);
   HGR_CHECK_ARG(K >= 1 && K <= HGR_TOPK_MAX, "hgr_score_topk: K = %d outside [1, %d]", K, HGR_TOPK_MAX);
@@ -125,7 +125,7 @@ static int score_topk_impl(const void* X, const void* bank, const int32_t* col_i
     const int variant = which - HGR_IMPL_TCGEN05;  // umma::Variant
     return launch_score_topk_umma(static_cast<const __nv_bfloat16*>(X), static_cast<const __nv_bfloat16*>(bank), col_id,
                                   id_base, targets, B, C, D, scale, K, workspace, workspace_bytes, topk_val, topk_idx,
-                                  hits, variant, skip_merge || which == HGR_IMPL_TCGEN05_NULL, s, scatter);
+                                  hits, variant, skip_merge || which == HGR_IMPL_TCGEN05_NULL, s, scatter, C_total);
   }
   if (which == HGR_IMPL_SIMT)
     return launch_score_topk_simt(static_cast<const __nv_bfloat16*>(X), static_cast<const __nv_bfloat16*>(bank), col_id,
@@ -149,25 +149,54 @@ int hgr_score_topk(const void* X, const void* bank, const int32_t* col_id, int32
                          topk_idx, hits, impl, stream, nullptr);
 }
 
-int hgr_score_topk_scatter(const void* X, const void* bank, const int32_t* col_id, int32_t id_base, int64_t B, int64_t C,
-                           int64_t D, float scale, int K, void* workspace, size_t workspace_bytes, int64_t block_rows,
-                           int n_blocks, float* const* val_blocks, int32_t* const* idx_blocks, int impl, void* stream) {
+static int score_topk_scatter_impl(const void* X, const void* bank, const int32_t* col_id, int32_t id_base, int64_t B,
+                                   int64_t C, int64_t D, float scale, int K, void* workspace, size_t workspace_bytes,
+                                   int64_t block_rows, int n_blocks, float* const* val_blocks, int32_t* const* idx_blocks,
+                                   float* const* bound_blocks, int64_t C_total, int impl, void* stream) {
   HGR_CHECK_ARG(n_blocks >= 1 && n_blocks <= kMaxScatterBlocks, "hgr_score_topk_scatter: n_blocks = %d outside [1, %d]",
                 n_blocks, kMaxScatterBlocks);
   HGR_CHECK_ARG(block_rows >= 1 && block_rows * n_blocks >= B, "hgr_score_topk_scatter: %d blocks of %lld rows do not cover B = %lld",
                 n_blocks, (long long)block_rows, (long long)B);
   HGR_CHECK_ARG(val_blocks && idx_blocks, "hgr_score_topk_scatter: null block tables");
-  HGR_CHECK_ARG((impl & HGR_IMPL_FLAG_NO_MERGE) == 0, "hgr_score_topk_scatter: NO_MERGE makes no sense here");
+  // (NO_MERGE with bounds: diagnostics -- the scoring kernel alone with the list length of the global certificate;
+  //  nothing is scattered, the block tables are not dereferenced)
+  HGR_CHECK_ARG((impl & HGR_IMPL_FLAG_NO_MERGE) == 0 || bound_blocks != nullptr, "hgr_score_topk_scatter: NO_MERGE makes no sense here");
   OutScatter sc;
   sc.n_blocks = n_blocks;
   sc.block_rows = block_rows;
+  sc.emit_bound = bound_blocks != nullptr;
   for (int g = 0; g < n_blocks; ++g) {
     HGR_CHECK_ARG(val_blocks[g] && idx_blocks[g], "hgr_score_topk_scatter: null block %d", g);
+    HGR_CHECK_ARG(bound_blocks == nullptr || bound_blocks[g], "hgr_score_topk_scatter_bounded: null bound block %d", g);
     sc.val[g] = val_blocks[g];
     sc.idx[g] = idx_blocks[g];
+    sc.bound[g] = bound_blocks ? bound_blocks[g] : nullptr;
   }
   return score_topk_impl(X, bank, col_id, id_base, nullptr, B, C, D, scale, K, workspace, workspace_bytes, nullptr, nullptr,
-                         nullptr, impl, stream, &sc);
+                         nullptr, impl, stream, &sc, C_total);
+}
+
+int hgr_score_topk_scatter(const void* X, const void* bank, const int32_t* col_id, int32_t id_base, int64_t B, int64_t C,
+                           int64_t D, float scale, int K, void* workspace, size_t workspace_bytes, int64_t block_rows,
+                           int n_blocks, float* const* val_blocks, int32_t* const* idx_blocks, int impl, void* stream) {
+  return score_topk_scatter_impl(X, bank, col_id, id_base, B, C, D, scale, K, workspace, workspace_bytes, block_rows,
+                                 n_blocks, val_blocks, idx_blocks, nullptr, 0, impl, stream);
+}
+
+int hgr_score_topk_scatter_bounded(const void* X, const void* bank, const int32_t* col_id, int32_t id_base, int64_t B,
+                                   int64_t C, int64_t D, float scale, int K, void* workspace, size_t workspace_bytes,
+                                   int64_t block_rows, int n_blocks, float* const* val_blocks, int32_t* const* idx_blocks,
+                                   float* const* bound_blocks, int64_t C_total, int impl, void* stream) {
+  HGR_CHECK_ARG(bound_blocks != nullptr, "hgr_score_topk_scatter_bounded: null bound table");
+  HGR_CHECK_ARG(C_total >= C, "hgr_score_topk_scatter_bounded: C_total = %lld < C = %lld", (long long)C_total, (long long)C);
+  return score_topk_scatter_impl(X, bank, col_id, id_base, B, C, D, scale, K, workspace, workspace_bytes, block_rows,
+                                 n_blocks, val_blocks, idx_blocks, bound_blocks, C_total, impl, stream);
+}
+
+int hgr_score_topk_global_list_len(int64_t B, int64_t C, int64_t D, int K, int64_t C_total) {
+  HGR_CHECK_ARG(K >= 1 && K <= HGR_TOPK_MAX, "hgr_score_topk_global_list_len: K = %d outside [1, %d]", K, HGR_TOPK_MAX);
+  if (!umma_supported(B, C, D, K)) return set_error(HGR_ERR_UNSUPPORTED, "hgr_score_topk_global_list_len: shape not supported by the tcgen05 kernel");
+  return umma_global_list_len(B, C, D, K, C_total);
 }
 
 int hgr_peer_alloc(size_t bytes, void** ptr, unsigned char* handle) {
@@ -251,6 +280,42 @@ int hgr_topk_merge(const float* part_val, const int32_t* part_idx, int64_t P, in
   m.topk_val = topk_val;
   m.topk_idx = topk_idx;
   m.hits = hits;
+  return launch_topk_merge(m, static_cast<cudaStream_t>(stream));
+}
+
+int hgr_topk_merge_certified(const float* part_val, const int32_t* part_idx, const float* part_bound, int64_t P, int64_t B,
+                             int K, int64_t part_stride, int64_t bound_stride, const int32_t* targets, float* topk_val,
+                             int32_t* topk_idx, int64_t* hits, const void* X, int64_t D, const hgr_shard_t* shards,
+                             float scale, unsigned int* repair_count, void* stream) {
+  HGR_CHECK_ARG(P >= 1 && P <= kMaxScatterBlocks && B >= 0, "hgr_topk_merge_certified: P = %lld outside [1, %d]", (long long)P,
+                kMaxScatterBlocks);
+  HGR_CHECK_ARG(K >= 1 && K <= HGR_TOPK_MAX, "hgr_topk_merge_certified: K = %d outside [1, %d]", K, HGR_TOPK_MAX);
+  if (B == 0) return HGR_OK;
+  HGR_CHECK_ARG(topk_val && topk_idx && part_val && part_idx && part_bound, "hgr_topk_merge_certified: null lists / bounds / output");
+  HGR_CHECK_ARG(X && shards && D > 0 && D % 8 == 0 && aligned16(X), "hgr_topk_merge_certified: the repair needs X (16-byte aligned, D %% 8 == 0) and the shard table");
+  HGR_CHECK_ARG(part_stride == 0 || part_stride >= B * K, "hgr_topk_merge_certified: part_stride < B*K");
+  HGR_CHECK_ARG(bound_stride >= B, "hgr_topk_merge_certified: bound_stride < B");
+  HGR_CHECK_ARG(scale > 0.f, "hgr_topk_merge_certified: scale must be > 0");
+  MergeArgs m{};
+  m.part_val = part_val;
+  m.part_idx = part_idx;
+  m.P = P;
+  m.B = B;
+  m.KL = K;
+  m.K = K;
+  m.part_stride = part_stride;
+  m.scale = 1.f;
+  m.targets = targets;
+  m.topk_val = topk_val;
+  m.topk_idx = topk_idx;
+  m.hits = hits;
+  m.part_bound = part_bound;
+  m.bound_stride = bound_stride;
+  m.shards = shards;
+  m.xrows = X;
+  m.xD8 = static_cast<int>(D / 8);
+  m.shard_scale = scale;
+  m.repair_count = repair_count;
   return launch_topk_merge(m, static_cast<cudaStream_t>(stream));
 }
 

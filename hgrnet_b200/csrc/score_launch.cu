@@ -136,6 +136,9 @@ double max_list_share(const Sched& s, int wpq) {
 int pick_list_len(int K, int64_t B, int64_t C, int64_t D, int lists_per_row, double share, bool allow_speculation) {
   const int exact = K <= 8 ? 8 : (K <= 12 ? 12 : (K <= 20 ? 20 : 32));
   if (!allow_speculation) return exact;
+#ifdef HGR_FORCE_KL   // kernel experiments (tools/build_variant.sh): the list length the policy is NOT allowed to pick
+  if (HGR_FORCE_KL < K) return HGR_FORCE_KL;
+#endif
   const int cand[4] = {8, 10, 12, 16};
   for (int i = 0; i < 4; ++i) {
     const int kl = cand[i];
@@ -148,7 +151,34 @@ int pick_list_len(int K, int64_t B, int64_t C, int64_t D, int lists_per_row, dou
   return exact;
 }
 
+// Class shard of a row's GLOBAL stream (hgr_score_topk_scatter_bounded): the certificate is taken by the owner of the
+// row against the global K-th value, so what counts is the share of the GLOBAL stream one list holds, and a repair
+// re-scans the doubtful shard completely with one warp, possibly over NVLink (budgeted at 1.5 us per bank row of 1024
+// elements).  N = 8 (4 lists of 683 of 21,841 columns per row and rank): KL = 10, 2e-5 repairs per batch; N = 4:
+// KL = 12; N = 2: KL = 16.
+int pick_list_len_global(int K, int64_t B, int64_t C, int64_t D, int64_t C_total, const Sched& s) {
+  const int exact = K <= 8 ? 8 : (K <= 12 ? 12 : (K <= 20 ? 20 : 32));
+  if (C_total < C) C_total = C;
+  const double cols = static_cast<double>((s.T + s.G - 1) / s.G) * kUnit;           // columns of the largest list
+  const double share = cols / static_cast<double>(C_total) > 1.0 ? 1.0 : cols / static_cast<double>(C_total);
+  const double lists = static_cast<double>(s.P) * static_cast<double>(C_total) / static_cast<double>(C);
+  const int cand[4] = {8, 10, 12, 16};
+  for (int i = 0; i < 4; ++i) {
+    const int kl = cand[i];
+    if (kl >= K) break;
+    const double repairs = static_cast<double>(B) * lists * overflow_bound(K, kl, share);
+    const double t_repair = static_cast<double>(C) * (static_cast<double>(D) / 1024.0) * 1.5e-6;
+    const double t_call = 2.0 * static_cast<double>(B) * static_cast<double>(C) * static_cast<double>(D) / (0.6 * 1.6e15);
+    if (repairs * t_repair < 0.015 * t_call) return kl;
+  }
+  return exact;
+}
+
 }  // namespace
+
+int umma_global_list_len(int64_t B, int64_t C, int64_t D, int K, int64_t C_total) {
+  return pick_list_len_global(K, B, C, D, C_total, pick_sched(B, C));
+}
 
 // floor-sketch epilogue: [B][20] floor words, [P][B] list lengths, [P][B][kSkCap] (value, bank row) entries
 static size_t sketch_workspace_bytes(int64_t B, int P) {
@@ -186,7 +216,8 @@ void umma_plan(int64_t B, int64_t C, int64_t D, int K, int32_t* plan) {
 int launch_score_topk_umma(const __nv_bfloat16* X, const __nv_bfloat16* bank, const int32_t* col_id,
                            int32_t id_base, const int32_t* targets, int64_t B, int64_t C, int64_t D, float scale,
                            int K, void* ws, size_t ws_bytes, float* topk_val, int32_t* topk_idx, int64_t* hits,
-                           int variant, bool skip_merge, cudaStream_t stream, const OutScatter* scatter) {
+                           int variant, bool skip_merge, cudaStream_t stream, const OutScatter* scatter,
+                           int64_t C_total) {
   // variants: kVarProd   production: deferred-insert lists, speculative (KL < K) when provably cheap
   //           kVarExact  the same kernel with K-entry lists (no speculation)
   //           kVarNull   main loop with a trivial epilogue (ceiling; NOT a top-k) -- diagnostics only
@@ -218,7 +249,9 @@ int launch_score_topk_umma(const __nv_bfloat16* X, const __nv_bfloat16* bank, co
     m.sk_cap = kSkCap;
     m.KL = K;
   } else {
-    const int KL = pick_list_len(K, B, C, D, p.sched.P, max_list_share(p.sched, 1), variant == kVarProd);
+    const bool global_cert = variant == kVarProd && C_total > 0 && scatter != nullptr && scatter->emit_bound != 0;
+    const int KL = global_cert ? pick_list_len_global(K, B, C, D, C_total, p.sched)
+                               : pick_list_len(K, B, C, D, p.sched.P, max_list_share(p.sched, 1), variant == kVarProd);
     p.KL = KL;
     p.part_val = reinterpret_cast<float*>(static_cast<uint8_t*>(ws) + kWsHeaderBytes);
     p.part_idx = reinterpret_cast<int32_t*>(p.part_val + static_cast<size_t>(p.sched.P) * B * KL);

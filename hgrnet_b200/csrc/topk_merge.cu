@@ -90,38 +90,102 @@ __device__ __noinline__ void repair_row(const RepairArgs a, int64_t row, int lan
   }
 }
 
+// Exact repair of a row of the class-sharded head whose GLOBAL certificate failed (hgr_topk_merge_certified): list p
+// is shard p's final local top-K (node ids, scaled values).  A doubtful shard (bit p of `dm`: its bound reaches the
+// merged K-th value) is re-scanned completely with the row's features -- over NVLink when the bank is a peer's --, its
+// exact local top-K mapped to node ids and scaled like the producer did; the lists of the other shards are final as
+// they are (what such a shard dropped is below the old K-th value, which can only rise).
+__device__ __noinline__ void repair_row_global(const float* part_val, const int32_t* part_idx, int64_t pstride,
+                                               int64_t row, int K, int P, unsigned dm, const uint4* xrow, int D8,
+                                               const hgr_shard_t* shards, float scale, int lane,
+                                               SortedList<HGR_TOPK_MAX>& full) {
+  full.init();
+  for (int p = 0; p < P; ++p) {
+    if ((dm >> p) & 1u) {
+      const hgr_shard_t sh = shards[p];
+      SortedList<HGR_TOPK_MAX> sub;
+      sub.init();
+      if (sh.C > 0)
+        scan_row_range_lanes<HGR_TOPK_MAX>(xrow, reinterpret_cast<const uint4*>(sh.bank), 0, sh.C, D8, lane, sub);
+#pragma unroll
+      for (int k = 0; k < HGR_TOPK_MAX; ++k) {
+        const int32_t it = sub.i[k];
+        const float v = sub.v[k] * scale;
+        if (it >= 0 && v > full.thr()) full.insert(v, sh.col_id ? sh.col_id[it] : sh.id_base + it);
+      }
+    } else {
+      for (int k = 0; k < K; ++k) {
+        const int64_t g = p * pstride + row * K + k;
+        const int32_t it = part_idx[g];
+        const float v = part_val[g];
+        if (it >= 0 && v > full.thr()) full.insert(v, it);
+      }
+    }
+  }
+}
+
+// Everything the rare repair paths need lives in the frame of this one cold function (two 32-entry lists), so that the
+// merge kernels themselves keep their register count and carry no stack.  `a` points at the kernel's __grid_constant__
+// parameter.  Returns rank `lane` of the repaired row.
+__device__ __noinline__ Cand repair_cold(const MergeArgs* a, int64_t row, int lane, int cnt, const uint32_t* dmask,
+                                         unsigned dm_global) {
+  SortedList<HGR_TOPK_MAX> full;
+  if (dm_global != 0u) {
+    if (lane == 0 && a->repair_count) atomicAdd(a->repair_count, 1u);
+    repair_row_global(a->part_val, a->part_idx, a->part_stride > 0 ? a->part_stride : a->B * a->K, row, a->K,
+                      static_cast<int>(a->P), dm_global, reinterpret_cast<const uint4*>(a->xrows) + row * a->xD8, a->xD8,
+                      a->shards, a->shard_scale, lane, full);
+  } else {
+    if (lane == 0 && a->rescan_count) atomicAdd(a->rescan_count, 1u);
+    RepairArgs ra;
+    ra.part_val = a->part_val;
+    ra.part_idx = a->part_idx;
+    ra.pstride = a->part_stride > 0 ? a->part_stride : a->B * a->KL;
+    ra.C = a->C;
+    ra.X = a->X;
+    ra.bank = a->bank;
+    ra.sched = a->sched;
+    ra.KL = a->KL;
+    ra.wpq = a->wpq;
+    ra.D8 = a->D8;
+    repair_row(ra, row, lane, cnt, dmask, full);
+  }
+  Cand c;
+  c.v = -INFINITY;
+  c.i = -1;
+#pragma unroll
+  for (int k = 0; k < HGR_TOPK_MAX; ++k) {
+    if (lane == k) {
+      c.v = full.v[k];
+      c.i = full.i[k];
+    }
+  }
+  return c;
+}
+
 // Tail shared by both merge kernels.  Lane r holds rank r of the merged list (my_v, my_i = bank row or -1).
 // `dmask` (per-warp shared memory, one bit per list): full speculative lists that end at or above the merged K-th
 // value -> the row is repaired exactly (repair_row).  Then: bank row -> node id, scale, store (dense or row-block
 // scatter), Hit@k.
+// `tailmax`: lane-local largest last entry of a FULL narrow list (-inf: none) -- what the producer of a class shard
+// reports as its bound when the certificate is left to the owner of the row (scatter.emit_bound).
 __device__ __forceinline__ void finish_row(const MergeArgs& a, int64_t row, int lane, float my_v, int32_t my_i,
-                                           bool doubt, const uint32_t* dmask, int cnt, int* s_hits) {
+                                           bool doubt, const uint32_t* dmask, int cnt, int* s_hits,
+                                           float tailmax = -INFINITY) {
   const int K = a.K;
-  if (a.KL < K && __any_sync(0xffffffffu, doubt)) {
-    if (lane == 0 && a.rescan_count) atomicAdd(a.rescan_count, 1u);
+  const bool emit_bound = a.scatter.n_blocks > 0 && a.scatter.emit_bound != 0;
+  unsigned dm = 0u;
+  if (a.part_bound != nullptr) {  // owner side of the global certificate: list p = shard p
+    const float kth = __shfl_sync(0xffffffffu, my_i >= 0 ? my_v : -INFINITY, K - 1);
+    const float bnd = lane < a.P ? a.part_bound[lane * a.bound_stride + row] : -INFINITY;
+    dm = __ballot_sync(0xffffffffu, bnd > -INFINITY && bnd >= kth);
+  }
+  const bool local_doubt = a.KL < K && !emit_bound && __any_sync(0xffffffffu, doubt);
+  if (dm != 0u || local_doubt) {
     __syncwarp();
-    SortedList<HGR_TOPK_MAX> full;
-    RepairArgs ra;
-    ra.part_val = a.part_val;
-    ra.part_idx = a.part_idx;
-    ra.pstride = a.part_stride > 0 ? a.part_stride : a.B * a.KL;
-    ra.C = a.C;
-    ra.X = a.X;
-    ra.bank = a.bank;
-    ra.sched = a.sched;
-    ra.KL = a.KL;
-    ra.wpq = a.wpq;
-    ra.D8 = a.D8;
-    repair_row(ra, row, lane, cnt, dmask, full);
-    my_v = -INFINITY;
-    my_i = -1;
-#pragma unroll
-    for (int k = 0; k < HGR_TOPK_MAX; ++k) {
-      if (lane == k) {
-        my_v = full.v[k];
-        my_i = full.i[k];
-      }
-    }
+    const Cand c = repair_cold(&a, row, lane, cnt, dmask, dm);
+    my_v = c.v;
+    my_i = c.i;
   }
   int32_t gid = -1;
   if (lane < K && my_i >= 0) gid = a.col_id ? a.col_id[my_i] : a.id_base + my_i;
@@ -138,6 +202,15 @@ __device__ __forceinline__ void finish_row(const MergeArgs& a, int64_t row, int 
     ov[orow * K + lane] = my_i >= 0 ? my_v * a.scale : -INFINITY;
     oi[orow * K + lane] = gid;
   }
+  if (emit_bound) {
+    float b = a.KL < K ? tailmax : -INFINITY;   // K-entry lists drop nothing that could matter
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) b = fmaxf(b, __shfl_xor_sync(0xffffffffu, b, o));
+    if (lane == 0) {
+      const int64_t g = row / a.scatter.block_rows;
+      a.scatter.bound[g][row - g * a.scatter.block_rows] = b * a.scale;
+    }
+  }
   if (a.hits && a.targets) {
     const int32_t target = a.targets[row];
     const unsigned m = __ballot_sync(0xffffffffu, lane < K && gid >= 0 && gid == target);
@@ -153,8 +226,8 @@ __device__ __forceinline__ void finish_row(const MergeArgs& a, int64_t row, int 
 // kMaxListsPerLane: 4 covers P <= 128 lists per row, 10 covers P <= 320 (one list per epilogue warp of
 // every CTA when a single row tile is spread over all 148 SMs)
 template <int kMaxListsPerLane>
-__global__ void __launch_bounds__(kMergeWarps * 32)
-topk_merge_kernel(const MergeArgs a) {
+__global__ void __launch_bounds__(kMergeWarps * 32, 7)  // (the cold repair functions must not set the register count)
+topk_merge_kernel(const __grid_constant__ MergeArgs a) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ int s_hits[HGR_NUM_HITS];
   __shared__ uint32_t s_dmask[kMergeWarps][kDoubtWords];
@@ -253,18 +326,22 @@ topk_merge_kernel(const MergeArgs a) {
     }
 
     bool doubt = false;
+    float tailmax = -INFINITY;
     if (KL < K) {
       // certificate for speculative (narrow) lists
 #pragma unroll
       for (int q = 0; q < kMaxListsPerLane; ++q) {
         const int p = lane + 32 * q;
-        if (p < cnt && li[p * KL + KL - 1] >= 0 && lv[p * KL + KL - 1] >= kth) {
-          doubt = true;
-          atomicOr(&s_dmask[warp][p >> 5], 1u << (p & 31));
+        if (p < cnt && li[p * KL + KL - 1] >= 0) {
+          tailmax = fmaxf(tailmax, lv[p * KL + KL - 1]);
+          if (lv[p * KL + KL - 1] >= kth) {
+            doubt = true;
+            atomicOr(&s_dmask[warp][p >> 5], 1u << (p & 31));
+          }
         }
       }
     }
-    finish_row(a, row, lane, my_v, my_i, doubt, s_dmask[warp], cnt, s_hits);
+    finish_row(a, row, lane, my_v, my_i, doubt, s_dmask[warp], cnt, s_hits, tailmax);
   }
   __syncthreads();
   if (a.hits && threadIdx.x < HGR_NUM_HITS && s_hits[threadIdx.x] != 0)
@@ -280,8 +357,8 @@ topk_merge_kernel(const MergeArgs a) {
 // ascending item, and the <= K winners are compacted and ranked by counting.  ~4x fewer instructions per row; the
 // result is the same (value desc, item asc) order.
 template <int NPL>
-__global__ void __launch_bounds__(kMergeWarps * 32)
-topk_select_kernel(const MergeArgs a) {
+__global__ void __launch_bounds__(kMergeWarps * 32, 7)  // (the cold repair functions must not set the register count)
+topk_select_kernel(const __grid_constant__ MergeArgs a) {
   __shared__ int s_hits[HGR_NUM_HITS];
   __shared__ unsigned long long s_win[kMergeWarps][32];
   __shared__ uint32_t s_dmask[kMergeWarps][kDoubtWords];
@@ -336,6 +413,10 @@ topk_select_kernel(const MergeArgs a) {
     float my_v = -INFINITY;
     int32_t my_i = -1;
     bool doubt = false;
+    float tailmax = -INFINITY;
+#pragma unroll
+    for (int s = 0; s < NPL; ++s)
+      if (tail[s]) tailmax = fmaxf(tailmax, val[s]);
     if (ksel > 0) {
       // largest T with #{key >= T} >= ksel
       uint32_t lo = kmin, hi = kmax;
@@ -400,7 +481,7 @@ topk_select_kernel(const MergeArgs a) {
         my_i = static_cast<int32_t>(~static_cast<uint32_t>(w));
       }
     }
-    finish_row(a, row, lane, my_v, my_i, doubt, s_dmask[warp], cnt, s_hits);
+    finish_row(a, row, lane, my_v, my_i, doubt, s_dmask[warp], cnt, s_hits, tailmax);
   }
   __syncthreads();
   if (a.hits && threadIdx.x < HGR_NUM_HITS && s_hits[threadIdx.x] != 0)
@@ -413,8 +494,8 @@ topk_select_kernel(const MergeArgs a) {
 // into shared memory (lane = list, one 8-byte entry per step), the K-th largest order key is found by bisection over
 // the gathered entries (stops early when a cut holds exactly K), ties at the cut resolve by ascending bank row, and the
 // <= K winners are ranked by counting on (key desc, bank row asc) -- the same documented order as the other paths.
-__global__ void __launch_bounds__(kMergeWarps * 32)
-topk_merge_counts_kernel(const MergeArgs a) {
+__global__ void __launch_bounds__(kMergeWarps * 32, 7)  // (the cold repair functions must not set the register count)
+topk_merge_counts_kernel(const __grid_constant__ MergeArgs a) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ int s_hits[HGR_NUM_HITS];
   __shared__ unsigned long long s_win[kMergeWarps][32];

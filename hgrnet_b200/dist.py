@@ -112,11 +112,13 @@ X_SLOTS = 4  # feature-ingest slots per exchange (ring length per channel: _ring
 def exchange_layout(B: int, K: int, world: int, slots: int, D: int = 0):
     """Byte layout of one rank's exchange buffer: a 256-byte header (list flags: one word per producer rank at
     byte 0, feature flags at byte 64), then per slot the value lists ``[world, block_rows, K]`` fp32 followed by
-    the id lists ``[world, block_rows, K]`` int32 and, when ``D`` is given, ``X_SLOTS`` replicas of the normalised
+    the id lists ``[world, block_rows, K]`` int32 and the bounds ``[world, block_rows]`` fp32 of the global certificate
+    (``hgr_score_topk_scatter_bounded``) and, when ``D`` is given, ``X_SLOTS`` replicas of the normalised
     image features ``[B, D]`` bf16 (feature ingest, see ``PeerExchange.ingest``)."""
     block_rows = (B + world - 1) // world
     part = block_rows * K * 4
-    slot_bytes = 2 * world * part
+    bound_bytes = (world * block_rows * 4 + 15) // 16 * 16     # per producer and row: bound of what the shard dropped
+    slot_bytes = 2 * world * part + bound_bytes
     x_off = (256 + slots * slot_bytes + 255) // 256 * 256
     x_bytes = (B * D * 2 + 255) // 256 * 256
     return {"block_rows": block_rows, "part_bytes": part, "slot_bytes": slot_bytes, "header": 256,
@@ -125,6 +127,97 @@ def exchange_layout(B: int, K: int, world: int, slots: int, D: int = 0):
 
 class PeerMemoryUnavailable(RuntimeError):
     """Raised by ``PeerExchange`` on EVERY rank when any rank could not set the exchange up."""
+
+
+def map_peer_buffers(nbytes: int, device, world: int, rank: int, group=None):
+    """Allocate ``nbytes`` of zeroed device memory on this rank (``hgr_peer_alloc``), swap the CUDA IPC handles through
+    ``torch.distributed`` and map every peer's allocation -> ``(own pointer, [pointer of rank g's buffer], [mapped])``.
+    A failure on ANY rank (no CUDA IPC in the container, no peer access between two GPUs, out of memory) is agreed on
+    collectively: every rank frees what it holds and raises ``PeerMemoryUnavailable``, so that callers can fall back
+    together (the NCCL exchange) instead of deadlocking in the next collective."""
+    err = None
+    own, handle = None, None
+    opened = []
+
+    def release():
+        for p in opened:
+            ops.peer_close(p)
+        if own is not None:
+            ops.peer_free(own)
+
+    with torch.cuda.device(device):
+        try:
+            own, handle = ops.peer_alloc(nbytes)
+        except Exception as e:  # noqa: BLE001 -- reported through the agreement below
+            err = e
+        if world == 1:
+            if err is not None:
+                raise PeerMemoryUnavailable("peer_alloc failed: %r" % (err,))
+            return own, [own], opened
+        handles = [None] * world
+        dist.all_gather_object(handles, handle, group=group)
+        bases = []
+        if err is None and all(h is not None for h in handles):
+            try:
+                for g in range(world):
+                    if g == rank:
+                        bases.append(own)
+                    else:
+                        bases.append(ops.peer_open(handles[g]))
+                        opened.append(bases[-1])
+            except Exception as e:  # noqa: BLE001
+                err = e
+        elif err is None:
+            err = RuntimeError("a peer could not allocate its exchange buffer")
+        oks = [None] * world
+        dist.all_gather_object(oks, err is None, group=group)
+        if not all(oks):
+            release()
+            raise PeerMemoryUnavailable("peer-memory exchange unavailable on rank(s) %s%s" % (
+                [g for g, ok in enumerate(oks) if not ok], "" if err is None else ": %r" % (err,)))
+        return own, bases, opened
+
+
+class PeerBank:
+    """A rank's class-bank shard (+ its node ids) in peer-visible memory, and the ``hgr_shard_t`` table of ALL ranks'
+    shards: what the owner of an image row needs to repair a row whose global certificate failed
+    (``hgr_topk_merge_certified`` re-scans the doubtful shard, over NVLink when it is a peer's)."""
+
+    def __init__(self, bank_shard: torch.Tensor, col_id: Optional[torch.Tensor], id_base: int, group=None):
+        self.device = bank_shard.device
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+        rank = dist.get_rank(group) if dist.is_initialized() else 0
+        C, D = bank_shard.shape
+        bank_bytes = (C * D * 2 + 255) // 256 * 256
+        nbytes = max(256, bank_bytes + (C * 4 if col_id is not None else 0))
+        self._own, bases, self._opened = map_peer_buffers(nbytes, self.device, world, rank, group)
+        raw = torch.as_tensor(_RawCuda(self._own, nbytes), device=self.device)
+        self.bank = raw[:C * D * 2].view(torch.bfloat16).view(C, D)
+        self.bank.copy_(bank_shard)
+        self.col_id = None
+        if col_id is not None:
+            self.col_id = raw[bank_bytes:bank_bytes + C * 4].view(torch.int32)
+            self.col_id.copy_(col_id)
+        meta = [None] * world
+        mine = (C, bank_bytes if col_id is not None else -1, int(id_base))
+        if world > 1:
+            dist.all_gather_object(meta, mine, group=group)
+        else:
+            meta = [mine]
+        self.table = ops.shard_table([(bases[g], bases[g] + meta[g][1] if meta[g][1] >= 0 else 0, meta[g][0], meta[g][2])
+                                      for g in range(world)], self.device)
+        self.C_total = sum(m[0] for m in meta)
+        torch.cuda.synchronize(self.device)
+        if world > 1:
+            dist.barrier(group=group)          # every shard is in place before anybody may re-scan it
+
+    def close(self) -> None:
+        for p in self._opened:
+            ops.peer_close(p)
+        self._opened = []
+        if self._own is not None:
+            ops.peer_free(self._own)
+            self._own = None
 
 
 class PeerExchange:
@@ -167,45 +260,7 @@ class PeerExchange:
         self.xflag_ptrs = [b + 64 + 4 * self.rank for b in self.bases]
 
     def _map_peers(self, group) -> None:
-        """Allocate this rank's buffer, swap the IPC handles, map every peer.  A failure on ANY rank (no CUDA IPC in
-        the container, no peer access between two GPUs, out of memory) is agreed on collectively: every rank frees
-        what it holds and raises ``PeerMemoryUnavailable``, so that callers can fall back together (the NCCL
-        exchange) instead of deadlocking in the next collective."""
-        err = None
-        own, handle = None, None
-        with torch.cuda.device(self.device):
-            try:
-                own, handle = ops.peer_alloc(self.lay["total"])
-                self._own = own
-            except Exception as e:  # noqa: BLE001 -- reported through the agreement below
-                err = e
-            if self.world == 1:
-                if err is not None:
-                    raise PeerMemoryUnavailable("peer_alloc failed: %r" % (err,))
-                self.bases = [own]
-                return
-            handles = [None] * self.world
-            dist.all_gather_object(handles, handle, group=group)
-            bases = []
-            if err is None and all(h is not None for h in handles):
-                try:
-                    for g in range(self.world):
-                        if g == self.rank:
-                            bases.append(own)
-                        else:
-                            bases.append(ops.peer_open(handles[g]))
-                            self._opened.append(bases[-1])
-                except Exception as e:  # noqa: BLE001
-                    err = e
-            elif err is None:
-                err = RuntimeError("a peer could not allocate its exchange buffer")
-            oks = [None] * self.world
-            dist.all_gather_object(oks, err is None, group=group)
-            if not all(oks):
-                self.close()
-                raise PeerMemoryUnavailable("peer-memory exchange unavailable on rank(s) %s%s" % (
-                    [g for g, ok in enumerate(oks) if not ok], "" if err is None else ": %r" % (err,)))
-            self.bases = bases
+        self._own, self.bases, self._opened = map_peer_buffers(self.lay["total"], self.device, self.world, self.rank, group)
 
     # -- addresses -------------------------------------------------------------------------------------------
     def _slot_base(self, base: int, slot: int) -> int:
@@ -217,6 +272,15 @@ class PeerExchange:
         val = [self._slot_base(b, slot) + self.rank * part for b in self.bases]
         idx = [self._slot_base(b, slot) + world * part + self.rank * part for b in self.bases]
         return val, idx
+
+    def bound_ptrs(self, slot: int):
+        """Where THIS rank's bounds of row block g go: row ``rank`` of the bound area of rank g's slot."""
+        off = 2 * self.world * self.lay["part_bytes"] + self.rank * self.block_rows * 4
+        return [self._slot_base(b, slot) + off for b in self.bases]
+
+    def local_bounds(self, slot: int) -> int:
+        """Pointer to the ``[world, block_rows]`` bounds received for my rows."""
+        return self._slot_base(self.bases[self.rank], slot) + 2 * self.world * self.lay["part_bytes"]
 
     def local_parts(self, slot: int):
         """(value pointer, id pointer, element stride) of the ``world`` lists received for my rows."""
@@ -245,21 +309,31 @@ class PeerExchange:
         return self.x_view(xslot)
 
     # -- per batch -------------------------------------------------------------------------------------------
-    def scatter(self, x_norm: torch.Tensor, bank: torch.Tensor, id_base: int, slot: int, col_id=None) -> None:
+    def scatter(self, x_norm: torch.Tensor, bank: torch.Tensor, id_base: int, slot: int, col_id=None,
+                C_total: int = 0) -> None:
+        """Score the batch against my shard and store the lists at their owners.  ``C_total`` > 0: narrow lists sized
+        for the GLOBAL certificate, with the bound of what was dropped next to every list (``merge(certify=...)``)."""
         val, idx = self.block_ptrs(slot)
-        ops.score_topk_scatter(x_norm, bank, val, idx, self.block_rows, col_id=col_id, id_base=id_base, K=self.K)
+        ops.score_topk_scatter(x_norm, bank, val, idx, self.block_rows, col_id=col_id, id_base=id_base, K=self.K,
+                               bound_block_ptrs=self.bound_ptrs(slot) if C_total else None, C_total=C_total)
         ops.peer_signal(self.flag_ptrs, self.seq[0:1])
 
     def merge(self, slot: int, targets: Optional[torch.Tensor], hits: Optional[torch.Tensor], out=None,
-              targets_local: bool = False):
+              targets_local: bool = False, certify=None):
         """Final top-K (+ hits) of MY rows ``[lo, hi)``; ``targets`` holds the labels of the whole batch (or of my
-        rows only with ``targets_local``)."""
+        rows only with ``targets_local``).  ``certify = (x_norm [B, D], shard table, repair counter)`` after a
+        ``scatter(C_total=...)``: rows whose K-th value does not beat every shard's bound are repaired exactly."""
         ops.peer_wait(self.bases[self.rank], self.world, self.seq[1:2])
         n = self.hi - self.lo
         if n <= 0:
             return None
         pv, pi, stride = self.local_parts(slot)
         t = None if targets is None else (targets if targets_local else targets[self.lo:self.hi])
+        if certify is not None:
+            x_norm, table, repairs = certify
+            return ops.topk_merge_certified(pv, pi, self.local_bounds(slot), self.world, n, self.K, stride, self.block_rows,
+                                            x_norm[self.lo:self.hi], table, self.device, targets=t, hits=hits,
+                                            repair_count=repairs, out=out)
         return ops.topk_merge_raw(pv, pi, self.world, n, self.K, stride, self.device, targets=t, hits=hits, out=out)
 
     def close(self) -> None:
@@ -299,9 +373,12 @@ class ShardedEvalStream:
 
     def __init__(self, bank_shard: torch.Tensor, id_base: int, *, batch: int, K: int = 20, steps: int = 8,
                  feat_dtype=torch.float32, banks=None, group=None, use_graph: bool = True, exchange: str = "p2p",
-                 channels: int = 4, host_io: bool = False, col_id: Optional[torch.Tensor] = None):
+                 channels: int = 4, host_io: bool = False, col_id: Optional[torch.Tensor] = None,
+                 certify: str = "global"):
         if exchange not in ("p2p", "nccl"):
             raise ValueError("exchange must be 'p2p' or 'nccl'")
+        if certify not in ("global", "local"):
+            raise ValueError("certify must be 'global' or 'local'")
         if host_io and exchange != "p2p":
             raise ValueError("host_io needs the peer-memory exchange")
         self.exchange, self.host_io = exchange, host_io
@@ -311,6 +388,20 @@ class ShardedEvalStream:
         self.col_id = col_id          # node id of every bank row of this shard (None: id_base + row)
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         D = bank_shard.shape[1]
+        # certify="global" (peer exchange only): the lists a rank keeps are sized for the row's GLOBAL stream and
+        # certified by the owner of the row against the global K-th value (hgr_score_topk_scatter_bounded /
+        # hgr_topk_merge_certified) -- a shard's own stream is too short for narrow lists to be certified locally, and
+        # exact 20-entry lists cost 39 us instead of 27 per call at the N = 8 shard.  The owner repairs an uncertified
+        # row by re-scanning the doubtful shard, so every rank's shard lives in peer-visible memory (PeerBank).
+        self.certify = certify if exchange == "p2p" else "local"
+        self.C_total = 0
+        self.repairs = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._x = [None] * steps
+        if self.certify == "global":
+            self.pbanks = [PeerBank(b, col_id, id_base, group) for b in self.banks]
+            self.banks = [pb.bank for pb in self.pbanks]
+            self.col_id = self.pbanks[0].col_id
+            self.C_total = self.pbanks[0].C_total
         if not host_io:
             self.dev_feats = [torch.empty((batch, D), dtype=feat_dtype, device=self.device) for _ in range(steps)]
             self.dev_labels = [torch.zeros((batch,), dtype=torch.int32, device=self.device) for _ in range(steps)]
@@ -390,12 +481,14 @@ class ShardedEvalStream:
             px, j = self.pxs[s % self.channels], s // self.channels
             self.dev_pack[s].copy_(self.host_pack[s], non_blocking=True)
             x = px.ingest(self.dev_feats[s], j % self._xring[s % self.channels])
-            px.scatter(x, bank, self.id_base, j % self._ring[s % self.channels], col_id=self.col_id)
+            self._x[s] = x
+            px.scatter(x, bank, self.id_base, j % self._ring[s % self.channels], col_id=self.col_id, C_total=self.C_total)
             return None
         x = ops.normalize_rows(self.dev_feats[s])
         if self.exchange == "p2p":
+            self._x[s] = x           # the owner's repair reads the row's features (kept alive for the captured graph)
             self.pxs[s % self.channels].scatter(x, bank, self.id_base, (s // self.channels) % self._ring[s % self.channels],
-                                                col_id=self.col_id)
+                                                col_id=self.col_id, C_total=self.C_total)
             return None
         if bank.shape[0] > 0:
             # results go straight into the send record (no pack copies)
@@ -412,8 +505,11 @@ class ShardedEvalStream:
 
     def _merge(self, s: int, work):
         if self.exchange == "p2p":
+            cert = None
+            if self.certify == "global":
+                cert = (self._x[s], self.pbanks[s % len(self.pbanks)].table, self.repairs)
             self.pxs[s % self.channels].merge((s // self.channels) % self._ring[s % self.channels], self.dev_labels[s], self.hits,
-                                              out=(self.val[s], self.idx[s]), targets_local=self.host_io)
+                                              out=(self.val[s], self.idx[s]), targets_local=self.host_io, certify=cert)
             if self.host_io:
                 self.host_hits[s].copy_(self.hits, non_blocking=True)
             return

@@ -218,9 +218,14 @@ def topk_merge_raw(part_val_ptr: int, part_idx_ptr: int, P: int, B: int, K: int,
 
 def score_topk_scatter(X: torch.Tensor, bank: torch.Tensor, val_block_ptrs, idx_block_ptrs, block_rows: int, *,
                        col_id: Optional[torch.Tensor] = None, id_base: int = 0, K: int = 20, scale: float = 1.0,
-                       impl: int = HGR_IMPL_AUTO) -> None:
+                       impl: int = HGR_IMPL_AUTO, bound_block_ptrs=None, C_total: int = 0) -> None:
     """``score_topk`` whose final lists of rows ``[g*block_rows, (g+1)*block_rows)`` are written to the dense
-    ``[block_rows, K]`` arrays at ``val_block_ptrs[g]`` / ``idx_block_ptrs[g]`` (device pointers, local or peer)."""
+    ``[block_rows, K]`` arrays at ``val_block_ptrs[g]`` / ``idx_block_ptrs[g]`` (device pointers, local or peer).
+
+    With ``bound_block_ptrs`` (``[block_rows]`` fp32 arrays) and ``C_total`` the bank is one shard of a row's global
+    stream of ``C_total`` classes: narrow lists sized for the GLOBAL certificate, no local repair, and per row an upper
+    bound of everything the shard dropped (``hgr_score_topk_scatter_bounded``; the owner runs
+    ``topk_merge_certified``)."""
     import ctypes
     lib = _cabi.load()
     X = _require(X, "X", torch.bfloat16)
@@ -236,8 +241,59 @@ def score_topk_scatter(X: torch.Tensor, bank: torch.Tensor, val_block_ptrs, idx_
     it = (ctypes.c_void_p * n)(*idx_block_ptrs)
     nbytes = lib.hgr_score_topk_workspace_bytes(B, C, D, K)
     ws = _workspace(nbytes, X.device)
+    if bound_block_ptrs is not None:
+        if len(bound_block_ptrs) != n:
+            raise ValueError("bound block table disagrees with the val/idx tables")
+        bt = (ctypes.c_void_p * n)(*bound_block_ptrs)
+        _cabi.check(lib.hgr_score_topk_scatter_bounded(_ptr(X), _ptr(bank), _ptr(col_id), id_base, B, C, D, float(scale),
+                                                       K, _ptr(ws), ws.numel(), block_rows, n, vt, it, bt,
+                                                       int(C_total), impl, _stream()))
+        return
     _cabi.check(lib.hgr_score_topk_scatter(_ptr(X), _ptr(bank), _ptr(col_id), id_base, B, C, D, float(scale), K,
                                            _ptr(ws), ws.numel(), block_rows, n, vt, it, impl, _stream()))
+
+
+def global_list_len(B: int, C: int, D: int, K: int, C_total: int) -> int:
+    """Entries per list ``score_topk_scatter`` keeps for a shard of ``C`` of ``C_total`` classes (host only)."""
+    r = _cabi.load().hgr_score_topk_global_list_len(B, C, D, K, C_total)
+    if r < 0:
+        _cabi.check(r)
+    return int(r)
+
+
+def shard_table(shards, device) -> torch.Tensor:
+    """Device copy of an ``hgr_shard_t`` array: ``shards`` = [(bank pointer, col_id pointer or 0, C, id_base), ...]
+    (32 bytes per entry: two pointers, int64 C, int32 id_base + padding)."""
+    rows = [[int(b), int(c or 0), int(n), int(base) & 0xFFFFFFFF] for (b, c, n, base) in shards]
+    return torch.tensor(rows, dtype=torch.int64).to(device)
+
+
+def topk_merge_certified(part_val_ptr: int, part_idx_ptr: int, part_bound_ptr: int, P: int, B: int, K: int,
+                         part_stride: int, bound_stride: int, x_rows: torch.Tensor, shards: torch.Tensor, device, *,
+                         scale: float = 1.0, targets: Optional[torch.Tensor] = None,
+                         hits: Optional[torch.Tensor] = None, repair_count: Optional[torch.Tensor] = None,
+                         out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Owner side of the global certificate (``hgr_topk_merge_certified``): merge the ``P`` shard lists of ``B`` rows,
+    certify every row against the shards' bounds, repair the rest exactly from ``shards`` (``shard_table``) with the
+    rows' normalised features ``x_rows [B, D]`` bf16."""
+    lib = _cabi.load()
+    x_rows = _require(x_rows, "x_rows", torch.bfloat16)
+    if x_rows.shape[0] != B:
+        raise ValueError("x_rows must hold the %d rows being merged" % B)
+    if shards.dtype != torch.int64 or tuple(shards.shape) != (P, 4) or not shards.is_cuda:
+        raise ValueError("shards must be the [P, 4] int64 device tensor shard_table() builds")
+    if targets is not None:
+        targets = _require(targets, "targets", torch.int32)
+    if hits is not None:
+        hits = _require(hits, "hits", torch.int64)
+    if repair_count is not None:
+        repair_count = _require(repair_count, "repair_count", torch.int32)
+    if out is None:
+        out = (torch.empty((B, K), dtype=torch.float32, device=device), torch.empty((B, K), dtype=torch.int32, device=device))
+    _cabi.check(lib.hgr_topk_merge_certified(part_val_ptr, part_idx_ptr, part_bound_ptr, P, B, K, part_stride, bound_stride,
+                                             _ptr(targets), _ptr(out[0]), _ptr(out[1]), _ptr(hits), _ptr(x_rows),
+                                             x_rows.shape[1], _ptr(shards), float(scale), _ptr(repair_count), _stream()))
+    return out
 
 
 def peer_alloc(nbytes: int) -> Tuple[int, bytes]:

@@ -172,6 +172,45 @@ int hgr_score_topk_scatter(const void* X, const void* bank, const int32_t* col_i
                            int64_t C, int64_t D, float scale, int K, void* workspace, size_t workspace_bytes,
                            int64_t block_rows, int n_blocks, float* const* val_blocks,
                            int32_t* const* idx_blocks, int impl, void* stream);
+/*
+ * GLOBAL CERTIFICATE of the class-sharded head.  A shard's share of a row's stream is short (N = 8: 2,731 of 21,841
+ * classes, cut into 4 lists per row), and short streams with exact K-entry lists are all list warm-up (measured:
+ * 39.4 us per call at the N = 8 shard against 26.7 us with 10-entry lists).  Narrow lists cannot be certified against
+ * the shard's OWN K-th value (a quarter of the shard's top-20 sits in every list), but they can against the GLOBAL
+ * K-th value, which only the owner of the row knows.  So:
+ *
+ * hgr_score_topk_scatter_bounded   hgr_score_topk_scatter with lists sized for the row's global stream of C_total
+ *                                  classes; no local certificate, no local repair.  Next to the final list of a row
+ *                                  the producer stores bound_blocks[g][row - g * block_rows] = scale * (the largest
+ *                                  last entry of its FULL narrow lists; -inf when no list dropped anything): every
+ *                                  candidate the shard did not report is <= that bound.
+ * hgr_topk_merge_certified         hgr_topk_merge of the P = n_shards lists of the owner's rows; a row is certified
+ *                                  when its merged K-th value beats every shard's bound STRICTLY.  Otherwise the
+ *                                  doubtful shards are re-scanned exactly on the CUDA cores with the row's features
+ *                                  X[row] against shards[p].bank (device pointers in DEVICE memory; a peer's bank is
+ *                                  read over NVLink), bank rows mapped to node ids by shards[p].col_id / id_base and
+ *                                  values multiplied by `scale` like the producers did.  With bank rows in random
+ *                                  order this is a < 1e-4-per-batch event by construction of the list length
+ *                                  (hgr_score_topk_global_list_len); *repair_count (optional, device) counts the rows.
+ * The result is exact either way -- same contract as hgr_score_topk.
+ */
+typedef struct hgr_shard {
+  const void* bank;       /* [C, D] bf16, 16-byte aligned */
+  const int32_t* col_id;  /* [C] node ids or NULL -> id_base + bank row */
+  int64_t C;
+  int32_t id_base;
+  int32_t reserved;
+} hgr_shard_t;
+int hgr_score_topk_global_list_len(int64_t B, int64_t C, int64_t D, int K, int64_t C_total);
+int hgr_score_topk_scatter_bounded(const void* X, const void* bank, const int32_t* col_id, int32_t id_base, int64_t B,
+                                   int64_t C, int64_t D, float scale, int K, void* workspace, size_t workspace_bytes,
+                                   int64_t block_rows, int n_blocks, float* const* val_blocks,
+                                   int32_t* const* idx_blocks, float* const* bound_blocks, int64_t C_total, int impl,
+                                   void* stream);
+int hgr_topk_merge_certified(const float* part_val, const int32_t* part_idx, const float* part_bound, int64_t P,
+                             int64_t B, int K, int64_t part_stride, int64_t bound_stride, const int32_t* targets,
+                             float* topk_val, int32_t* topk_idx, int64_t* hits, const void* X, int64_t D,
+                             const hgr_shard_t* shards, float scale, unsigned int* repair_count, void* stream);
  /* hgr_normalize_rows_bcast: feature ingest of the sharded head.  A rank copies only ITS block of image rows from the
   * host; this kernel normalises them (clip_tree.py:330) and stores row r at row (row0 + r) of every destination
   * dst[g] (HOST array of n_dst device pointers to bf16 [*, D] arrays, local or peer), so the A operand of

@@ -87,7 +87,9 @@ def test_exchange_layout_and_row_blocks():
         lay = exchange_layout(B, K, world, slots, D)
         rows = lay["block_rows"]
         assert rows * world >= B and (rows - 1) * world < B       # smallest block size that covers the batch
-        assert lay["part_bytes"] == rows * K * 4 and lay["slot_bytes"] == 2 * world * lay["part_bytes"]
+        assert lay["part_bytes"] == rows * K * 4
+        # value lists, id lists, then the [world, block_rows] fp32 bounds of the global certificate (16-byte padded)
+        assert lay["slot_bytes"] % 16 == 0 and lay["slot_bytes"] >= 2 * world * lay["part_bytes"] + world * rows * 4
         assert lay["header"] >= 64 + 4 * 16                      # two flag sets of up to 16 ranks
         assert lay["x_off"] % 256 == 0 and lay["x_off"] >= lay["header"] + slots * lay["slot_bytes"]
         assert lay["total"] == lay["x_off"] + (X_SLOTS * lay["x_bytes"] if D else 0)

@@ -75,9 +75,12 @@ def test_other_real_sizes_match_oracle(B, C, D):
     _check_against_oracle(B, C, D)
 
 
-def test_class_sharded_exchange_matches_oracle_at_cfg5():
+@pytest.mark.parametrize("certify", ["global", "local"])
+def test_class_sharded_exchange_matches_oracle_at_cfg5(certify):
     """8 logical ranks on one GPU, B = 4096, C = 21,841: every rank scores its class shard, scatters its local
-    top-20 to the row owners over (here: local) peer memory, owners merge -- compared with the fp32 ORACLE."""
+    top-20 to the row owners over (here: local) peer memory, owners merge -- compared with the fp32 ORACLE.
+    `global`: the production arrangement of ShardedEvalStream (narrow lists certified by the row owner against the
+    global K-th value); `local`: exact 20-entry lists per shard."""
     from hgrnet_b200 import ops
     from hgrnet_b200.dist import PeerExchange, exchange_layout, shard_bounds
     dev = torch.device(DEV)
@@ -93,11 +96,19 @@ def test_class_sharded_exchange_matches_oracle_at_cfg5():
         ranks = [PeerExchange(B, K, dev, slots=4, _bases=bufs, _rank=r, _world=G) for r in range(G)]
         bounds = shard_bounds(C, G)
         hits = ops.new_hits(dev)
+        shards = [wb[lo:hi].contiguous() for lo, hi in bounds]
+        cert = None
+        if certify == "global":
+            table = ops.shard_table([(s.data_ptr(), 0, s.shape[0], lo) for s, (lo, _) in zip(shards, bounds)], dev)
+            repairs = torch.zeros(1, dtype=torch.int32, device=dev)
+            cert = (xn, table, repairs)
+            assert ops.global_list_len(B, shards[0].shape[0], D, K, C) < K
         for r, px in enumerate(ranks):
-            lo, hi = bounds[r]
-            px.scatter(xn, wb[lo:hi].contiguous(), lo, 0)
-        outs = [px.merge(0, targets.to(dev), hits) for px in ranks]
+            px.scatter(xn, shards[r], bounds[r][0], 0, C_total=C if cert else 0)
+        outs = [px.merge(0, targets.to(dev), hits, certify=cert) for px in ranks]
         torch.cuda.synchronize()
+        if cert:
+            assert int(repairs.item()) == 0
         val = torch.cat([o[0] for o in outs if o is not None])
         idx = torch.cat([o[1] for o in outs if o is not None])
         ties = compare_topk(val, idx, logits, torch.arange(C), K)

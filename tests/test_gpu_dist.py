@@ -65,6 +65,25 @@ def _worker(rank, world, port, B, C, D, K, out):
                 assert torch.equal(ses.idx[s_], ri[ses.row_lo:ses.row_hi]), exchange
                 assert torch.equal(ses.val[s_], rv[ses.row_lo:ses.row_hi]), exchange
             dist.barrier()
+        # hostile bank (siblings adjacent and similar, queries near a leaf): a shard's narrow lists overflow, the row
+        # owner must notice (bound >= global K-th value) and re-scan that shard -- a PEER's bank, over NVLink
+        from tests.util import hostile_bank, hostile_queries
+        wh = hostile_bank(C, D, "clustered")
+        xh = hostile_queries(wh.to(dev), B, "clustered")
+        ses = ShardedEvalStream(wh[lo:hi].to(dev).contiguous(), lo, batch=B, K=K, steps=2)
+        for s_ in range(2):
+            ses.dev_feats[s_].copy_(xh.float())
+        ses.run()
+        torch.cuda.synchronize()
+        hv, hi_ = ops.score_topk(ops.normalize_rows(xh.float()), wh.to(dev), K=K, impl=ops.HGR_IMPL_SIMT)
+        rep = ses.repairs.clone()
+        dist.all_reduce(rep)
+        if ops.global_list_len(B, hi - lo, D, K, C) < K:
+            assert int(rep.item()) > 0, "the clustered bank should defeat the narrow lists of some rows"
+        mine_v, mine_i = ses.val[1], ses.idx[1]
+        assert torch.allclose(mine_v, hv[ses.row_lo:ses.row_hi], rtol=1e-3, atol=1e-5)
+        assert (mine_i != hi_[ses.row_lo:ses.row_hi]).any(1).float().mean().item() < 0.1   # near-ties may swap
+        dist.barrier()
         # host-fed evaluator: every rank copies only its row block from pinned memory, NVLink replicates the rest
         ses = ShardedEvalStream(w[lo:hi].to(dev).contiguous(), lo, batch=B, K=K, steps=8, host_io=True)
         for s_ in range(8):

@@ -138,3 +138,75 @@ def test_sharded_eval_stream_single_rank(host_io):
     assert ses.all_reduce_hits().tolist() == [2 * h for h in ref_hits.tolist()]
     if host_io:
         assert torch.equal(torch.stack(ses.host_hits).max(dim=0).values, ses.hits.cpu())
+
+
+def _run_certified(x, w, G, K=20, targets=None, reps=1):
+    """G logical ranks, global-certificate mode: narrow lists + bounds scattered to the owners, owners certify / repair
+    against the shard table.  Returns (val, idx, hits, repaired rows, list length of the first shard)."""
+    from hgrnet_b200 import ops
+    from hgrnet_b200.dist import PeerExchange, exchange_layout, shard_bounds
+    dev = x.device
+    B, D = x.shape
+    C = w.shape[0]
+    lay = exchange_layout(B, K, G, 4)
+    bufs = [ops.peer_alloc(lay["total"])[0] for _ in range(G)]
+    try:
+        ranks = [PeerExchange(B, K, dev, slots=4, _bases=bufs, _rank=r, _world=G) for r in range(G)]
+        bounds = shard_bounds(C, G)
+        shards = [w[lo:hi].contiguous() for lo, hi in bounds]
+        table = ops.shard_table([(s.data_ptr() if s.numel() else 0, 0, s.shape[0], lo) for s, (lo, _) in zip(shards, bounds)], dev)
+        hits = ops.new_hits(dev)
+        repairs = torch.zeros(1, dtype=torch.int32, device=dev)
+        for rep in range(reps):
+            slot = rep % 4
+            for r, px in enumerate(ranks):
+                px.scatter(x, shards[r], bounds[r][0], slot, C_total=C)
+            outs = [px.merge(slot, targets, hits if targets is not None else None, certify=(x, table, repairs)) for px in ranks]
+        torch.cuda.synchronize()
+        val = torch.cat([o[0] for o in outs if o is not None])
+        idx = torch.cat([o[1] for o in outs if o is not None])
+        kl = ops.global_list_len(B, shards[0].shape[0], D, K, C) if shards[0].shape[0] else K
+        return val, idx, hits, int(repairs.item()), kl
+    finally:
+        torch.cuda.synchronize()
+        for b in bufs:
+            ops.peer_free(b)
+
+
+@pytest.mark.parametrize("B,C,D,G", [(4096, 21841, 1024, 8), (4096, 21841, 1024, 4), (4096, 21841, 1024, 2),
+                                     (512, 21841, 1024, 8), (130, 1000, 256, 3), (5, 300, 128, 8)])
+def test_global_certificate_matches_single_gpu(B, C, D, G):
+    """Class shards keep NARROW lists sized for the row's global stream (10 entries at the N = 8 shard of cfg 5) and
+    report a bound of what they dropped; the owner certifies against the global K-th value.  On an i.i.d. bank nothing
+    needs a repair and the result is bit-identical to the single-GPU head (main.py:136-147)."""
+    from hgrnet_b200 import ops
+    dev = torch.device("cuda", 0)
+    K = 20
+    x = _emb(B, D, 11).to(dev)
+    w = _emb(C, D, 12).to(dev)
+    targets = torch.randint(0, C, (B,), generator=torch.Generator().manual_seed(3)).int().to(dev)
+    h_ref = ops.new_hits(dev)
+    rv, ri = ops.score_topk(x, w, targets=targets, K=K, hits=h_ref, impl=ops.HGR_IMPL_TCGEN05_EXACT)
+    val, idx, hits, repaired, kl = _run_certified(x, w, G, K, targets, reps=3)
+    if B == 4096:
+        assert kl < K, "the cfg-5 shards are expected to run narrow lists (got %d)" % kl
+        assert repaired == 0
+    assert torch.equal(idx, ri) and torch.equal(val, rv)
+    assert hits.tolist() == [3 * h for h in h_ref.tolist()]
+
+
+@pytest.mark.parametrize("kind", ["clustered", "ascending", "equal", "dups"])
+@pytest.mark.parametrize("B,C,D,G", [(512, 21841, 1024, 8), (130, 2000, 256, 4)])
+def test_global_certificate_repairs_hostile_banks(kind, B, C, D, G):
+    """Banks whose best classes sit in adjacent rows of ONE shard overflow that shard's narrow lists: its bound reaches
+    the global K-th value, the owner must notice and re-scan that shard exactly (here the 'peer' banks are local)."""
+    from hgrnet_b200 import ops
+    from tests.util import compare_topk, hostile_bank, hostile_queries
+    dev = torch.device("cuda", 0)
+    w = hostile_bank(C, D, kind).to(dev)
+    xn = hostile_queries(w, B, kind)
+    logits = (xn.float() @ w.float().T).cpu()
+    val, idx, _, repaired, kl = _run_certified(xn, w, G)
+    compare_topk(val, idx, logits, torch.arange(C), 20)
+    if kl < 20:
+        assert repaired > 0, "a hostile bank should defeat the narrow lists of at least one row"
