@@ -553,6 +553,19 @@ class ShardedEvalStream:
         else:
             self._issue()
 
+    def close(self) -> None:
+        """Release the peer-memory allocations (exchange buffers, peer-visible bank shards).  Call it on every rank,
+        after the last replay has finished; the stream must not be used afterwards."""
+        torch.cuda.synchronize(self.device)
+        self.graph = None
+        if self.world > 1:
+            dist.barrier(group=self.group)     # nobody unmaps a buffer a peer may still be writing
+        for px in getattr(self, "pxs", []):
+            px.close()
+        for pb in getattr(self, "pbanks", []):
+            pb.close()
+        self.pxs, self.pbanks = [], []
+
     def all_reduce_hits(self) -> torch.Tensor:
         """Hit@k counters of the whole batch stream.  With the peer exchange every rank counted its own rows, so
         the counters are summed over ranks (the single collective of an evaluation); the NCCL exchange already
