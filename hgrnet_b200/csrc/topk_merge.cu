@@ -489,6 +489,110 @@ topk_select_kernel(const __grid_constant__ MergeArgs a) {
               static_cast<unsigned long long>(s_hits[threadIdx.x]));
 }
 
+// ---- ranking merge (very few candidates per row) ------------------------------------------------------------------
+// Up to 32 * NPL <= 96 candidates per row -- the class-sharded head at B = 4096: 4-6 lists of 10-16 entries for each of
+// 4,096 rows, where the bisection of topk_select_kernel (~1,500 instructions per row, 66 % issue utilisation: it
+// competes with the persistent GEMM of the next batch for SMs) is the expensive part.  Here every candidate is packed
+// into one 64-bit word (order key << 32 | ~item: larger word = better candidate, ties by ascending item) and staged in
+// shared memory list by list; the lists are SORTED, so the output position of a candidate is its position in its own
+// list plus, for every other list, the number of entries that beat it -- a 5-step binary search each.
+// ~350 instructions per row at 40 candidates.  Same result, same order as the other merge kernels.  Requires every
+// list sorted by (value desc, item asc) -- true for the lists the scoring kernel writes.
+template <int NPL>
+__global__ void __launch_bounds__(kMergeWarps * 32, 7)
+topk_rank_kernel(const __grid_constant__ MergeArgs a) {
+  __shared__ int s_hits[HGR_NUM_HITS];
+  __shared__ unsigned long long s_list[kMergeWarps][32 * NPL];
+  __shared__ unsigned long long s_win[kMergeWarps][32];
+  __shared__ uint32_t s_dmask[kMergeWarps][kDoubtWords];
+  if (threadIdx.x < HGR_NUM_HITS) s_hits[threadIdx.x] = 0;
+  if (threadIdx.x < kMergeWarps * kDoubtWords) (&s_dmask[0][0])[threadIdx.x] = 0;
+  __syncthreads();
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int KL = a.KL, K = a.K;
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * kMergeWarps + warp;
+  const int64_t pstride = a.part_stride > 0 ? a.part_stride : a.B * KL;
+  if (row < a.B) {
+    int cnt = static_cast<int>(a.P);
+    if (a.use_sched) cnt = a.sched.parts(static_cast<int32_t>(row / a.sched.rows)) * a.wpq;
+    const int N = cnt * KL;
+
+    unsigned long long w[NPL];   // 0 = empty slot
+    int32_t item[NPL];
+    float val[NPL];
+    int lp[NPL], lk[NPL];        // list / position of my candidate
+#pragma unroll
+    for (int s = 0; s < NPL; ++s) {   // all loads first (an out-of-range slot re-reads entry 0)
+      const int e = lane + 32 * s;
+      lp[s] = e < N ? e / KL : 0;
+      lk[s] = e < N ? e - lp[s] * KL : 0;
+      const int64_t g = N > 0 ? lp[s] * pstride + row * KL + lk[s] : 0;
+      item[s] = (N > 0) ? __ldg(a.part_idx + g) : -1;
+      val[s] = (N > 0) ? __ldg(a.part_val + g) : 0.f;
+    }
+    int nvalid = 0;
+    float tailmax = -INFINITY;
+    bool tail[NPL];
+#pragma unroll
+    for (int s = 0; s < NPL; ++s) {
+      const bool ok = (lane + 32 * s < N) && item[s] >= 0;
+      w[s] = ok ? (static_cast<unsigned long long>(f32_order_key(val[s])) << 32) | static_cast<uint32_t>(~item[s]) : 0ull;
+      tail[s] = ok && lk[s] == KL - 1;
+      if (tail[s]) tailmax = fmaxf(tailmax, val[s]);
+      nvalid += ok;
+      s_list[warp][lane + 32 * s] = w[s];
+    }
+    __syncwarp();
+    nvalid = __reduce_add_sync(0xffffffffu, nvalid);
+    const int ksel = nvalid < K ? nvalid : K;
+
+#pragma unroll
+    for (int s = 0; s < NPL; ++s) {
+      int rank = lk[s];
+#pragma unroll 4
+      for (int q = 0; q < cnt; ++q) {
+        // entries of list q that come before mine: strictly larger words; an identical word (the same item reported
+        // twice) counts when it sits in an earlier list
+        const unsigned long long bar = w[s] - (q < lp[s] ? 1ull : 0ull);
+        const unsigned long long* lq = &s_list[warp][q * KL];
+        int lo = 0, hi = KL;
+        while (lo < hi) {   // <= 6 steps, warp-uniform trip count would need KL a power of two: plain loop
+          const int mid = (lo + hi) >> 1;
+          if (lq[mid] > bar) lo = mid + 1;
+          else hi = mid;
+        }
+        rank += q == lp[s] ? 0 : lo;
+      }
+      if (w[s] != 0ull && rank < 32) s_win[warp][rank] = w[s];
+    }
+    __syncwarp();
+    float my_v = -INFINITY;
+    int32_t my_i = -1;
+    bool doubt = false;
+    if (ksel > 0) {
+      if (lane < ksel) {
+        const unsigned long long x = s_win[warp][lane];
+        my_v = f32_from_order_key(static_cast<uint32_t>(x >> 32));
+        my_i = static_cast<int32_t>(~static_cast<uint32_t>(x));
+      }
+      const uint32_t T = static_cast<uint32_t>(s_win[warp][ksel - 1] >> 32);   // key of the K-th winner
+#pragma unroll
+      for (int s = 0; s < NPL; ++s) {
+        if (tail[s] && static_cast<uint32_t>(w[s] >> 32) >= T) {
+          doubt = true;
+          atomicOr(&s_dmask[warp][lp[s] >> 5], 1u << (lp[s] & 31));
+        }
+      }
+    }
+    finish_row(a, row, lane, my_v, my_i, doubt, s_dmask[warp], cnt, s_hits, tailmax);
+  }
+  __syncthreads();
+  if (a.hits && threadIdx.x < HGR_NUM_HITS && s_hits[threadIdx.x] != 0)
+    atomicAdd(reinterpret_cast<unsigned long long*>(a.hits) + threadIdx.x,
+              static_cast<unsigned long long>(s_hits[threadIdx.x]));
+}
+
 // ---- candidate-list merge (floor-sketch epilogue) ---------------------------------------------------------------
 // The lists of a row are short, UNSORTED and of different lengths (sk_cnt).  One warp per row: the lists are gathered
 // into shared memory (lane = list, one 8-byte entry per step), the K-th largest order key is found by bisection over
@@ -702,6 +806,16 @@ int launch_topk_merge(const MergeArgs& args, cudaStream_t stream) {
     return set_error(HGR_ERR_BAD_ARG, "topk merge: speculative lists need X / bank / the schedule for the exact repair");
   const int blocks = static_cast<int>((args.B + kMergeWarps - 1) / kMergeWarps);
   const int64_t cand = args.P * args.KL;  // candidates per row (upper bound)
+  // (only for the scoring kernel's own lists: bank rows, sorted (value desc, row asc) by construction -- lists handed
+  //  to hgr_topk_merge carry node ids, whose order among equal values is the caller's)
+#ifndef HGR_NO_RANK_KERNEL   // (kernel experiments: tools/build_variant.sh norank -DHGR_NO_RANK_KERNEL topk_merge.cu)
+  if (cand <= 96 && args.use_sched) {
+    if (cand <= 64) topk_rank_kernel<2><<<blocks, kMergeWarps * 32, 0, stream>>>(args);
+    else topk_rank_kernel<3><<<blocks, kMergeWarps * 32, 0, stream>>>(args);
+    HGR_CHECK_LAUNCH();
+    return HGR_OK;
+  }
+#endif
   if (cand <= 320) {
     if (cand <= 128) topk_select_kernel<4><<<blocks, kMergeWarps * 32, 0, stream>>>(args);
     else if (cand <= 192) topk_select_kernel<6><<<blocks, kMergeWarps * 32, 0, stream>>>(args);

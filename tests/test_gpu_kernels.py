@@ -253,7 +253,8 @@ def test_score_topk_empty_and_bad_args():
 
 
 # --------------------------------------------------------------------------- merge
-@pytest.mark.parametrize("P,B,K", [(1, 5, 20), (2, 64, 20), (8, 130, 20), (37, 33, 20), (128, 9, 7)])
+@pytest.mark.parametrize("P,B,K", [(1, 5, 20), (2, 64, 20), (4, 70, 20), (3, 40, 32), (5, 1000, 20), (8, 130, 20), (37, 33, 20),
+                                   (128, 9, 7)])
 def test_topk_merge_matches_sort(P, B, K):
     g = torch.Generator().manual_seed(P * 100 + B)
     vals = torch.randn(P, B, K, generator=g)
