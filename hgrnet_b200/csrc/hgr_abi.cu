@@ -319,6 +319,61 @@ int hgr_topk_merge_certified(const float* part_val, const int32_t* part_idx, con
   return launch_topk_merge(m, static_cast<cudaStream_t>(stream));
 }
 
+int64_t hgr_sample_replay(const uint32_t* words, int64_t n_words, int64_t n, int64_t k, int64_t setsize, int32_t* out_pos,
+                          int32_t* scratch) {
+  if (!words || !out_pos || !scratch || n < 0 || k < 0 || k > n || n >= (int64_t(1) << 31)) return -2;
+  auto bit_length = [](uint32_t v) { return v == 0 ? 0 : 32 - __builtin_clz(v); };
+  int64_t p = 0;
+  if (n <= setsize) {
+    for (int64_t i = 0; i < n; ++i) scratch[i] = static_cast<int32_t>(i);
+    for (int64_t i = 0; i < k; ++i) {
+      const uint32_t left = static_cast<uint32_t>(n - i);
+      const int sh = 32 - bit_length(left);
+      uint32_t r;
+      do {
+        if (p >= n_words) return -1;
+        r = words[p++] >> sh;
+      } while (r >= left);
+      out_pos[i] = scratch[r];
+      scratch[r] = scratch[left - 1];
+    }
+    return p;
+  }
+  for (int64_t i = 0; i < n; ++i) scratch[i] = 0;
+  const int sh = 32 - bit_length(static_cast<uint32_t>(n));
+  for (int64_t i = 0; i < k; ++i) {
+    uint32_t r;
+    do {
+      do {
+        if (p >= n_words) return -1;
+        r = words[p++] >> sh;
+      } while (r >= static_cast<uint32_t>(n));
+    } while (scratch[r]);
+    scratch[r] = 1;
+    out_pos[i] = static_cast<int32_t>(r);
+  }
+  return p;
+}
+
+int64_t hgr_sample_replay_many(const uint32_t* words, int64_t n_words, int64_t count, const int64_t* n, const int64_t* k,
+                               int32_t* out_pos, int32_t* scratch) {
+  if (!n || !k || count < 0) return -2;
+  int64_t used = 0, off = 0;
+  for (int64_t c = 0; c < count; ++c) {
+    int64_t setsize = 21;                       // CPython: 21, + 4 ** ceil(log(3 k, 4)) when k > 5
+    if (k[c] > 5) {
+      int64_t p4 = 1;
+      while (p4 < 3 * k[c]) p4 *= 4;
+      setsize += p4;
+    }
+    const int64_t r = hgr_sample_replay(words + used, n_words - used, n[c], k[c], setsize, out_pos + off, scratch);
+    if (r < 0) return r;
+    used += r;
+    off += k[c];
+  }
+  return used;
+}
+
 int hgr_logits_dense(const void* X, const void* bank, int64_t B, int64_t C, int64_t D, float scale, float* out,
                      int64_t ldo, int impl, void* stream) {
   HGR_CHECK_ARG(B >= 0 && C >= 0, "hgr_logits_dense: negative size");

@@ -27,7 +27,7 @@ import torch.nn as nn
 from . import ops
 from .hierarchy import Hierarchy
 from .levels import layer_weight_init, level_weights
-from .sampling import (contra_brothers, contra_random, contra_topk, hierarchical_schedule, om_schedule,
+from .sampling import (contra_brothers, contra_random, contra_topk, contra_topk_many, hierarchical_schedule, om_schedule,
                        sample_stream)
 
 TEMPLATE_SIMPLE = "a photo of a {}."  # data/templates.py:98-100 (TEMPLATES_SIMPLE[0], hard-wired at clip_tree.py:52)
@@ -256,32 +256,44 @@ class tree_model(nn.Module):
             raise NotImplementedError("training_method %r (the reference implements OM and hierarchical)" % training_method)
         # every `random.sample` of the step runs on one SampleStream: same draws and same generator state afterwards
         # as the reference's per-iteration calls (clip_tree.py:134), at a fraction of the host time
+        if training_method == "OM":
+            weighting = self.opts.weighting                                          # clip_tree.py:265-273
+            m_in = "equal" if weighting == "out" else self.opts.weights
+            m_out = "equal" if weighting == "in" else self.opts.weights
+            sched = om_schedule(self.c2p, target, self.opts.out_ratio, self.opts.in_ratio)
+            requests = [(p_out, depth, parents_in) for (_, _, p_out, depth, parents_in, _, _) in sched]
+            recipes = [((m_in, n_in, m_loop), (m_out, n_out, k_loop)) for (k_loop, m_loop, _, _, _, n_out, n_in) in sched]
+        else:
+            sched = hierarchical_schedule(self.c2p, target)
+            requests = [(t_in, depth, parents) for (_, t_in, depth, parents, _) in sched]
+            recipes = [((self.opts.weights, n_lvl, j),) for (j, _, _, _, n_lvl) in sched]      # clip_tree.py:304-305
         with sample_stream(self._rng) as rng:
-            if training_method == "OM":
-                for (k_loop, m_loop, p_out, depth, parents_in, n_out, n_in) in om_schedule(
-                        self.c2p, target, self.opts.out_ratio, self.opts.in_ratio):
-                    ids, pos = self._contra_ids(sample_strategy, p_out, depth, parents_in, rng)
-                    weighting = self.opts.weighting                                  # clip_tree.py:265-273
-                    m_in = "equal" if weighting == "out" else self.opts.weights
-                    m_out = "equal" if weighting == "in" else self.opts.weights
-                    its.append((ids, pos, ((m_in, n_in, m_loop), (m_out, n_out, k_loop))))
+            if sample_strategy == "topk":
+                # all T draws of the step in one call of the library's host helper (sampling.contra_topk_many)
+                picked = contra_topk_many(self.d2n, requests, self.opts.k, self.opts.num_compare, rng,
+                                          cache=self._contra_cache)
             else:
-                for (j, t_in, depth, parents, n_lvl) in hierarchical_schedule(self.c2p, target):
-                    ids, pos = self._contra_ids(sample_strategy, t_in, depth, parents, rng)
-                    its.append((ids, pos, ((self.opts.weights, n_lvl, j),)))         # clip_tree.py:304-305
-        return its
+                picked = [self._contra_ids(sample_strategy, t, depth, parents, rng) for (t, depth, parents) in requests]
+        return [(ids, pos, rec) for (ids, pos), rec in zip(picked, recipes)]
 
     @staticmethod
-    def _iteration_weight(recipe, lw, memo=None):
-        w = None
-        for (method, n, pos) in recipe:
-            vec = memo.get((method, n)) if memo is not None else None
-            if vec is None:
-                vec = level_weights(method, n, lw)
-                if memo is not None:
-                    memo[(method, n)] = vec
-            f = vec[pos]
-            w = f if w is None else w * f
+    def _iteration_weights(its, lw):
+        """w_t = product of the level weights the recipe of iteration t names (clip_tree.py:265-273, :304-305), for all
+        T iterations with a handful of torch ops: every distinct (method, n) vector is computed once, all of them are
+        concatenated, and each factor is ONE gather -- differentiable w.r.t. ``lw`` (the adaptive ``layer_weight``)."""
+        offs, vecs, off = {}, [], 0
+        for _, _, rec in its:
+            for (method, n, _) in rec:
+                if (method, n) not in offs:
+                    v = level_weights(method, n, lw).float()
+                    offs[(method, n)] = off
+                    off += v.shape[0]
+                    vecs.append(v)
+        allv = torch.cat(vecs)
+        idx = np.asarray([[offs[(m, n)] + pos for (m, n, pos) in rec] for _, _, rec in its], dtype=np.int64)   # [T, factors]
+        w = allv[torch.from_numpy(idx[:, 0].copy())]
+        for f in range(1, idx.shape[1]):
+            w = w * allv[torch.from_numpy(idx[:, f].copy())]
         return w
 
     def train_batch(self, inputs, targets, training_method, sample_strategy):
@@ -297,13 +309,12 @@ class tree_model(nn.Module):
         T = len(its)
         # union of the sampled classes and every set as columns of it (numpy: ~4,400 ids per step at cfg 3)
         lens = np.fromiter((len(ids) for ids, _, _ in its), dtype=np.int64, count=T)
-        cat = np.fromiter((i for ids, _, _ in its for i in ids), dtype=np.int64, count=int(lens.sum()))
+        cat = np.concatenate([np.asarray(ids, dtype=np.int64) for ids, _, _ in its])
         union, inv = np.unique(cat, return_inverse=True)
         set_ptr = np.zeros(T + 1, dtype=np.int32)
         np.cumsum(lens, out=set_ptr[1:])
         lw_host = self._layer_weight_host()
-        memo = {}
-        weight_host = torch.stack([self._iteration_weight(r, lw_host, memo) for _, _, r in its]).float()
+        weight_host = self._iteration_weights(its, lw_host).detach()
         # ONE host->device copy for everything the step's kernels read: offsets, columns, label positions, weights
         # (as raw fp32 bits) and the union ids
         n_col = int(cat.shape[0])
@@ -340,8 +351,7 @@ class tree_model(nn.Module):
         lw_param = getattr(self, "layer_weight", None)
         if lw_param is not None and lw_param.requires_grad and self.opts.weights == "adaptive":
             lw_leaf = lw_host.clone().requires_grad_(True)
-            memo = {}
-            w_again = torch.stack([self._iteration_weight(r, lw_leaf, memo) for _, _, r in its])
+            w_again = self._iteration_weights(its, lw_leaf)
             ((loss_host / weight_host).detach() * w_again).sum().backward()            # d loss_t / d w_t = CE_t
             g = lw_leaf.grad.to(lw_param.device, lw_param.dtype)
             lw_param.grad = g if lw_param.grad is None else lw_param.grad + g

@@ -45,6 +45,9 @@ class SampleStream:
         self.state = None
         self.words = None
         self.pos = 0          # words consumed so far
+        self._words_ptr = 0
+        self._scratch = None
+        self._scratch_ptr = 0
 
     def __enter__(self):
         import numpy as np
@@ -58,11 +61,12 @@ class SampleStream:
         import numpy as np
         have = self.words.shape[0] - self.pos
         if have < m:
-            extra = max(m - have, 4096)
+            extra = max(m - have, 8192)
             new = np.frombuffer(self.rng.getrandbits(32 * extra).to_bytes(4 * extra, "little"), dtype="<u4")
             self.words = np.concatenate([self.words[self.pos:], new])
             self._base = getattr(self, "_base", 0) + self.pos
             self.pos = 0
+        self._words_ptr = self.words.__array_interface__["data"][0]
 
     def consumed(self) -> int:
         return getattr(self, "_base", 0) + self.pos
@@ -75,12 +79,91 @@ class SampleStream:
             self.rng.getrandbits(32 * used)
         return False
 
+    # -- the selected POSITIONS of random.sample(range(n), k), by the library's host helper (hgr_sample_replay: the same
+    #    two algorithms as below in C, ~2 us per call instead of ~40)
+    def positions(self, n: int, k: int):
+        import numpy as np
+        if not 0 <= k <= n:
+            raise ValueError("Sample larger than population or is negative")
+        lib = _host_lib()
+        setsize = _sample_setsize(k)
+        out = np.empty(k, dtype=np.int32)
+        if self._scratch is None or self._scratch.shape[0] < n:
+            self._scratch = np.empty(max(n, 4096), dtype=np.int32)
+            self._scratch_ptr = self._scratch.__array_interface__["data"][0]
+        m = 2 * k + 64 if n <= setsize else int(k * (1 << n.bit_length()) / max(n, 1) * 1.25) + 64
+        while True:
+            self.ensure(m)
+            avail = self.words.shape[0] - self.pos
+            # (`ndarray.ctypes` costs ~10 us per access; the array interface gives the same address for ~1 us)
+            used = lib.hgr_sample_replay(self._words_ptr + 4 * self.pos, avail, n, k, setsize,
+                                         out.__array_interface__["data"][0], self._scratch_ptr)
+            if used >= 0:
+                self.pos += int(used)
+                return out
+            if used != -1:
+                raise ValueError("hgr_sample_replay rejected n = %d, k = %d" % (n, k))
+            m = 2 * max(m, avail)
+
+    def sample_arrays(self, populations, ks):
+        """A run of `random.sample(populations[c], ks[c])` calls (numpy populations) in ONE library call."""
+        import numpy as np
+        lib = _host_lib()
+        if lib is None:
+            return [np.asarray(self._sample_py(p.tolist(), int(k)), dtype=p.dtype) for p, k in zip(populations, ks)]
+        cnt = len(populations)
+        if cnt == 0:
+            return []
+        ns = np.fromiter((p.shape[0] for p in populations), dtype=np.int64, count=cnt)
+        kk = np.asarray(ks, dtype=np.int64)
+        if (kk > ns).any() or (kk < 0).any():
+            raise ValueError("Sample larger than population or is negative")
+        total = int(kk.sum())
+        out = np.empty(max(total, 1), dtype=np.int32)
+        nmax = int(ns.max())
+        if self._scratch is None or self._scratch.shape[0] < nmax:
+            self._scratch = np.empty(max(nmax, 4096), dtype=np.int32)
+            self._scratch_ptr = self._scratch.__array_interface__["data"][0]
+        m = int(1.6 * total) + 32 * cnt        # ~1.5 words per draw at ImageNet-21K level sizes; doubled when short
+        while True:
+            self.ensure(m)
+            avail = self.words.shape[0] - self.pos
+            used = lib.hgr_sample_replay_many(self._words_ptr + 4 * self.pos, avail, cnt, ns.__array_interface__["data"][0],
+                                              kk.__array_interface__["data"][0], out.__array_interface__["data"][0],
+                                              self._scratch_ptr)
+            if used >= 0:
+                self.pos += int(used)
+                break
+            if used != -1:
+                raise ValueError("hgr_sample_replay_many rejected its arguments")
+            m = 2 * max(m, avail)
+        res, off = [], 0
+        for p, k in zip(populations, kk.tolist()):
+            res.append(p[out[off:off + k]])
+            off += k
+        return res
+
+    def sample_array(self, population, k: int):
+        """`random.sample(population, k)` for a numpy `population`, as a numpy array (same elements, same order)."""
+        return population[self.positions(population.shape[0], k)]
+
     # -- random.sample(population, k) on the stream
     def sample(self, population, k: int):
         import numpy as np
         n = len(population)
         if not 0 <= k <= n:
             raise ValueError("Sample larger than population or is negative")
+        if _host_lib() is not None:
+            pos = self.positions(n, k).tolist()
+            return [population[j] for j in pos]
+        return self._sample_py(population, k)
+
+    # pure-Python restatement (no library): what `_fast_sample_ok` pins the C helper and itself against
+    def _sample_py(self, population, k: int):
+        import numpy as np
+        n = len(population)
+        if k == 0:
+            return []          # random.sample(population, 0) draws nothing
         if n <= _sample_setsize(k):
             # pool algorithm: j = randbelow(n - i); result[i] = pool[j]; pool[j] = pool[n - i - 1]
             m = 2 * k + 64
@@ -127,19 +210,40 @@ class SampleStream:
 
 
 _FAST_SAMPLE = None
+_HOST_LIB = False        # False: not looked for yet; None: unavailable
+
+
+def _host_lib():
+    """libhgr_b200.so for its host helper `hgr_sample_replay` (None when it is not built -- the pure-Python restatement
+    of the same algorithms runs instead; this is host-side integer logic, not a fallback of any device computation)."""
+    global _HOST_LIB
+    if _HOST_LIB is False:
+        try:
+            from . import _cabi
+            _HOST_LIB = _cabi.load()
+        except Exception:
+            _HOST_LIB = None
+    return _HOST_LIB
 
 
 def _fast_sample_ok() -> bool:
-    global _FAST_SAMPLE
+    """Both replays (C helper, pure Python) against the running interpreter's `random.sample`, once per process."""
+    global _FAST_SAMPLE, _HOST_LIB
     if _FAST_SAMPLE is None:
-        try:
-            ok = True
+        shapes = ((300, 256), (1045, 256), (1046, 256), (5500, 256), (40, 7), (4097, 64), (21841, 256), (7, 7), (1, 1), (3, 0))
+
+        def agrees(use_lib) -> bool:
             a, b = _random.Random(11), _random.Random(11)
+            ok = True
             with SampleStream(b) as st:
-                for (n, k) in ((300, 256), (1045, 256), (1046, 256), (5500, 256), (40, 7), (4097, 64), (21841, 256)):
+                for (n, k) in shapes:
                     pop = list(range(1000, 1000 + n))
-                    ok = ok and a.sample(pop, k) == st.sample(pop, k)
-            _FAST_SAMPLE = ok and a.getstate() == b.getstate()
+                    ok = ok and a.sample(pop, k) == (st.sample(pop, k) if use_lib else st._sample_py(pop, k))
+            return ok and a.getstate() == b.getstate()
+        try:
+            if _host_lib() is not None and not agrees(True):
+                _HOST_LIB = None          # never trust a helper that disagrees with the interpreter
+            _FAST_SAMPLE = agrees(False) if _host_lib() is None else True
         except Exception:
             _FAST_SAMPLE = False
     return _FAST_SAMPLE
@@ -176,6 +280,21 @@ def contra_topk(d2n, target: int, depth: int, parents: Sequence[int], k: int, nu
     list handed to ``random.sample`` -- and therefore the draw -- is exactly what rebuilding it every call (as the
     reference does, :125-131) would give: the same objects built by the same operations.
     """
+    base = contra_topk_candidates(d2n, depth, parents, k, cache)
+    if len(base) > num_compare:
+        compare_idx = rng.sample(base, num_compare)   # a new list; the cached one is never modified (rng may be a SampleStream)
+    else:
+        compare_idx = list(base)
+    if target not in compare_idx:
+        compare_idx.append(target)
+    return compare_idx, compare_idx.index(target)
+
+
+def contra_topk_candidates(d2n, depth: int, parents: Sequence[int], k: int, cache: Optional[dict] = None,
+                           as_array: bool = False):
+    """The list `random.sample` draws from in `contra_topk` (clip_tree.py:118-131): nodes of the depth window minus the
+    anchor chain, in the iteration order of the reference's set difference.  ``as_array``: the same ids as a (cached)
+    int64 numpy array, for `SampleStream.sample_arrays`."""
     low = min(d2n.keys())
     if depth - k > low:
         low = depth - k
@@ -200,13 +319,43 @@ def contra_topk(d2n, target: int, depth: int, parents: Sequence[int], k: int, nu
                 cache.pop(order.pop(0), None)
             order.append(lkey)
             cache[lkey] = base
-    if len(base) > num_compare:
-        compare_idx = rng.sample(base, num_compare)   # a new list; the cached one is never modified (rng may be a SampleStream)
-    else:
-        compare_idx = list(base)
-    if target not in compare_idx:
-        compare_idx.append(target)
-    return compare_idx, compare_idx.index(target)
+    if not as_array:
+        return base
+    import numpy as np
+    akey = ("array",) + lkey[1:]
+    arr = cache.get(akey) if cache is not None else None
+    if arr is None:
+        arr = np.asarray(base, dtype=np.int64)
+        if cache is not None:
+            order = cache.setdefault("_list_keys", [])
+            order.append(akey)          # evicted with the lists, oldest first
+            cache[akey] = arr
+    return arr
+
+
+def contra_topk_many(d2n, requests, k: int, num_compare: int, rng, cache: Optional[dict] = None):
+    """`contra_topk` for a run of (target, depth, parents) requests -- the T iterations of one OM step -- with all the
+    `random.sample` calls of the run replayed in ONE library call (`SampleStream.sample_arrays`): same draws, same
+    order, same generator state.  Returns [(compare_idx int64 numpy array, label position)]."""
+    import numpy as np
+    bases = [contra_topk_candidates(d2n, depth, parents, k, cache, as_array=True) for (_, depth, parents) in requests]
+    need = [i for i, b in enumerate(bases) if b.shape[0] > num_compare]
+    if hasattr(rng, "sample_arrays"):
+        drawn = rng.sample_arrays([bases[i] for i in need], [num_compare] * len(need)) if need else []
+    else:       # plain `random` (the restatement did not match this interpreter): call by call
+        drawn = [np.asarray(rng.sample(bases[i].tolist(), num_compare), dtype=np.int64) for i in need]
+    for i, d in zip(need, drawn):
+        bases[i] = d
+    out = []
+    for (target, _, _), ids in zip(requests, bases):
+        hit = np.flatnonzero(ids == target)
+        if hit.shape[0] == 0:
+            ids = np.append(ids, target)
+            pos = ids.shape[0] - 1
+        else:
+            pos = int(hit[0])
+        out.append((ids, pos))
+    return out
 
 
 def contra_random(train_ids: Sequence[int], target: int, num_compare: int, rng=_random) -> Tuple[List[int], int]:

@@ -221,6 +221,24 @@ int hgr_peer_signal(uint32_t* const* flags, int n, uint32_t* seq, void* stream);
 int hgr_peer_wait(const uint32_t* flags, int n, uint32_t* seq, void* stream);
 
 /*
+ * HOST helper of row a7 (no device work): draw-identical replay of the index selection of CPython's
+ * `random.sample(population, k)` -- the call the reference draws its negatives with (model/clip_tree.py:134; 17 calls
+ * per OM step at cfg 3) -- on a window of Mersenne-Twister outputs.  words[i] is the i-th 32-bit output the generator
+ * would produce next (a k-bit getrandbits, k <= 32, is `word >> (32 - k)`); n = len(population); setsize is CPython's
+ * threshold between its two algorithms (21, + 4 ** ceil(log4(3 k)) when k > 5): n <= setsize runs the pool algorithm
+ * (j = randbelow(n - i); result[i] = pool[j]; pool[j] = pool[n - i - 1]), else the set algorithm (j = randbelow(n),
+ * redrawn while already selected).  Writes the k selected POSITIONS to out_pos; scratch holds n int32.
+ * Returns the number of words consumed (>= 0), -1 when the window is too short (call again with more words), -2 on
+ * bad arguments.  hgrnet_b200/sampling.py (SampleStream) keeps the generator state identical to the reference's.
+ */
+int64_t hgr_sample_replay(const uint32_t* words, int64_t n_words, int64_t n, int64_t k, int64_t setsize,
+                          int32_t* out_pos, int32_t* scratch);
+/* `count` consecutive calls random.sample(range(n[c]), k[c]) in one go (an OM step's 17 draws): positions of call c at
+ * out_pos[k[0] + ... + k[c-1] ...]; scratch holds max(n) int32; setsize is computed here.  Same return values. */
+int64_t hgr_sample_replay_many(const uint32_t* words, int64_t n_words, int64_t count, const int64_t* n, const int64_t* k,
+                               int32_t* out_pos, int32_t* scratch);
+
+/*
  * Dense logits, out[b, c] = scale * <X[b], bank[c]>, fp32, leading dimension ldo >= C.
  * Same TMA/tcgen05 main loop as hgr_score_topk with a plain store epilogue.  Keeps
  * tree_model.forward()'s contract (model/clip_tree.py:328-333: returns [B, N] logits) for

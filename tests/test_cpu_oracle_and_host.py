@@ -435,3 +435,48 @@ def test_sample_stream_is_draw_identical_to_random_sample():
     with pytest.raises(ValueError):
         with sampling.sample_stream(random.Random(1)) as st:
             st.sample([1, 2, 3], 4)
+
+
+def test_sample_replay_helper_and_batched_draws_match_random_sample():
+    """The library's host helper `hgr_sample_replay(_many)` (include/hgr_b200.h) and the pure-Python restatement
+    (`SampleStream._sample_py`) both reproduce `random.sample` (clip_tree.py:134) draw for draw; a whole OM step's run of
+    draws through `sampling.contra_topk_many` equals the reference-order sequence of `contra_topk` calls, with the
+    generator left in the same state."""
+    import numpy as np
+    from hgrnet_b200 import sampling
+    from hgrnet_b200.hierarchy import synthetic_hierarchy
+    assert sampling._fast_sample_ok() and sampling._host_lib() is not None, "libhgr_b200.so host helper not loaded"
+    for seed in range(40):
+        rnd = random.Random(1000 + seed)
+        a, b, c = (random.Random(seed * 3 + 2) for _ in range(3))
+        calls = []
+        for _ in range(rnd.randint(1, 20)):
+            n = rnd.choice([1, 2, 17, 40, 257, 300, 1000, 1045, 1046, 2000, 5500, 21841])
+            k = min(rnd.choice([0, 1, 5, 6, 16, 64, 255, 256]), n)
+            calls.append((np.asarray([rnd.randrange(10 ** 6) for _ in range(n)], dtype=np.int64), k))
+        want = [a.sample(p_.tolist(), k) for p_, k in calls]
+        with sampling.sample_stream(b) as st:
+            got = st.sample_arrays([p_ for p_, _ in calls], [k for _, k in calls])
+        with sampling.sample_stream(c) as st:
+            got_py = [st._sample_py(p_.tolist(), k) for p_, k in calls]
+        assert [g.tolist() for g in got] == want and got_py == want
+        assert a.getstate() == b.getstate() == c.getstate()
+    # a step's worth of contra_topk calls, batched vs one by one
+    h = synthetic_hierarchy((6, 40, 300, 1500, 2600, 900), seed=4)
+    for target in (len(h) - 1, len(h) - 700, 50, 3):
+        reqs = []
+        for (_, _, p_out, depth, parents_in, _, _) in sampling.om_schedule(h.c2p, target, 0.5, 0.75):
+            reqs.append((p_out, depth, parents_in))
+        random.seed(target)
+        one_by_one = [sampling.contra_topk(h.d2n, t, d, par, 2, 64, cache={}) for (t, d, par) in reqs]
+        s1 = random.getstate()
+        random.seed(target)
+        cache = {}
+        with sampling.sample_stream(random) as st:
+            many = sampling.contra_topk_many(h.d2n, reqs, 2, 64, st, cache=cache)
+        assert random.getstate() == s1
+        assert [(ids.tolist(), pos) for ids, pos in many] == [(ids, pos) for ids, pos in one_by_one]
+        random.seed(target)
+        with sampling.sample_stream(random) as st:        # warm cache: same draws
+            again = sampling.contra_topk_many(h.d2n, reqs, 2, 64, st, cache=cache)
+        assert [(i.tolist(), p_) for i, p_ in again] == [(i.tolist(), p_) for i, p_ in many]
