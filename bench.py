@@ -732,10 +732,11 @@ def run_ours(args):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel, keyed by (B, C_local, D); from the
-# `ncu --set full` captures summarised in profiles/r02_ncu_summary.md (a profiler cannot run inside the timed region).
+# `ncu --set full` captures summarised in profiles/r02_ncu_summary.md and, for the shard shapes in the list lengths of
+# the global certificate, profiles/r02b_ncu_certified.md (a profiler cannot run inside the timed region).
 # Shards of one bank differ by a row or two: _traffic() matches C within 2 rows.
 NCU_DRAM_BYTES = {(512, 21841, 1024): 45837056 + 22272, (4096, 21841, 1024): 53206784 + 1389312,
-                  (4096, 10921, 1024): 30801920, (4096, 5461, 1024): 19619840, (4096, 2731, 1024): 14028800,
+                  (4096, 10921, 1024): 30800640 + 1536, (4096, 5461, 1024): 19621376 + 5888, (4096, 2731, 1024): 14041344,
                   (1024, 10450, 512): 11798016}
 
 
