@@ -231,7 +231,9 @@ def run_ours(args):
     banks = [shard.clone() for _ in range(n_bank)]
     n_feat = 8
     feats_host = [synthetic_embeddings(B, D, 100 + i, normalize=False).pin_memory() for i in range(n_feat)]
-    feats_dev = [f.to(dev) for f in feats_host]
+    # resident inputs are kept as bf16: the synthetic embeddings are bf16-valued, so this is the
+    # same data in half the bytes -- what the normalise kernel (clip_tree.py:330) then has to read
+    feats_dev = [f.to(dev).to(torch.bfloat16) for f in feats_host]
     g = torch.Generator().manual_seed(7)
     labels_host = [torch.full((B,), int(torch.randint(0, C, (1,), generator=g)), dtype=torch.long).pin_memory()
                    for _ in range(n_feat)]
@@ -340,7 +342,8 @@ def run_ours(args):
 
     # ---- device-resident throughput: the public streaming evaluator without host I/O
     if world == 1:
-        es_res = model.make_eval_stream(batch=B, slots=cycle, streams=n_streams, banks=banks, host_io=False)
+        es_res = model.make_eval_stream(batch=B, slots=cycle, streams=n_streams, banks=banks, host_io=False,
+                                        feat_dtype=torch.bfloat16)
         for s_ in range(cycle):
             es_res.dev_feats[s_].copy_(feats_dev[s_ % n_feat])
             es_res.dev_labels[s_].copy_(labels_dev[s_ % n_feat])
@@ -352,12 +355,13 @@ def run_ours(args):
         from hgrnet_b200.dist import PeerMemoryUnavailable
         try:
             ses = ShardedEvalStream(banks[0], lo, batch=B, K=K, steps=G_STEPS, banks=banks, exchange=args.exchange,
-                                    col_id=shard_ids, channels=CHANNELS)
+                                    col_id=shard_ids, channels=CHANNELS, feat_dtype=torch.bfloat16)
         except PeerMemoryUnavailable as e:      # raised on every rank alike: fall back together
             if rank == 0:
                 print("bench: %s -- falling back to the NCCL exchange" % (e,), file=sys.stderr)
             args.exchange = "nccl"
-            ses = ShardedEvalStream(banks[0], lo, batch=B, K=K, steps=G_STEPS, banks=banks, exchange="nccl", col_id=shard_ids)
+            ses = ShardedEvalStream(banks[0], lo, batch=B, K=K, steps=G_STEPS, banks=banks, exchange="nccl", col_id=shard_ids,
+                                    feat_dtype=torch.bfloat16)
         for s_ in range(G_STEPS):
             ses.dev_feats[s_].copy_(feats_dev[s_ % n_feat])
             ses.dev_labels[s_].copy_(labels_dev[s_ % n_feat])
@@ -470,9 +474,10 @@ def run_ours(args):
         fb = [full_bank] + [full_bank.clone() for _ in range(nb - 1)]
         from hgrnet_b200.stream import EvalStream
         slots = nb * n_feat // math.gcd(nb, n_feat)
-        es1 = EvalStream(full_bank, col_id=ids, batch=Bx, K=K, slots=slots, streams=n_streams, banks=fb, host_io=False)
+        es1 = EvalStream(full_bank, col_id=ids, batch=Bx, K=K, slots=slots, streams=n_streams, banks=fb, host_io=False,
+                         feat_dtype=torch.bfloat16)       # same resident dtype as the sharded run it is compared with
         gx = torch.Generator().manual_seed(5)
-        fx = [torch.randn(Bx, D, generator=gx).to(dev) for _ in range(n_feat)]
+        fx = [torch.randn(Bx, D, generator=gx).to(dev).to(torch.bfloat16) for _ in range(n_feat)]
         for s_ in range(slots):
             es1.dev_feats[s_].copy_(fx[s_ % n_feat])
             es1.dev_labels[s_].fill_(int(ids[s_ % ids.numel()]))
@@ -685,6 +690,7 @@ def run_ours(args):
                                      if args.exchange == "p2p" else
                                      "NCCL all-gather of batch i overlaps the GEMM of batch i+1")),
                      "exchange": None if world == 1 else args.exchange,
+                     "resident_features": "bfloat16 [B, D], unnormalised (the synthetic embeddings are bf16-valued)",
                      "lists": ("%d-entry lists per (row, worker), sized for the row's GLOBAL stream and certified by the row "
                                "owner against the global K-th value (hgr_score_topk_scatter_bounded / "
                                "hgr_topk_merge_certified); rows repaired on rank 0 in this run: %d"
