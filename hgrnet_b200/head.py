@@ -342,10 +342,10 @@ class tree_model(nn.Module):
         if ls.requires_grad:
             g = d_log_scale.to(ls.dtype).reshape(ls.shape)
             ls.grad = g if ls.grad is None else ls.grad + g
-        if text_raw.requires_grad:
-            text_raw.backward(d_text_raw.to(text_raw.dtype))
-        if img_feats.requires_grad:
-            img_feats.backward(d_img_raw.to(img_feats.dtype))                         # :280
+        # one pass of the autograd engine for both encoders (clip_tree.py:276 per iteration, :280)
+        roots = [(t, g.to(t.dtype)) for t, g in ((text_raw, d_text_raw), (img_feats, d_img_raw)) if t.requires_grad]
+        if roots:
+            torch.autograd.backward([t for t, _ in roots], [g for _, g in roots])
 
         loss_host = loss_t.cpu()                                                        # the step's only result read-back
         lw_param = getattr(self, "layer_weight", None)
