@@ -314,7 +314,13 @@ class tree_model(nn.Module):
         set_ptr = np.zeros(T + 1, dtype=np.int32)
         np.cumsum(lens, out=set_ptr[1:])
         lw_host = self._layer_weight_host()
-        weight_host = self._iteration_weights(its, lw_host).detach()
+        lw_param = getattr(self, "layer_weight", None)
+        want_lw_grad = lw_param is not None and lw_param.requires_grad and self.opts.weights == "adaptive"
+        # the weights are computed ONCE; when `layer_weight` trains they stay attached to a host-side leaf so that
+        # d loss / d layer_weight follows from the per-iteration losses at the end of the step
+        lw_leaf = lw_host.clone().requires_grad_(True) if want_lw_grad else lw_host
+        w_attached = self._iteration_weights(its, lw_leaf)
+        weight_host = w_attached.detach()
         # ONE host->device copy for everything the step's kernels read: offsets, columns, label positions, weights
         # (as raw fp32 bits) and the union ids
         n_col = int(cat.shape[0])
@@ -348,11 +354,8 @@ class tree_model(nn.Module):
             torch.autograd.backward([t for t, _ in roots], [g for _, g in roots])
 
         loss_host = loss_t.cpu()                                                        # the step's only result read-back
-        lw_param = getattr(self, "layer_weight", None)
-        if lw_param is not None and lw_param.requires_grad and self.opts.weights == "adaptive":
-            lw_leaf = lw_host.clone().requires_grad_(True)
-            w_again = self._iteration_weights(its, lw_leaf)
-            ((loss_host / weight_host).detach() * w_again).sum().backward()            # d loss_t / d w_t = CE_t
+        if want_lw_grad:
+            ((loss_host / weight_host).detach() * w_attached).sum().backward()         # d loss_t / d w_t = CE_t
             g = lw_leaf.grad.to(lw_param.device, lw_param.dtype)
             lw_param.grad = g if lw_param.grad is None else lw_param.grad + g
         self.last_losses = loss_host.tolist()
