@@ -44,4 +44,5 @@ for _ in range(30):
 torch.cuda.synchronize()
 pr.disable()
 st = pstats.Stats(pr)
-st.sort_stats("cumulative").print_stats(45)
+st.sort_stats("cumulative").print_stats(30)
+st.sort_stats("tottime").print_stats(25)
