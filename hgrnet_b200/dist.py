@@ -10,6 +10,12 @@ be counted per shard).  No other collective is on the data path.
 ``ShardedScorer.score`` is synchronous; ``ShardedScorer.submit`` / ``collect`` pipeline batches so
 that the all-gather + merge of batch i overlap the GEMM of batch i+1 (the exchange is latency
 bound: 2*B*K*4 bytes per rank).
+
+The production arrangement is ``ShardedEvalStream`` over ``PeerExchange`` / ``PeerBank``: no collective on the data
+path -- every rank's scoring kernel stores its lists straight into the buffer of the rank that OWNS the image rows
+(peer memory over NVLink, flag-ordered), the lists are narrow and sized for the row's GLOBAL stream, and the owner
+certifies each row against the global K-th value (``hgr_score_topk_scatter_bounded`` / ``hgr_topk_merge_certified``),
+repairing the rare uncertified row from the peers' bank shards.
 """
 from __future__ import annotations
 
