@@ -197,6 +197,39 @@ def main():
                               "us_reference_torch_passes_gpu": us_ref,
                               "speedup_vs_torch_passes": us_ref / (us_fused + us_dense),
                               "note": "reference = L+1 clone/index_fill/gather/topk passes over [B,N] (without its Python BxL loop)"}
+    # ---- the same row with a REAL-SHAPED train split: 1,000 train classes + their ancestors (ImageNet-1K inside the
+    # 21K hierarchy: ~1,900 of 21,841 nodes), test bank = all 21,841 nodes.  What `evaluate.test` runs per batch with
+    # the metrics on: fused top-20 head + dense logits over the TRAIN columns + hier_metrics, against the head alone.
+    rs = np.random.RandomState(3)
+    deep = [n for n in range(N) if hier.depth[n] >= 5]
+    picked = set()
+    for n in rs.permutation(deep)[:1000].tolist():
+        picked.add(n)
+        picked.update(model.c2p[n])
+    train_nodes = [hier.nodes[n] for n in sorted(picked)]
+    m2 = tree_model(opts, train_nodes, hier.nodes, clip_model=TableEncoder(table).to(DEV), hierarchy=hier,
+                    node_tokens=node_id_tokens(N))
+    m2.update_classifier()
+    hm2 = HierMetrics(m2)
+    tgt2 = sorted(picked)[-1]
+    lab2 = torch.full((Bt,), tgt2, dtype=torch.int32, device=DEV)
+    hits2 = ops.new_hits(DEV)
+    dense2 = ops.logits_dense(xt, m2.bank_train)
+    ch2 = torch.tensor([hm2._pos_of.get(p_, -1) for p_ in list(m2.c2p[tgt2]) + [tgt2]], dtype=torch.int32, device=DEV)
+    cl2 = torch.tensor([len(m2.c2p[p_]) for p_ in list(m2.c2p[tgt2]) + [tgt2]], dtype=torch.int32, device=DEV)
+    cnt2 = torch.zeros(3, dtype=torch.int64, device=DEV)
+    us_head = graph_us(lambda i: ops.score_topk(xt, m2.bank_test, col_id=m2._test_index_i32, targets=lab2, K=20, hits=hits2))
+
+    def with_metrics(i):
+        ops.score_topk(xt, m2.bank_test, col_id=m2._test_index_i32, targets=lab2, K=20, hits=hits2)
+        ops.logits_dense(xt, m2.bank_train, out=dense2)
+        ops.hier_metrics(dense2, None, hm2._level, hm2.n_levels, hm2._first_out, ch2, cl2, cnt2)
+    us_with = graph_us(with_metrics)
+    out["hier_metrics_f1_real_split"] = {
+        "B": Bt, "test_classes": int(m2.bank_test.shape[0]), "train_columns": int(m2.bank_train.shape[0]),
+        "us_head_alone": us_head, "us_head_plus_metrics": us_with, "ratio": us_with / us_head,
+        "note": "kernels of one eval batch (one CUDA graph replay each, same bank every replay: L2-warm), metrics = dense "
+                "logits over the train columns + hgr_hier_metrics"}
     print(json.dumps(out, indent=1))
 
 
