@@ -244,6 +244,11 @@ def test_score_topk_plan_policy():
         p = ops.score_topk_plan(4096, C, 1024)
         assert p["workers"] == 64 and p["workers"] % p["row_tiles"] == 0 and p["lists_per_row"] == 4
         assert p["list_len"] == 20
+    # the same shards under the GLOBAL certificate (hgr_score_topk_scatter_bounded): the lists are sized for the row's
+    # stream of 21,841 classes -- 10 / 12 / 16 entries at N = 8 / 4 / 2, never longer than exact
+    assert [ops.global_list_len(4096, C, 1024, 20, 21841) for C in (2731, 5461, 10921)] == [10, 12, 16]
+    assert ops.global_list_len(4096, 21841, 1024, 20, 21841) == 20        # one shard = the whole stream: exact lists
+    assert ops.global_list_len(4096, 2731, 1024, 5, 21841) <= 8 and ops.global_list_len(64, 100, 64, 20, 100) <= 20
     for (B, C, D) in [(64, 1000, 1024), (1024, 10450, 512), (512, 2731, 1024), (1, 17, 64), (300, 5000, 512)]:
         p = ops.score_topk_plan(B, C, D)
         assert 1 <= p["workers"] <= 74 and p["warps_per_quarter"] == 1
