@@ -145,7 +145,86 @@ hier_metrics_kernel(const float* __restrict__ logits, int64_t ldl, const int32_t
   }
 }
 
+// Second half of the FUSED path (hgr_hier_metrics_fused): the per-level in-level maxima come from the GEMM epilogue
+// (score_pair.cu, kEpiLevel) as (order key << 32 | ~sorted bank row) words; one thread per image row decodes them, maps
+// the sorted bank row back to its position in `train_index`, and applies the same rules as the kernel above: the -1
+// fill (first_out), first position among equal values, chain matching and counting.
+__global__ void __launch_bounds__(128)
+hier_finish_kernel(unsigned long long* __restrict__ lvl_best, int64_t B, int64_t M, int n_levels,
+                   const int32_t* __restrict__ sorted_to_pos, const int32_t* __restrict__ first_out,
+                   const int32_t* __restrict__ chain, const int32_t* __restrict__ chain_level, int L,
+                   int32_t* __restrict__ lvl_idx, int32_t* __restrict__ top1, unsigned long long* counts) {
+  // one WARP per image row, lane = level (n_levels <= 32): every load of a row is issued at once
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  if (row >= B) return;
+  float v = -INFINITY;          // in-level maximum of my level (before the -1 rule)
+  int32_t j = 0x7FFFFFFF;       // its position in train_index
+  int32_t node = 0;             // winner of my level after the -1 rule
+  if (lane < n_levels) {
+    const unsigned long long w = lvl_best[row * n_levels + lane];
+    lvl_best[row * n_levels + lane] = 0ull;     // the workspace is handed back zeroed: the next call needs no memset
+    const int32_t fo = first_out[lane];
+    if (w != 0ull) {
+      const uint32_t k = static_cast<uint32_t>(w >> 32);
+      v = __uint_as_float((k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k);
+      j = sorted_to_pos[~static_cast<uint32_t>(w)];
+    }
+    node = j;
+    if (fo >= 0 && fo < M && better(-1.0f, fo, v, j)) node = fo;   // the masked array holds -1 at every out-of-level position
+    if (node == 0x7FFFFFFF) node = 0;
+    if (lvl_idx) lvl_idx[row * n_levels + lane] = node;
+  }
+  // overall top-1 over the train columns = best of the in-level maxima (value desc, position asc)
+  float bv = v;
+  int32_t bj = j;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+    const int32_t oj = __shfl_xor_sync(0xffffffffu, bj, o);
+    if (better(ov, oj, bv, bj)) {
+      bv = ov;
+      bj = oj;
+    }
+  }
+  const int32_t t1 = bj == 0x7FFFFFFF ? -1 : bj;
+  if (top1 && lane == 0) top1[row] = t1;
+  // chain matching: lane k takes chain entries k, k + 32 (L <= 64); match[k] needs the winner of level chain_level[k]
+  unsigned long long tor = 0, point = 0, edge = 0;
+  bool carry = false;           // match[k0 - 1] of the previous group of 32
+  for (int k0 = 0; k0 < L; k0 += 32) {
+    const int k = k0 + lane;
+    const int32_t p = k < L ? chain[k] : -2;
+    const int cl = k < L ? chain_level[k] : -1;
+    const int32_t win = __shfl_sync(0xffffffffu, node, cl >= 0 && cl < 32 ? cl : 0);
+    const bool m = k < L && cl >= 0 && cl < n_levels && win == p;
+    const unsigned mm = __ballot_sync(0xffffffffu, m);
+    tor += __popc(__ballot_sync(0xffffffffu, k < L && t1 == p));
+    point += __popc(mm);
+    edge += __popc(mm & ((mm << 1) | (carry ? 1u : 0u)));   // match[k] and match[k - 1]
+    carry = (mm >> 31) & 1u;
+  }
+  if (L == 1) edge = point;
+  if (lane == 0) {
+    if (tor) atomicAdd(counts + 0, tor);
+    if (point) atomicAdd(counts + 1, point);
+    if (edge) atomicAdd(counts + 2, edge);
+  }
+}
+
 }  // namespace
+
+int launch_hier_finish(unsigned long long* lvl_best, int64_t B, int64_t M, int n_levels, const int32_t* sorted_to_pos,
+                       const int32_t* first_out, const int32_t* chain, const int32_t* chain_level, int L, int32_t* lvl_idx,
+                       int32_t* top1, int64_t* counts, cudaStream_t stream) {
+  if (n_levels < 1 || n_levels > kMaxLevels)
+    return set_error(HGR_ERR_UNSUPPORTED, "hgr_hier_metrics_fused: %d levels outside [1, %d]", n_levels, kMaxLevels);
+  const int blocks = static_cast<int>((B + 3) / 4);     // one warp per image row
+  hier_finish_kernel<<<blocks, 128, 0, stream>>>(lvl_best, B, M, n_levels, sorted_to_pos, first_out, chain, chain_level, L,
+                                                 lvl_idx, top1, reinterpret_cast<unsigned long long*>(counts));
+  HGR_CHECK_LAUNCH();
+  return HGR_OK;
+}
 
 int launch_hier_metrics(const float* logits, int64_t ldl, int64_t B, const int32_t* cols, int64_t M,
                         const int8_t* level, int n_levels, const int32_t* first_out, const int32_t* chain,

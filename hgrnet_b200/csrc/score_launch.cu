@@ -284,6 +284,29 @@ int launch_score_topk_umma(const __nv_bfloat16* X, const __nv_bfloat16* bank, co
   return launch_topk_merge(m, stream);
 }
 
+// Row f1 without the dense matrix: X . bank_sorted^T on the tcgen05 loop, per-level arg-max in the epilogue.
+int launch_level_argmax_umma(const __nv_bfloat16* X, const __nv_bfloat16* bank_sorted, int64_t B, int64_t M, int64_t D,
+                             const int32_t* level_end, int n_levels, unsigned long long* lvl_best, cudaStream_t stream) {
+  if (n_levels < 1 || n_levels > kMaxHierLevels)
+    return set_error(HGR_ERR_UNSUPPORTED, "hgr_hier_metrics_fused: %d levels outside [1, %d]", n_levels, kMaxHierLevels);
+  CUtensorMap mx, mb;
+  Params p{};
+  int rc = common_setup(X, bank_sorted, B, M, D, &mx, &mb, &p);
+  if (rc != HGR_OK) return rc;
+  p.KL = 0;
+  p.scale = 1.f;
+  p.n_levels = n_levels;
+  int32_t prev = 0;
+  for (int l = 0; l < n_levels; ++l) {
+    if (level_end[l] < prev || level_end[l] > M)
+      return set_error(HGR_ERR_BAD_ARG, "hgr_hier_metrics_fused: level_end must be non-decreasing and <= M");
+    p.lvl_end[l] = prev = level_end[l];
+  }
+  if (prev != M) return set_error(HGR_ERR_BAD_ARG, "hgr_hier_metrics_fused: level_end[n_levels - 1] must be M");
+  p.lvl_best = lvl_best;   // all zero: on first use by contract, afterwards because hier_finish_kernel zeroes what it reads
+  return launch_pair_kernel(kEpiLevel, 8, mx, mb, p, stream);
+}
+
 int launch_logits_umma(const __nv_bfloat16* X, const __nv_bfloat16* bank, int64_t B, int64_t C, int64_t D,
                        float scale, float* out, int64_t ldo, cudaStream_t stream) {
   CUtensorMap mx, mb;

@@ -326,6 +326,81 @@ score_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
       tl[16] = ck.wait, tl[17] = ck.warm, tl[18] = ck.ld, tl[19] = ck.scan, tl[20] = ck.drain;
       tl[27] = prof.sel, tl[28] = prof.cmp, tl[29] = prof.crowded, tl[30] = prof.passes, tl[31] = prof.selects;
     }
+  } else if (EPI == kEpiLevel) {
+    // ===================== epilogue: per-level arg-max (row f1, main.py:163-176 without the [B, N] matrix) ==========
+    // thread = image row; the bank rows are sorted by level, so the level of a column is warp-uniform and changes a
+    // handful of times per worker: a running (max, first column) per row, flushed with ONE 64-bit atomicMax per level.
+    const int quarter = warp & 3;
+    const int row_in_tile = static_cast<int>(rank) * kTileM + quarter * 32 + lane;
+    TileWalker walk(p.sched, pair, p.C, p.rem_first);
+    SubTile t;
+    int it = 0;
+    int lvl = 0;
+    float best = -INFINITY;
+    int bcol = 0x7FFFFFFF;
+    while (walk.next(t)) {
+      const int buf = it & 1;
+      const int64_t row = static_cast<int64_t>(t.mt) * (2 * kTileM) + row_in_tile;
+      auto flush = [&]() {
+        if (row < p.B && bcol != 0x7FFFFFFF) {
+          const uint32_t b = __float_as_uint(best);
+          const uint32_t key = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+          atomicMax(p.lvl_best + row * p.n_levels + lvl,
+                    (static_cast<unsigned long long>(key) << 32) | static_cast<uint32_t>(~static_cast<uint32_t>(bcol)));
+        }
+        best = -INFINITY;
+        bcol = 0x7FFFFFFF;
+      };
+      if (t.first) {
+        lvl = 0;
+        while (lvl < p.n_levels - 1 && t.col0 >= p.lvl_end[lvl]) ++lvl;
+        best = -INFINITY;
+        bcol = 0x7FFFFFFF;
+      }
+      ptx::mbar_wait(&ctl->tmem_full[buf], (it >> 1) & 1);
+      ptx::tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + buf * kSubN;
+      for (int c0 = 0; c0 < t.nvalid; c0 += kChunk) {
+        uint32_t r[kChunk];
+        ptx::tmem_ld_x32(taddr + c0, r);
+        ptx::tmem_ld_wait();
+        const int cbeg = t.col0 + c0;
+        const int nv = t.nvalid - c0 < kChunk ? t.nvalid - c0 : kChunk;
+        if (cbeg + nv <= p.lvl_end[lvl] || lvl == p.n_levels - 1) {   // the whole chunk lies in the current level
+#pragma unroll
+          for (int j = 0; j < kChunk; ++j) {
+            const float x = __uint_as_float(r[j]);
+            if (j < nv && x > best) {
+              best = x;
+              bcol = cbeg + j;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < kChunk; ++j) {
+            if (j < nv) {
+              while (lvl < p.n_levels - 1 && cbeg + j >= p.lvl_end[lvl]) {
+                flush();
+                ++lvl;
+              }
+              const float x = __uint_as_float(r[j]);
+              if (x > best) {
+                best = x;
+                bcol = cbeg + j;
+              }
+            }
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (rank == 0) ptx::mbar_arrive(&ctl->tmem_empty[buf]);
+        else ptx::mbar_arrive_cluster(ptx::mapa_shared(ptx::smem_u32(&ctl->tmem_empty[buf]), 0));
+      }
+      if (t.last) flush();
+      ++it;
+    }
   } else {
     // ===================== epilogue (both CTAs, own 128 rows each) =====================
     const int quarter = warp & 3;
@@ -525,6 +600,7 @@ int launch_pair_kernel(int epi, int KL, const CUtensorMap& mx, const CUtensorMap
   if (epi == kEpiDense) return launch_one<kEpiDense, 8, 2>(mx, mb, p, stream);
   if (epi == kEpiNull) return launch_one<kEpiNull, 8, 1>(mx, mb, p, stream);
   if (epi == kEpiSketch) return launch_one<kEpiSketch, 8, 1>(mx, mb, p, stream);
+  if (epi == kEpiLevel) return launch_one<kEpiLevel, 8, 1>(mx, mb, p, stream);
   switch (KL) {
     case 8: return launch_one<kEpiTopkDefer, 8, 1>(mx, mb, p, stream);
     case 10: return launch_one<kEpiTopkDefer, 10, 1>(mx, mb, p, stream);

@@ -18,8 +18,9 @@ constexpr int kBBoxBytes = kBBoxRows * kBlockK * 2; // 8 KB
 constexpr int kEpiWarp0 = 2;
 constexpr int kTmemCols = 512;
 constexpr int kChunk = 32;                          // accumulator columns per tcgen05.ld
+constexpr int kMaxHierLevels = 32;                  // hierarchy levels of the per-level arg-max epilogue
 
-enum EpiMode { kEpiDense = 0, kEpiNull = 3, kEpiTopkDefer = 4, kEpiSketch = 5 };
+enum EpiMode { kEpiDense = 0, kEpiNull = 3, kEpiTopkDefer = 4, kEpiSketch = 5, kEpiLevel = 6 };
 enum Variant { kVarProd = 0, kVarExact = 2, kVarNull = 3, kVarSketch = 10 };   // impl code - HGR_IMPL_TCGEN05
 
 // SubTile / TileWalker (the walk of one worker over its chunk of the schedule) live in sched.cuh: plain integer
@@ -42,6 +43,12 @@ struct Params {
   int rem_first;       // sub-tile order inside a segment: remainder first (1) or last (0)
   int stages;          // operand ring depth of the CTA-pair kernel (set by its launcher)
   // floor-sketch epilogue (sketch_epi.cuh); stats[1] = launch epoch of the workspace, stats[2] = finished CTAs
+  // per-level arg-max epilogue (kEpiLevel, row f1: TOR / POR without the dense logits): the bank rows are sorted by
+  // hierarchy level, level l = rows [lvl_end[l-1], lvl_end[l]); lvl_best[row * n_levels + l] takes the in-level maximum
+  // of a row as (order key << 32 | ~bank row) by atomicMax (0 = no column seen; the finishing kernel zeroes what it reads)
+  int n_levels;
+  int lvl_end[kMaxHierLevels];
+  unsigned long long* lvl_best;
   uint2* sk_part;                  // [slots][B][kSkCap] (value bits, bank row)
   int32_t* sk_cnt;                 // [slots][B] entries of each list
   unsigned long long* sk_floors;   // [B][kSkSlots] (epoch << 32 | order key)

@@ -61,6 +61,13 @@ class HierMetrics:
             out = (dt != l).nonzero()
             first_out.append(int(out[0]) if out.numel() else M)
         self._first_out = torch.tensor(first_out, dtype=torch.int32, device=dev)
+        # fused path (hgr_hier_metrics_fused): the train rows of the bank sorted by level -- stable, so that inside a
+        # level the sorted order is the train_index order and "first position among equal values" is preserved
+        order = torch.sort(dt, stable=True).indices
+        self._sorted_to_pos = order.to(torch.int32).to(dev)
+        self._level_end = torch.cumsum(torch.bincount(dt, minlength=self.n_levels), 0).tolist()
+        self._bank_sorted = None      # built on first use from model.bank_train (update_classifier must have run)
+        self._bank_version = None
 
     def update(self, logits_train: torch.Tensor, target: int):
         """``logits_train`` [B, M]: cosine logits against ``model.bank_train`` (column j = node train_index[j])."""
@@ -77,6 +84,29 @@ class HierMetrics:
         self.hits_all += c[0]                                               # main.py:158-160
         self.path_all += c[2] if L == 1 else c[2] / (L - 1)                 # main.py:179-190
         self.point_all += c[1] / L                                          # main.py:191
+        self.path_all_count += B
+
+    def update_fused(self, x_norm: torch.Tensor, target: int):
+        """``update`` without the dense logits: ``x_norm`` [B, D] bf16 normalised image features; the per-level arg-max
+        over the train classes runs in the epilogue of the GEMM against the level-sorted train bank."""
+        m = self.model
+        bank = m.bank_train
+        if self._bank_sorted is None or self._bank_version is not bank:
+            self._bank_sorted = bank[self._sorted_to_pos.long()].contiguous()
+            self._bank_version = bank
+        B = x_norm.shape[0]
+        parents = list(m.c2p[target]) + [target]
+        L = len(parents)
+        dev = x_norm.device
+        chain = torch.tensor([self._pos_of.get(p, -1) for p in parents], dtype=torch.int32).to(dev, non_blocking=True)
+        chain_level = torch.tensor([len(m.c2p[p]) for p in parents], dtype=torch.int32).to(dev, non_blocking=True)
+        counts = torch.zeros(3, dtype=torch.int64, device=dev)
+        ops.hier_metrics_fused(x_norm, self._bank_sorted, self._level_end, self._sorted_to_pos, self._first_out, chain,
+                               chain_level, counts)
+        c = counts.double()
+        self.hits_all += c[0]
+        self.path_all += c[2] if L == 1 else c[2] / (L - 1)
+        self.point_all += c[1] / L
         self.path_all_count += B
 
     def ratios(self, num_sample):
@@ -106,8 +136,11 @@ def test(opts, model, device, splits=None, loader: Optional[Iterable] = None, lo
             model.score_topk(None, targets, hits=hits, feats_normalized=x)   # main.py:135-147, fused
             num_sample += len(targets)
             if hier is not None:
-                logits_train = ops.logits_dense(x, model.bank_train)         # clip_tree.py:331, train columns only
-                hier.update(logits_train, int(data["label"][0][0]))
+                if getattr(opts, "hgr_hier_dense", False):                   # cross-check path: dense [B, M] logits
+                    logits_train = ops.logits_dense(x, model.bank_train)     # clip_tree.py:331, train columns only
+                    hier.update(logits_train, int(data["label"][0][0]))
+                else:                                                        # per-level arg-max in the GEMM epilogue
+                    hier.update_fused(x, int(data["label"][0][0]))
             if i % opts.print_freq == 0:
                 out_str = _format(hits, num_sample, hier)
                 print(out_str, flush=True)

@@ -394,6 +394,40 @@ def hier_metrics(logits: torch.Tensor, cols: Optional[torch.Tensor], level: torc
                                      _ptr(top1), _ptr(counts), _stream()))
 
 
+def hier_metrics_fused(x_norm: torch.Tensor, bank_sorted: torch.Tensor, level_end, sorted_to_pos: torch.Tensor,
+                       first_out: torch.Tensor, chain: torch.Tensor, chain_level: torch.Tensor, counts: torch.Tensor,
+                       lvl_idx: Optional[torch.Tensor] = None, top1: Optional[torch.Tensor] = None) -> None:
+    """``hier_metrics`` without the dense logits: ``bank_sorted`` holds the train rows of the bank sorted by level
+    (``level_end``: host list of exclusive ends), the per-level arg-max runs in the epilogue of the tcgen05 GEMM
+    (``hgr_hier_metrics_fused``).  Positions (chain, first_out, lvl_idx, top1) are positions in ``train_index``."""
+    import ctypes
+    lib = _cabi.load()
+    x_norm = _require(x_norm, "x_norm", torch.bfloat16)
+    bank_sorted = _require(bank_sorted, "bank_sorted", torch.bfloat16)
+    sorted_to_pos = _require(sorted_to_pos, "sorted_to_pos", torch.int32)
+    first_out = _require(first_out, "first_out", torch.int32)
+    chain = _require(chain, "chain", torch.int32)
+    chain_level = _require(chain_level, "chain_level", torch.int32)
+    counts = _require(counts, "counts", torch.int64)
+    B, D = x_norm.shape
+    M = bank_sorted.shape[0]
+    n_levels = len(level_end)
+    if sorted_to_pos.numel() != M or first_out.numel() != n_levels or chain.numel() != chain_level.numel():
+        raise ValueError("hier_metrics_fused: inconsistent sizes")
+    ends = (ctypes.c_int32 * n_levels)(*[int(e) for e in level_end])
+    # its own scratch (zeroed by every call): the scoring kernel's workspace on this stream keeps header words
+    key = ("hier", x_norm.device.index, _stream())
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < B * n_levels * 8:
+        if ws is not None:
+            _retired.append(ws)
+        ws = torch.zeros(max(B * n_levels * 8, 1 << 16), dtype=torch.uint8, device=x_norm.device)
+        _workspaces[key] = ws
+    _cabi.check(lib.hgr_hier_metrics_fused(_ptr(x_norm), _ptr(bank_sorted), B, M, D, ends, n_levels, _ptr(sorted_to_pos),
+                                           _ptr(first_out), _ptr(chain), _ptr(chain_level), chain.numel(), _ptr(ws),
+                                           ws.numel(), _ptr(lvl_idx), _ptr(top1), _ptr(counts), _stream()))
+
+
 def masked_ce(logits: torch.Tensor, set_ptr: torch.Tensor, set_col: torch.Tensor, label_pos: torch.Tensor,
               weight: torch.Tensor, need_grad: bool = True):
     """Fused masked CE over T class sets (model/clip_tree.py:241-277).  Returns ``(loss [T], dlogits [B,U] | None)``."""

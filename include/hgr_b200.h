@@ -270,6 +270,27 @@ int hgr_hier_metrics(const float* logits, int64_t ldl, int64_t B, int64_t N, con
                      void* stream);
 
 /*
+ * The same metrics WITHOUT the dense matrix (SURVEY.md 8-f1 as written: "per-depth-level masked arg-max ... in the
+ * epilogue").  The train rows of the bank are handed over SORTED BY LEVEL (stable: inside a level in train_index
+ * order); X . bank_sorted^T runs on the tcgen05 main loop and the epilogue keeps, per image row, a running arg-max of
+ * the current level -- the level of a column is warp-uniform and changes n_levels - 1 times over the whole bank -- and
+ * publishes it with one 64-bit atomicMax per (row, level, worker).  A second, tiny kernel decodes the winners, maps
+ * sorted rows back to train POSITIONS (positions in train_index; chain / first_out / lvl_idx / top1 are positions too,
+ * i.e. hgr_hier_metrics with cols == NULL on the [B, M] train logits), applies the -1 rule and counts.
+ *
+ *  X            [B, D] bf16, row-normalised          bank_sorted [M, D] bf16, train rows sorted by level
+ *  level_end    [n_levels] int32 HOST array: level l = sorted rows [level_end[l-1], level_end[l]); last entry = M
+ *  sorted_to_pos [M] int32 (device): position in train_index of sorted row s
+ *  workspace    B * n_levels * 8 bytes (device): ZERO on first use; the call hands it back zeroed (no memset per batch)
+ * Same results as hgr_hier_metrics on hgr_logits_dense(X, bank_train) -- ties included.
+ */
+int hgr_hier_metrics_fused(const void* X, const void* bank_sorted, int64_t B, int64_t M, int64_t D,
+                           const int32_t* level_end, int n_levels, const int32_t* sorted_to_pos,
+                           const int32_t* first_out, const int32_t* chain, const int32_t* chain_level, int L,
+                           void* workspace, size_t workspace_bytes, int32_t* lvl_idx, int32_t* top1, int64_t* counts,
+                           void* stream);
+
+/*
  * Fused masked cross-entropy of the OM training step over T sampled class sets
  * (model/clip_tree.py:241-277 with nn.CrossEntropyLoss, :49,:275).
  *
