@@ -367,12 +367,25 @@ score_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
         const int cbeg = t.col0 + c0;
         const int nv = t.nvalid - c0 < kChunk ? t.nvalid - c0 : kChunk;
         if (cbeg + nv <= p.lvl_end[lvl] || lvl == p.n_levels - 1) {   // the whole chunk lies in the current level
+          // four interleaved running maxima (a single one is a 32-deep chain of dependent compare + select pairs),
+          // folded by (value desc, column asc) -- `>` keeps the first of equal values inside a stream
+          float b4[4] = {best, -INFINITY, -INFINITY, -INFINITY};
+          int c4[4] = {bcol, 0x7FFFFFFF, 0x7FFFFFFF, 0x7FFFFFFF};
 #pragma unroll
           for (int j = 0; j < kChunk; ++j) {
             const float x = __uint_as_float(r[j]);
-            if (j < nv && x > best) {
-              best = x;
-              bcol = cbeg + j;
+            if (j < nv && x > b4[j & 3]) {
+              b4[j & 3] = x;
+              c4[j & 3] = cbeg + j;
+            }
+          }
+          best = b4[0];
+          bcol = c4[0];
+#pragma unroll
+          for (int q = 1; q < 4; ++q) {
+            if (b4[q] > best || (b4[q] == best && c4[q] < bcol)) {
+              best = b4[q];
+              bcol = c4[q];
             }
           }
         } else {
