@@ -52,6 +52,8 @@ SIGNATURES = {
                                          c_void_p, c_void_p]),
     "hgr_sample_replay": (c_int64, [c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p, c_void_p]),
     "hgr_sample_replay_many": (c_int64, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "hgr_om_plan": (c_int64, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p,
+                              c_void_p, c_void_p, c_void_p, c_void_p]),
     "hgr_normalize_rows_bcast": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_int, c_void_p, c_void_p]),
     "hgr_peer_signal": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
     "hgr_peer_wait": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),

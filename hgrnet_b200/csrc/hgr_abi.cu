@@ -374,6 +374,70 @@ int64_t hgr_sample_replay_many(const uint32_t* words, int64_t n_words, int64_t c
   return used;
 }
 
+int64_t hgr_om_plan(const uint32_t* words, int64_t n_words, int64_t T, const int64_t* const* cand, const int64_t* n_cand,
+                    const int64_t* anchor, int64_t num_compare, int64_t n_nodes, int32_t* set_ptr, int32_t* set_col,
+                    int32_t* label_pos, int32_t* union_ids, int64_t* counts, int32_t* scratch) {
+  if (!cand || !n_cand || !anchor || !set_ptr || !set_col || !label_pos || !union_ids || !counts || !scratch || T < 0 ||
+      num_compare < 0 || n_nodes <= 0 || n_nodes >= (int64_t(1) << 31))
+    return -2;
+  int64_t max_n = 0;
+  for (int64_t t = 0; t < T; ++t) {
+    if (n_cand[t] < 0 || (n_cand[t] > 0 && !cand[t]) || anchor[t] < 0 || anchor[t] >= n_nodes) return -2;
+    max_n = n_cand[t] > max_n ? n_cand[t] : max_n;
+  }
+  int32_t* mark = scratch;                 // [n_nodes]: 0, then union position + 1
+  int32_t* pool = scratch + n_nodes;       // [max_n]
+  int32_t* pos = pool + max_n;             // [num_compare]
+  for (int64_t i = 0; i < n_nodes; ++i) mark[i] = 0;
+  int64_t setsize = 21;                    // CPython: 21, + 4 ** ceil(log(3 k, 4)) when k > 5
+  if (num_compare > 5) {
+    int64_t p4 = 1;
+    while (p4 < 3 * num_compare) p4 *= 4;
+    setsize += p4;
+  }
+  int64_t used = 0;
+  set_ptr[0] = 0;
+  for (int64_t t = 0; t < T; ++t) {
+    int32_t* out = set_col + set_ptr[t];
+    int64_t m = 0;
+    if (n_cand[t] > num_compare) {
+      if (words == nullptr) return -2;
+      const int64_t r = hgr_sample_replay(words + used, n_words - used, n_cand[t], num_compare, setsize, pos, pool);
+      if (r < 0) return r;
+      used += r;
+      for (int64_t i = 0; i < num_compare; ++i) out[i] = static_cast<int32_t>(cand[t][pos[i]]);
+      m = num_compare;
+    } else {
+      for (int64_t i = 0; i < n_cand[t]; ++i) out[i] = static_cast<int32_t>(cand[t][i]);
+      m = n_cand[t];
+    }
+    int64_t lp = -1;
+    for (int64_t i = 0; i < m && lp < 0; ++i)
+      if (out[i] == anchor[t]) lp = i;
+    if (lp < 0) {
+      out[m] = static_cast<int32_t>(anchor[t]);
+      lp = m++;
+    }
+    label_pos[t] = static_cast<int32_t>(lp);
+    for (int64_t i = 0; i < m; ++i) {
+      if (out[i] < 0 || out[i] >= n_nodes) return -2;
+      mark[out[i]] = 1;
+    }
+    set_ptr[t + 1] = set_ptr[t] + static_cast<int32_t>(m);
+  }
+  int64_t nu = 0;
+  for (int64_t i = 0; i < n_nodes; ++i)
+    if (mark[i]) {
+      union_ids[nu] = static_cast<int32_t>(i);
+      mark[i] = static_cast<int32_t>(++nu);
+    }
+  const int64_t n_col = set_ptr[T];
+  for (int64_t e = 0; e < n_col; ++e) set_col[e] = mark[set_col[e]] - 1;
+  counts[0] = n_col;
+  counts[1] = nu;
+  return used;
+}
+
 int hgr_logits_dense(const void* X, const void* bank, int64_t B, int64_t C, int64_t D, float scale, float* out,
                      int64_t ldo, int impl, void* stream) {
   HGR_CHECK_ARG(B >= 0 && C >= 0, "hgr_logits_dense: negative size");

@@ -27,7 +27,7 @@ import torch.nn as nn
 from . import ops
 from .hierarchy import Hierarchy
 from .levels import layer_weight_init, level_weights
-from .sampling import (contra_brothers, contra_random, contra_topk, contra_topk_many, hierarchical_schedule, om_schedule,
+from .sampling import (contra_brothers, contra_random, contra_topk, contra_topk_many, hierarchical_schedule, om_plan, om_schedule,
                        sample_stream)
 
 TEMPLATE_SIMPLE = "a photo of a {}."  # data/templates.py:98-100 (TEMPLATES_SIMPLE[0], hard-wired at clip_tree.py:52)
@@ -249,13 +249,10 @@ class tree_model(nn.Module):
                           slots=slots, streams=streams, banks=banks, host_io=host_io)
 
     # ------------------------------------------------------------------ training step
-    def _iterations(self, training_method, sample_strategy, target):
-        """Host-side expansion of the loop nest into T (ids, label position, weight-recipe) records."""
-        its = []
+    def _schedule(self, training_method, target):
+        """Host-side expansion of the loop nest into T (anchor, depth, chain) requests and weight recipes."""
         if training_method not in ("OM", "hierarchical"):
             raise NotImplementedError("training_method %r (the reference implements OM and hierarchical)" % training_method)
-        # every `random.sample` of the step runs on one SampleStream: same draws and same generator state afterwards
-        # as the reference's per-iteration calls (clip_tree.py:134), at a fraction of the host time
         if training_method == "OM":
             weighting = self.opts.weighting                                          # clip_tree.py:265-273
             m_in = "equal" if weighting == "out" else self.opts.weights
@@ -267,22 +264,40 @@ class tree_model(nn.Module):
             sched = hierarchical_schedule(self.c2p, target)
             requests = [(t_in, depth, parents) for (_, t_in, depth, parents, _) in sched]
             recipes = [((self.opts.weights, n_lvl, j),) for (j, _, _, _, n_lvl) in sched]      # clip_tree.py:304-305
+        return requests, recipes
+
+    def _plan_sets(self, requests, sample_strategy):
+        """The T sampled class sets of a step as ``(set_ptr, set_col, label_pos, union)`` int32 numpy arrays: offsets,
+        columns of the union, position of the anchor in every set, node ids of the union (ascending).  Every
+        `random.sample` of the step runs on one SampleStream: same draws and same generator state afterwards as the
+        reference's per-iteration calls (clip_tree.py:134); for `topk` the whole plan is one call of the library's host
+        helper (`hgr_om_plan`)."""
+        T = len(requests)
         with sample_stream(self._rng) as rng:
             if sample_strategy == "topk":
-                # all T draws of the step in one call of the library's host helper (sampling.contra_topk_many)
+                planned = om_plan(self.d2n, requests, self.opts.k, self.opts.num_compare, rng, len(self.nodes),
+                                  cache=self._contra_cache)
+                if planned is not None:
+                    return planned
                 picked = contra_topk_many(self.d2n, requests, self.opts.k, self.opts.num_compare, rng,
                                           cache=self._contra_cache)
             else:
                 picked = [self._contra_ids(sample_strategy, t, depth, parents, rng) for (t, depth, parents) in requests]
-        return [(ids, pos, rec) for (ids, pos), rec in zip(picked, recipes)]
+        # numpy path (other strategies / no library): union of the sampled classes, every set as columns of it
+        lens = np.fromiter((len(ids) for ids, _ in picked), dtype=np.int64, count=T)
+        cat = np.concatenate([np.asarray(ids, dtype=np.int64) for ids, _ in picked])
+        union, inv = np.unique(cat, return_inverse=True)
+        set_ptr = np.zeros(T + 1, dtype=np.int32)
+        np.cumsum(lens, out=set_ptr[1:])
+        return (set_ptr, inv.astype(np.int32), np.asarray([p for _, p in picked], np.int32), union.astype(np.int32))
 
     @staticmethod
-    def _iteration_weights(its, lw):
+    def _iteration_weights(recipes, lw):
         """w_t = product of the level weights the recipe of iteration t names (clip_tree.py:265-273, :304-305), for all
         T iterations with a handful of torch ops: every distinct (method, n) vector is computed once, all of them are
         concatenated, and each factor is ONE gather -- differentiable w.r.t. ``lw`` (the adaptive ``layer_weight``)."""
         offs, vecs, off = {}, [], 0
-        for _, _, rec in its:
+        for rec in recipes:
             for (method, n, _) in rec:
                 if (method, n) not in offs:
                     v = level_weights(method, n, lw).float()
@@ -290,7 +305,7 @@ class tree_model(nn.Module):
                     off += v.shape[0]
                     vecs.append(v)
         allv = torch.cat(vecs)
-        idx = np.asarray([[offs[(m, n)] + pos for (m, n, pos) in rec] for _, _, rec in its], dtype=np.int64)   # [T, factors]
+        idx = np.asarray([[offs[(m, n)] + pos for (m, n, pos) in rec] for rec in recipes], dtype=np.int64)   # [T, factors]
         w = allv[torch.from_numpy(idx[:, 0].copy())]
         for f in range(1, idx.shape[1]):
             w = w * allv[torch.from_numpy(idx[:, f].copy())]
@@ -305,27 +320,21 @@ class tree_model(nn.Module):
         target = int(targets[0].item())                                                # :228 (single-label batch)
         B = x.shape[0]
 
-        its = self._iterations(training_method, sample_strategy, target)
-        T = len(its)
-        # union of the sampled classes and every set as columns of it (numpy: ~4,400 ids per step at cfg 3)
-        lens = np.fromiter((len(ids) for ids, _, _ in its), dtype=np.int64, count=T)
-        cat = np.concatenate([np.asarray(ids, dtype=np.int64) for ids, _, _ in its])
-        union, inv = np.unique(cat, return_inverse=True)
-        set_ptr = np.zeros(T + 1, dtype=np.int32)
-        np.cumsum(lens, out=set_ptr[1:])
+        requests, recipes = self._schedule(training_method, target)
+        T = len(requests)
+        set_ptr, set_col, label_pos, union = self._plan_sets(requests, sample_strategy)
         lw_host = self._layer_weight_host()
         lw_param = getattr(self, "layer_weight", None)
         want_lw_grad = lw_param is not None and lw_param.requires_grad and self.opts.weights == "adaptive"
         # the weights are computed ONCE; when `layer_weight` trains they stay attached to a host-side leaf so that
         # d loss / d layer_weight follows from the per-iteration losses at the end of the step
         lw_leaf = lw_host.clone().requires_grad_(True) if want_lw_grad else lw_host
-        w_attached = self._iteration_weights(its, lw_leaf)
+        w_attached = self._iteration_weights(recipes, lw_leaf)
         weight_host = w_attached.detach()
         # ONE host->device copy for everything the step's kernels read: offsets, columns, label positions, weights
         # (as raw fp32 bits) and the union ids
-        n_col = int(cat.shape[0])
-        pack = np.concatenate([set_ptr, inv.astype(np.int32), np.asarray([p for _, p, _ in its], np.int32),
-                               weight_host.numpy().view(np.int32), union.astype(np.int32)])
+        n_col = int(set_col.shape[0])
+        pack = np.concatenate([set_ptr, set_col, label_pos, weight_host.numpy().view(np.int32), union])
         meta = torch.from_numpy(pack).to(self.device, non_blocking=True)
         o1, o2, o3, o4 = T + 1, T + 1 + n_col, 2 * T + 1 + n_col, 3 * T + 1 + n_col
         d_set_ptr, d_set_col, d_label = meta[:o1], meta[o1:o2], meta[o2:o3]

@@ -143,6 +143,48 @@ class SampleStream:
             off += k
         return res
 
+    def plan(self, cands, anchors, num_compare: int, n_nodes: int, ptrs=None):
+        """The host-side plan of one OM step in ONE library call (`hgr_om_plan`): every candidate array longer than
+        `num_compare` is sub-sampled exactly like `random.sample`, anchors are appended where the draw missed them, the
+        union of the sets is formed in ascending node id and the sets are rewritten as positions in it.  Returns
+        ``(set_ptr [T+1], set_col [n_col], label_pos [T], union [n_union])`` int32 arrays, or None without the library."""
+        import numpy as np
+        lib = _host_lib()
+        if lib is None:
+            return None
+        T = len(cands)
+        ns = np.fromiter((c.shape[0] for c in cands), dtype=np.int64, count=T)
+        if ptrs is None:
+            ptrs = [c.__array_interface__["data"][0] for c in cands]
+        ptrs = np.asarray(ptrs, dtype=np.uint64)
+        anc = np.asarray(anchors, dtype=np.int64)
+        cap = T * (num_compare + 1) + 1
+        set_ptr = np.empty(T + 1, dtype=np.int32)
+        set_col = np.empty(cap, dtype=np.int32)
+        label = np.empty(max(T, 1), dtype=np.int32)
+        union = np.empty(cap, dtype=np.int32)
+        counts = np.zeros(2, dtype=np.int64)
+        need = n_nodes + (int(ns.max()) if T else 0) + num_compare + 8
+        if self._scratch is None or self._scratch.shape[0] < need:
+            self._scratch = np.empty(max(need, 4096), dtype=np.int32)
+            self._scratch_ptr = self._scratch.__array_interface__["data"][0]
+        draws = int((ns > num_compare).sum())
+        m = int(1.6 * draws * num_compare) + 32 * draws + 8
+        addr = lambda a: a.__array_interface__["data"][0]
+        while True:
+            self.ensure(m)
+            avail = self.words.shape[0] - self.pos
+            used = lib.hgr_om_plan(self._words_ptr + 4 * self.pos, avail, T, addr(ptrs), addr(ns), addr(anc), num_compare,
+                                   n_nodes, addr(set_ptr), addr(set_col), addr(label), addr(union), addr(counts),
+                                   self._scratch_ptr)
+            if used >= 0:
+                self.pos += int(used)
+                break
+            if used != -1:
+                raise ValueError("hgr_om_plan rejected its arguments")
+            m = 2 * max(m, avail)
+        return set_ptr, set_col[:int(counts[0])], label[:T], union[:int(counts[1])]
+
     def sample_array(self, population, k: int):
         """`random.sample(population, k)` for a numpy `population`, as a numpy array (same elements, same order)."""
         return population[self.positions(population.shape[0], k)]
@@ -356,6 +398,26 @@ def contra_topk_many(d2n, requests, k: int, num_compare: int, rng, cache: Option
             pos = int(hit[0])
         out.append((ids, pos))
     return out
+
+
+def om_plan(d2n, requests, k: int, num_compare: int, rng, n_nodes: int, cache: Optional[dict] = None):
+    """`contra_topk_many` + the union / inverse of `train_batch` in one call of the library's host helper
+    (`SampleStream.plan`); None when `rng` is not a SampleStream over the library (the caller then takes the numpy path)."""
+    if not hasattr(rng, "plan"):
+        return None
+    cands = [contra_topk_candidates(d2n, depth, parents, k, cache, as_array=True) for (_, depth, parents) in requests]
+    ptrs = None
+    if cache is not None:      # the candidate arrays are cached objects: so are their addresses (`__array_interface__` is slow)
+        known = cache.setdefault("_ptrs", {})
+        if len(known) > 4 * _LIST_CACHE_ENTRIES:
+            known.clear()
+        ptrs = []
+        for c in cands:
+            e = known.get(id(c))
+            if e is None or e[0] is not c:
+                e = known[id(c)] = (c, c.__array_interface__["data"][0])
+            ptrs.append(e[1])
+    return rng.plan(cands, [t for (t, _, _) in requests], num_compare, n_nodes, ptrs)
 
 
 def contra_random(train_ids: Sequence[int], target: int, num_compare: int, rng=_random) -> Tuple[List[int], int]:

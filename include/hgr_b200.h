@@ -237,6 +237,17 @@ int64_t hgr_sample_replay(const uint32_t* words, int64_t n_words, int64_t n, int
  * out_pos[k[0] + ... + k[c-1] ...]; scratch holds max(n) int32; setsize is computed here.  Same return values. */
 int64_t hgr_sample_replay_many(const uint32_t* words, int64_t n_words, int64_t count, const int64_t* n, const int64_t* k,
                                int32_t* out_pos, int32_t* scratch);
+/* The whole host-side plan of one OM training step (model/clip_tree.py:116-141 per iteration, :241-262 over the T
+ * iterations) in one call: for iteration t the candidate list cand[t] (n_cand[t] node ids, already without the anchor
+ * chain) is sub-sampled to num_compare ids exactly like `random.sample` would (only when it is longer), the anchor is
+ * appended when the draw missed it (label_pos[t] = its position), the union of all sets is formed in ascending node id
+ * (what numpy.unique gives) and every set is rewritten as positions in that union.
+ *   set_ptr [T + 1], set_col [>= T * (num_compare + 1)], label_pos [T], union_ids [>= T * (num_compare + 1)] int32;
+ *   counts[0] = entries of set_col, counts[1] = size of the union; scratch: n_nodes + max(n_cand) + num_compare int32.
+ * Returns the generator words consumed (>= 0), -1 when the window is too short, -2 on bad arguments. */
+int64_t hgr_om_plan(const uint32_t* words, int64_t n_words, int64_t T, const int64_t* const* cand, const int64_t* n_cand,
+                    const int64_t* anchor, int64_t num_compare, int64_t n_nodes, int32_t* set_ptr, int32_t* set_col,
+                    int32_t* label_pos, int32_t* union_ids, int64_t* counts, int32_t* scratch);
 
 /*
  * Dense logits, out[b, c] = scale * <X[b], bank[c]>, fp32, leading dimension ldo >= C.

@@ -485,3 +485,36 @@ def test_sample_replay_helper_and_batched_draws_match_random_sample():
         with sampling.sample_stream(random) as st:        # warm cache: same draws
             again = sampling.contra_topk_many(h.d2n, reqs, 2, 64, st, cache=cache)
         assert [(i.tolist(), p_) for i, p_ in again] == [(i.tolist(), p_) for i, p_ in many]
+
+
+def test_om_plan_helper_matches_the_numpy_path():
+    """`hgr_om_plan` (include/hgr_b200.h): the whole host-side plan of an OM step -- draws (clip_tree.py:134), anchor
+    append (:135-141), union of the sets and the sets as columns of it (what train_batch fed its kernels from numpy) -- in
+    one library call.  Must equal the call-by-call path: same sets in the same order, same union, same label positions,
+    same generator state afterwards."""
+    import numpy as np
+    from hgrnet_b200 import sampling
+    from hgrnet_b200.hierarchy import synthetic_hierarchy
+    assert sampling._fast_sample_ok() and sampling._host_lib() is not None
+    h = synthetic_hierarchy((6, 40, 300, 1500, 2600, 900), seed=4)
+    n_nodes = len(h)
+    for (target, k, num_compare, out_ratio, in_ratio) in ((n_nodes - 1, 2, 64, 0.5, 0.75), (n_nodes - 700, 1, 256, 0.25, 0.5),
+                                                           (50, 1, 16, 1.0, 1.0), (3, 3, 8, 0.5, 0.5), (n_nodes - 1, 1, 100000, 0.5, 0.5)):
+        reqs = [(p_out, depth, parents_in)
+                for (_, _, p_out, depth, parents_in, _, _) in sampling.om_schedule(h.c2p, target, out_ratio, in_ratio)]
+        random.seed(target + k)
+        with sampling.sample_stream(random) as st:
+            picked = sampling.contra_topk_many(h.d2n, reqs, k, num_compare, st, cache={})
+        s_ref = random.getstate()
+        cat = np.concatenate([ids for ids, _ in picked])
+        union, inv = np.unique(cat, return_inverse=True)
+        ptr = np.concatenate([[0], np.cumsum([len(ids) for ids, _ in picked])])
+        random.seed(target + k)
+        with sampling.sample_stream(random) as st:
+            set_ptr, set_col, label_pos, uni = sampling.om_plan(h.d2n, reqs, k, num_compare, st, n_nodes, cache={})
+        assert random.getstate() == s_ref
+        assert set_ptr.tolist() == ptr.tolist() and uni.tolist() == union.tolist()
+        assert set_col.tolist() == inv.tolist() and label_pos.tolist() == [p for _, p in picked]
+        assert all(int(uni[set_col[set_ptr[t] + label_pos[t]]]) == reqs[t][0] for t in range(len(reqs)))
+    # a pass-through generator (no SampleStream) has no plan: the caller takes the numpy path
+    assert sampling.om_plan(h.d2n, reqs, 1, 8, random, n_nodes) is None
