@@ -26,7 +26,7 @@ import torch.nn as nn
 
 from . import ops
 from .hierarchy import Hierarchy
-from .levels import layer_weight_init, level_weights
+from .levels import iteration_weights_grad_np, iteration_weights_np, layer_weight_init, level_weights
 from .sampling import (contra_brothers, contra_random, contra_topk, contra_topk_many, hierarchical_schedule, om_plan, om_schedule,
                        sample_stream)
 
@@ -291,26 +291,6 @@ class tree_model(nn.Module):
         np.cumsum(lens, out=set_ptr[1:])
         return (set_ptr, inv.astype(np.int32), np.asarray([p for _, p in picked], np.int32), union.astype(np.int32))
 
-    @staticmethod
-    def _iteration_weights(recipes, lw):
-        """w_t = product of the level weights the recipe of iteration t names (clip_tree.py:265-273, :304-305), for all
-        T iterations with a handful of torch ops: every distinct (method, n) vector is computed once, all of them are
-        concatenated, and each factor is ONE gather -- differentiable w.r.t. ``lw`` (the adaptive ``layer_weight``)."""
-        offs, vecs, off = {}, [], 0
-        for rec in recipes:
-            for (method, n, _) in rec:
-                if (method, n) not in offs:
-                    v = level_weights(method, n, lw).float()
-                    offs[(method, n)] = off
-                    off += v.shape[0]
-                    vecs.append(v)
-        allv = torch.cat(vecs)
-        idx = np.asarray([[offs[(m, n)] + pos for (m, n, pos) in rec] for rec in recipes], dtype=np.int64)   # [T, factors]
-        w = allv[torch.from_numpy(idx[:, 0].copy())]
-        for f in range(1, idx.shape[1]):
-            w = w * allv[torch.from_numpy(idx[:, f].copy())]
-        return w
-
     def train_batch(self, inputs, targets, training_method, sample_strategy):
         """clip_tree.py:222-316.  Returns the python-float loss sum; gradients are accumulated on the
         encoder parameters, ``logit_scale`` and ``layer_weight`` as a side effect (no zero_grad, as the
@@ -326,15 +306,14 @@ class tree_model(nn.Module):
         lw_host = self._layer_weight_host()
         lw_param = getattr(self, "layer_weight", None)
         want_lw_grad = lw_param is not None and lw_param.requires_grad and self.opts.weights == "adaptive"
-        # the weights are computed ONCE; when `layer_weight` trains they stay attached to a host-side leaf so that
-        # d loss / d layer_weight follows from the per-iteration losses at the end of the step
-        lw_leaf = lw_host.clone().requires_grad_(True) if want_lw_grad else lw_host
-        w_attached = self._iteration_weights(recipes, lw_leaf)
-        weight_host = w_attached.detach()
+        # w_t = product of the level weights the recipe of iteration t names (clip_tree.py:265-273, :304-305), in numpy
+        # (levels.iteration_weights_np); d loss / d layer_weight follows analytically at the end of the step
+        lw_np = None if lw_host is None else lw_host.numpy()
+        weight_np, w_ctx = iteration_weights_np(recipes, lw_np)
         # ONE host->device copy for everything the step's kernels read: offsets, columns, label positions, weights
         # (as raw fp32 bits) and the union ids
         n_col = int(set_col.shape[0])
-        pack = np.concatenate([set_ptr, set_col, label_pos, weight_host.numpy().view(np.int32), union])
+        pack = np.concatenate([set_ptr, set_col, label_pos, weight_np.view(np.int32), union])
         meta = torch.from_numpy(pack).to(self.device, non_blocking=True)
         o1, o2, o3, o4 = T + 1, T + 1 + n_col, 2 * T + 1 + n_col, 3 * T + 1 + n_col
         d_set_ptr, d_set_col, d_label = meta[:o1], meta[o1:o2], meta[o2:o3]
@@ -364,8 +343,8 @@ class tree_model(nn.Module):
 
         loss_host = loss_t.cpu()                                                        # the step's only result read-back
         if want_lw_grad:
-            ((loss_host / weight_host).detach() * w_attached).sum().backward()         # d loss_t / d w_t = CE_t
-            g = lw_leaf.grad.to(lw_param.device, lw_param.dtype)
+            ce = loss_host.numpy() / weight_np                                          # d loss_t / d w_t = CE_t
+            g = torch.from_numpy(iteration_weights_grad_np(w_ctx, ce, lw_np)).to(lw_param.device, lw_param.dtype)
             lw_param.grad = g if lw_param.grad is None else lw_param.grad + g
         self.last_losses = loss_host.tolist()
         return sum(self.last_losses)                                                    # :279

@@ -518,3 +518,50 @@ def test_om_plan_helper_matches_the_numpy_path():
         assert all(int(uni[set_col[set_ptr[t] + label_pos[t]]]) == reqs[t][0] for t in range(len(reqs)))
     # a pass-through generator (no SampleStream) has no plan: the caller takes the numpy path
     assert sampling.om_plan(h.d2n, reqs, 1, 8, random, n_nodes) is None
+
+
+def test_iteration_weights_numpy_twin_matches_torch_and_autograd():
+    """levels.iteration_weights_np / iteration_weights_grad_np (the per-iteration loss weights of the OM step and
+    d loss / d layer_weight, clip_tree.py:198-219,265-273) against `level_weights` in torch: values within float32
+    rounding, the analytic gradient (softmax Jacobian of softmax(100 ** lw)) against float64 autograd."""
+    import numpy as np
+    import torch.nn.functional as F
+    from hgrnet_b200.levels import METHODS, iteration_weights_grad_np, iteration_weights_np, level_weights, level_weights_np
+
+    def vec64(m, n, lw):
+        if m == "adaptive":
+            return F.softmax(100 ** lw[:n], dim=0)
+        return level_weights(m, n, None).double()
+
+    rs = np.random.RandomState(0)
+    for m in METHODS:
+        for n in (1, 2, 7, 13):
+            lw32 = torch.tensor(rs.rand(13).astype(np.float32))
+            assert np.allclose(level_weights_np(m, n, lw32.numpy()), level_weights(m, n, lw32).float().numpy(), rtol=2e-5, atol=0)
+    for trial in range(120):
+        base = (rs.rand(13) * 0.9 + 0.01).astype(np.float32)
+        lw = torch.tensor(base.astype(np.float64), requires_grad=True)
+        recs = []
+        for t in range(rs.randint(1, 25)):
+            rec = []
+            for f in range(rs.randint(1, 3)):
+                m = METHODS[rs.randint(0, len(METHODS))] if rs.rand() < 0.4 else "adaptive"
+                n = rs.randint(1, 14)
+                rec.append((m, n, rs.randint(0, n)))
+            recs.append(tuple(rec))
+        ws = []
+        for rec in recs:
+            w = None
+            for (m, n, p_) in rec:
+                f = vec64(m, n, lw)[p_]
+                w = f if w is None else w * f
+            ws.append(w)
+        wt = torch.stack(ws)
+        c = rs.randn(len(recs)).astype(np.float32)
+        if wt.requires_grad:
+            (wt * torch.tensor(c.astype(np.float64))).sum().backward()
+        g64 = lw.grad.numpy() if lw.grad is not None else np.zeros(13)
+        w_np, ctx = iteration_weights_np(recs, base)
+        assert np.allclose(w_np, wt.detach().numpy(), rtol=5e-5, atol=1e-30)       # (float32 denormals aside)
+        g_np = iteration_weights_grad_np(ctx, c, base)
+        assert np.allclose(g_np, g64, rtol=1e-4, atol=1e-6 * float(np.abs(c).sum())), (g_np, g64)
