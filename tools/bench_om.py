@@ -143,7 +143,7 @@ def main():
         ops.om_backward(dl_, lg_, xn_, xnorm_, tn_, tnorm_, 14.2857)
     us_head = graph_us(head_device)
     out["om_step_cfg3"]["us_head_kernels_per_step"] = us_head
-    out["om_step_cfg3"]["note_breakdown"] = ("of the wall clock per step ~0.35 ms is the host-side sampling (one call of the library host helper) / set building, "
+    out["om_step_cfg3"]["note_breakdown"] = ("of the wall clock per step ~0.2 ms is the host-side plan of the step (one call of the library host helper), "
                                              "the head's own kernels take us_head_kernels_per_step; the rest is the "
                                              "stand-in encoder's autograd (a dense 21,841 x 1024 table gradient per step) "
                                              "and three host synchronisations (label, logit scale, losses)")
