@@ -91,9 +91,10 @@ class HierMetrics:
         over the train classes runs in the epilogue of the GEMM against the level-sorted train bank."""
         m = self.model
         bank = m.bank_train
-        if self._bank_sorted is None or self._bank_version is not bank:
+        stamp = (bank.data_ptr(), bank._version)       # a refreshed bank (new tensor or in-place update) is re-sorted
+        if self._bank_sorted is None or self._bank_version != stamp:
             self._bank_sorted = bank[self._sorted_to_pos.long()].contiguous()
-            self._bank_version = bank
+            self._bank_version = stamp
         B = x_norm.shape[0]
         parents = list(m.c2p[target]) + [target]
         L = len(parents)
